@@ -1,0 +1,155 @@
+/*
+ * rfi_b200.h -- C ABI of librfi_b200.so, the B200 (sm_100a) implementation of the
+ * rfi_toolbox preprocessing / evaluation hot path.
+ *
+ * The reference (preshanth/rfi_toolbox 0.2.0) is pure Python and has no FFI layer of
+ * its own; each entry point below names the reference function
+ * (file:line under rfi_toolbox/) whose arithmetic it replaces.  The Python host layer in
+ * rfi_toolbox_b200/ binds these with ctypes and mirrors the reference's public API.
+ *
+ * Conventions
+ *   - plain C: device pointers, sizes, a cudaStream_t passed as void*; no torch types;
+ *   - no allocation inside (one exception: none), no host synchronisation, re-entrant per stream;
+ *   - every call returns 0 on success or a negative RFI_E_* code; rfi_last_error_string()
+ *     gives the text for the calling thread's last failure;
+ *   - all device buffers are owned by the caller.
+ */
+#ifndef RFI_B200_H
+#define RFI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RFI_B200_ABI_VERSION 1
+
+/* status codes */
+#define RFI_OK 0
+#define RFI_E_INVALID (-1)     /* bad argument / unsupported combination */
+#define RFI_E_UNSUPPORTED (-2) /* legal in the reference, not built on this path yet */
+#define RFI_E_CUDA (-3)        /* CUDA runtime error (text in rfi_last_error_string) */
+
+/* element types of the visibility cube (preprocessor.py:175-196 accepts any of them) */
+#define RFI_F32 0
+#define RFI_F64 1
+#define RFI_C64 2
+#define RFI_C128 3
+
+/* stretch (preprocessor.py:672-706) */
+#define RFI_STRETCH_NONE 0
+#define RFI_STRETCH_SQRT 1
+#define RFI_STRETCH_LOG10 2
+
+/* where the labels come from (preprocessor.py:315-334) */
+#define RFI_FLAGS_CUSTOM 0    /* caller's flags, rotated + tiled like the data */
+#define RFI_FLAGS_MAD 1       /* median +- sigma * MAD of the processed patch */
+#define RFI_FLAGS_INFERENCE 2 /* all-zero labels */
+
+/* Plan of one create_dataset call over a cube (B, Npol, C, T), C-order.
+ * Fast path: C and T multiples of P (no padding), P = 128. */
+typedef struct rfi_plan {
+    int32_t dtype;       /* RFI_F32 .. RFI_C128 */
+    int32_t magnitude;   /* complex input only: 1 = take |z| on load and run the real branch
+                            (reference fed np.abs(data), ms_loader.py:556-561);
+                            0 = complex branch (preprocessor.py:285-292, 562-606) */
+    int64_t n_waterfalls; /* B * Npol */
+    int64_t channels;    /* C (rows of a waterfall)  */
+    int64_t times;       /* T (columns of a waterfall) */
+    int32_t patch;       /* P */
+    int32_t rotations;   /* effective views per waterfall: 1, 2 or 4 (preprocessor.py:413-446) */
+    int32_t stretch;     /* RFI_STRETCH_* */
+    int32_t norm_before; /* preprocessor.py:295-297 */
+    int32_t norm_after;  /* preprocessor.py:309-311 */
+    int32_t flag_mode;   /* RFI_FLAGS_* */
+    double sigma;        /* flag_sigma, applied in the data's precision */
+} rfi_plan_t;
+
+/* Per ORIGINAL tile statistics produced by rfi_tile_stats and consumed by
+ * rfi_write_patches (they are rotation invariant, SURVEY.md section 8 identity (i)).
+ * Stored as doubles; for float32/complex64 input each holds an exactly representable
+ * float32 value. */
+typedef struct rfi_tile_stat {
+    double median_before; /* nanmedian of the raw tile           (preprocessor.py:663) */
+    double inf_fill;      /* MAD of the finite stretched values  (preprocessor.py:697-702) */
+    double median_after;  /* nanmedian after the stretch         (preprocessor.py:311) */
+    double centre;        /* nanmedian of the processed tile     (preprocessor.py:737) */
+    double mad;           /* MAD of the processed tile           (preprocessor.py:736) */
+    double thr_lo;        /* centre - mad * sigma                (preprocessor.py:740) */
+    double thr_hi;        /* centre + mad * sigma                (preprocessor.py:739) */
+    int32_t n_valid;      /* non-NaN samples of the raw tile */
+    int32_t n_inf;        /* +-inf samples after the stretch */
+    int32_t n_flagged;    /* samples flagged (MAD mode) or non-zero custom flags */
+    int32_t reserved;
+} rfi_tile_stat_t;
+
+/* Number of original tiles / output patches of a plan (host arithmetic only). */
+int64_t rfi_plan_num_tiles(const rfi_plan_t* plan);
+int64_t rfi_plan_num_patches(const rfi_plan_t* plan); /* rotations * tiles */
+
+/* Phase 1 -- replaces _normalize / _apply_stretch statistics / _generate_mad_flags
+ * (preprocessor.py:646-745) and the `any()` of _remove_blank_patches (:749).
+ *   data   device, cube in the plan's dtype
+ *   flags  device, uint8/bool cube of the same shape (RFI_FLAGS_CUSTOM) or NULL
+ *   stats  device, rfi_plan_num_tiles() entries, written
+ * One CTA per original tile; tile resident in registers, order statistics by
+ * register-resident MSB-first binary radix select. */
+int rfi_tile_stats(const rfi_plan_t* plan, const void* data, const uint8_t* flags,
+                   rfi_tile_stat_t* stats, void* stream);
+
+/* Phase 2 -- replaces _apply_rotations, patchify, _normalize, _apply_stretch, flag
+ * application, _extract_channels_from_{real,complex}, ImageNet normalisation and the
+ * compaction + shuffle gathers (preprocessor.py:22-42, 413-446, 562-783).
+ *   dest_slot device int64[rfi_plan_num_patches()], canonical patch index -> output slot,
+ *             -1 = dropped (blank / beyond num_patches)
+ *   images    device float32 (N, P, P, 3), labels device uint8 (N, P, P) */
+int rfi_write_patches(const rfi_plan_t* plan, const void* data, const uint8_t* flags,
+                      const rfi_tile_stat_t* stats, const int64_t* dest_slot,
+                      float* images, uint8_t* labels, void* stream);
+
+/* Confusion counts -- replaces the boolean reductions of evaluation/metrics.py:36-40,
+ * 63-68, 95-99, 142-147.  `elem_*` is the element size in bytes (1, 2, 4 or 8) and
+ * `is_float_*` selects float semantics (x != 0, NaN counts as True) over integer ones.
+ *   counts device uint64[3] = {TP, FP, FN}, ACCUMULATED into (caller zeroes). */
+int rfi_confusion_counts(const void* pred, int elem_pred, int is_float_pred,
+                         const void* truth, int elem_true, int is_float_true,
+                         int64_t n, unsigned long long* counts, void* stream);
+
+/* Same, one triple per consecutive segment of `seg` elements (per-pair sweep,
+ * BASELINE config 4).  counts device uint64[n_seg][3], written. */
+int rfi_confusion_counts_segmented(const void* pred, int elem_pred, int is_float_pred,
+                                   const void* truth, int elem_true, int is_float_true,
+                                   int64_t n_seg, int64_t seg, unsigned long long* counts,
+                                   void* stream);
+
+/* Robust statistics -- replaces compute_statistics (evaluation/statistics.py:16-56): stats
+ * of |data| over the samples whose flag byte is zero (all samples when flags is NULL),
+ * computed in the data's own precision T and widened to double on output. */
+typedef struct rfi_stats {
+    double mean;       /* float64-accumulated sum / count, rounded to T  (statistics.py:50) */
+    double median;     /* mean of the two middle order statistics in T    (statistics.py:51) */
+    double std;        /* population std (ddof 0), two-pass               (statistics.py:52) */
+    double mad;        /* median(|x - median|)                            (statistics.py:10-13) */
+    int64_t count;     /* unflagged samples                               (statistics.py:54) */
+    int64_t n_flagged; /* non-zero flag bytes                             (statistics.py:34) */
+    int64_t n_nan;     /* NaNs among the unflagged samples; if > 0 median and mad are NaN */
+} rfi_stats_t;
+
+size_t rfi_statistics_workspace_bytes(void);
+
+/*   data      device, n samples of `dtype` (RFI_F32 .. RFI_C128)
+ *   flags     device uint8[n] or NULL
+ *   out       device rfi_stats_t, written (stream-ordered)
+ *   workspace device, rfi_statistics_workspace_bytes() bytes */
+int rfi_statistics(const void* data, int dtype, const uint8_t* flags, int64_t n,
+                   rfi_stats_t* out, void* workspace, void* stream);
+
+const char* rfi_last_error_string(void);
+int rfi_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RFI_B200_H */

@@ -1,0 +1,100 @@
+"""ctypes binding of librfi_b200.so (C ABI declared in include/rfi_b200.h).
+
+There is no CPU fallback: if the library cannot be loaded, or no CUDA device is present,
+every entry point raises.  `rfi_toolbox_b200.csrc.build.build()` (run by
+`__graft_entry__.build()`) produces the library in-tree with nvcc for sm_100a.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "_lib" / "librfi_b200.so"
+
+RFI_F32, RFI_F64, RFI_C64, RFI_C128 = 0, 1, 2, 3
+RFI_STRETCH_NONE, RFI_STRETCH_SQRT, RFI_STRETCH_LOG10 = 0, 1, 2
+RFI_FLAGS_CUSTOM, RFI_FLAGS_MAD, RFI_FLAGS_INFERENCE = 0, 1, 2
+RFI_E_INVALID, RFI_E_UNSUPPORTED, RFI_E_CUDA = -1, -2, -3
+ABI_VERSION = 1
+
+
+class RfiPlan(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32), ("magnitude", C.c_int32),
+        ("n_waterfalls", C.c_int64), ("channels", C.c_int64), ("times", C.c_int64),
+        ("patch", C.c_int32), ("rotations", C.c_int32), ("stretch", C.c_int32),
+        ("norm_before", C.c_int32), ("norm_after", C.c_int32), ("flag_mode", C.c_int32),
+        ("sigma", C.c_double),
+    ]
+
+
+class RfiTileStat(C.Structure):
+    _fields_ = [
+        ("median_before", C.c_double), ("inf_fill", C.c_double), ("median_after", C.c_double),
+        ("centre", C.c_double), ("mad", C.c_double), ("thr_lo", C.c_double), ("thr_hi", C.c_double),
+        ("n_valid", C.c_int32), ("n_inf", C.c_int32), ("n_flagged", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class RfiStats(C.Structure):
+    _fields_ = [
+        ("mean", C.c_double), ("median", C.c_double), ("std", C.c_double), ("mad", C.c_double),
+        ("count", C.c_int64), ("n_flagged", C.c_int64), ("n_nan", C.c_int64),
+    ]
+
+
+TILE_STAT_BYTES = C.sizeof(RfiTileStat)
+assert TILE_STAT_BYTES == 72
+
+# every symbol include/rfi_b200.h declares: name -> (restype, argtypes)
+_VP, _I, _I64 = C.c_void_p, C.c_int, C.c_int64
+SYMBOLS = {
+    "rfi_plan_num_tiles": (_I64, [C.POINTER(RfiPlan)]),
+    "rfi_plan_num_patches": (_I64, [C.POINTER(RfiPlan)]),
+    "rfi_tile_stats": (_I, [C.POINTER(RfiPlan), _VP, _VP, _VP, _VP]),
+    "rfi_write_patches": (_I, [C.POINTER(RfiPlan), _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "rfi_confusion_counts": (_I, [_VP, _I, _I, _VP, _I, _I, _I64, _VP, _VP]),
+    "rfi_confusion_counts_segmented": (_I, [_VP, _I, _I, _VP, _I, _I, _I64, _I64, _VP, _VP]),
+    "rfi_statistics_workspace_bytes": (C.c_size_t, []),
+    "rfi_statistics": (_I, [_VP, _I, _VP, _I64, _VP, _VP, _VP]),
+    "rfi_last_error_string": (C.c_char_p, []),
+    "rfi_abi_version": (_I, []),
+}
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load (once) and return the ctypes handle.  Raises if the library is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise NativeError(
+            f"{LIB_PATH} not found: build it with `python -m rfi_toolbox_b200.csrc.build` "
+            "(nvcc, sm_100a).  rfi_toolbox_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError here = header / library mismatch
+        fn.restype, fn.argtypes = res, args
+    if lib.rfi_abi_version() != ABI_VERSION:
+        raise NativeError(f"ABI mismatch: library {lib.rfi_abi_version()} != binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc == 0:
+        return
+    msg = load().rfi_last_error_string().decode("utf-8", "replace")
+    if rc == RFI_E_UNSUPPORTED:
+        raise NotImplementedError(f"{what}: {msg}")
+    if rc == RFI_E_INVALID:
+        raise ValueError(f"{what}: {msg}")
+    raise NativeError(f"{what}: {msg}")

@@ -1,0 +1,316 @@
+// rfi_common.cuh -- shared device helpers for the sm_100a hot-path kernels.
+//
+// Everything numeric here is written so that the float32 / float64 results equal what
+// NumPy computes for the same op on the host: one IEEE operation per source-level
+// operation, no FMA contraction (the build passes -fmad=false; the only fused op is the
+// explicit fma inside cabs_np, which NumPy's SIMD complex-abs loop also fuses).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/rfi_b200.h"
+
+#define RFI_DEVINL __device__ __forceinline__
+
+namespace rfi {
+
+// ----------------------------------------------------------------------------------------
+// error plumbing (host)
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+#define RFI_CUDA_TRY(expr)                                   \
+    do {                                                     \
+        cudaError_t _e = (expr);                             \
+        if (_e != cudaSuccess) return rfi::cuda_fail(_e, #expr); \
+    } while (0)
+
+// ----------------------------------------------------------------------------------------
+// scalar traits: T in {float, double}; K = order-preserving unsigned key type
+template <typename T> struct Scalar;
+template <> struct Scalar<float> {
+    using key_t = uint32_t;
+    static constexpr int kBits = 32;
+    RFI_DEVINL static uint32_t bits(float x) { return __float_as_uint(x); }
+    RFI_DEVINL static float from_bits(uint32_t b) { return __uint_as_float(b); }
+    RFI_DEVINL static float nan() { return __uint_as_float(0x7fffffffu); }
+    RFI_DEVINL static float inf() { return __uint_as_float(0x7f800000u); }
+    RFI_DEVINL static float sqrt_rn(float x) { return __fsqrt_rn(x); }
+    RFI_DEVINL static float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+    RFI_DEVINL static float fmin_nan(float a, float b) { return fminf(a, b); }
+    RFI_DEVINL static float fmax_nan(float a, float b) { return fmaxf(a, b); }
+    // log10 of a float32, correctly rounded in practice (fp64 evaluation, one final rounding).
+    // NumPy's float32 log10 is SVML on AVX-512 hosts (<= 3 ulp off); see DESIGN.md "numerics".
+    RFI_DEVINL static float log10_(float x) { return (float)::log10((double)x); }
+    RFI_DEVINL static float atan2_(float y, float x) { return (float)::atan2((double)y, (double)x); }
+};
+template <> struct Scalar<double> {
+    using key_t = unsigned long long;
+    static constexpr int kBits = 64;
+    RFI_DEVINL static unsigned long long bits(double x) { return (unsigned long long)__double_as_longlong(x); }
+    RFI_DEVINL static double from_bits(unsigned long long b) { return __longlong_as_double((long long)b); }
+    RFI_DEVINL static double nan() { return __longlong_as_double(0x7fffffffffffffffLL); }
+    RFI_DEVINL static double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+    RFI_DEVINL static double sqrt_rn(double x) { return __dsqrt_rn(x); }
+    RFI_DEVINL static double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+    RFI_DEVINL static double fmin_nan(double a, double b) { return ::fmin(a, b); }
+    RFI_DEVINL static double fmax_nan(double a, double b) { return ::fmax(a, b); }
+    RFI_DEVINL static double log10_(double x) { return ::log10(x); }
+    RFI_DEVINL static double atan2_(double y, double x) { return ::atan2(y, x); }
+};
+
+RFI_DEVINL float fabs_(float x) { return fabsf(x); }
+RFI_DEVINL double fabs_(double x) { return ::fabs(x); }
+template <typename T> RFI_DEVINL bool is_nan(T x) { return x != x; }
+template <typename T> RFI_DEVINL bool is_inf(T x) { return fabs_(x) == Scalar<T>::inf(); }
+
+// Order-preserving key: ascending float order == ascending unsigned order; every NaN maps
+// to the all-ones key, which doubles as the "excluded" marker (nanmedian drops NaNs).
+template <typename T>
+RFI_DEVINL typename Scalar<T>::key_t to_key(T x) {
+    using K = typename Scalar<T>::key_t;
+    constexpr K kSign = K(1) << (Scalar<T>::kBits - 1);
+    K b = Scalar<T>::bits(x);
+    K k = (b & kSign) ? ~b : (b | kSign);
+    return is_nan(x) ? ~K(0) : k;
+}
+template <typename T>
+RFI_DEVINL T from_key(typename Scalar<T>::key_t k) {
+    using K = typename Scalar<T>::key_t;
+    constexpr K kSign = K(1) << (Scalar<T>::kBits - 1);
+    K b = (k & kSign) ? (k & ~kSign) : ~k;
+    return (k == ~K(0)) ? Scalar<T>::nan() : Scalar<T>::from_bits(b);
+}
+
+// |re + i*im| exactly as NumPy's SIMD complex absolute computes it (verified bit-for-bit
+// against np.abs for complex64 and complex128 on AVX2/AVX-512 builds, tests/test_oracle*):
+//     hi = max(|re|,|im|); lo = min(|re|,|im|); r = lo / hi; hi * sqrt(fma(r, r, 1))
+// with the inf/nan rules of C hypot (inf wins over nan).
+template <typename T>
+RFI_DEVINL T cabs_np(T re, T im) {
+    T a = fabs_(re), b = fabs_(im);
+    if (is_inf(a) || is_inf(b)) return Scalar<T>::inf();
+    if (is_nan(a) || is_nan(b)) return Scalar<T>::nan();
+    T hi = a > b ? a : b, lo = a > b ? b : a;
+    if (hi == T(0)) return T(0);
+    T r = lo / hi;
+    return Scalar<T>::sqrt_rn(Scalar<T>::fma(r, r, T(1))) * hi;
+}
+
+// keys of +inf / -inf
+template <typename T>
+__host__ __device__ constexpr typename Scalar<T>::key_t to_key_const_inf(bool negative) {
+    using K = typename Scalar<T>::key_t;
+    constexpr K kSign = K(1) << (Scalar<T>::kBits - 1);
+    constexpr K kInfBits = sizeof(T) == 4 ? K(0x7f800000u) : (K(0x7ff00000u) << 32);
+    return negative ? ~(kInfBits | kSign) : (kInfBits | kSign);
+}
+
+// ----------------------------------------------------------------------------------------
+// block-wide reductions.  NT threads; `slots` is NT/32 words of shared scratch per buffer,
+// double buffered so that back-to-back reductions need ONE __syncthreads each.
+template <int NT>
+struct BlockScratch {
+    static constexpr int kWarps = NT / 32;
+    alignas(16) unsigned long long w[2][kWarps * 2];  // two 64-bit lanes per warp (enough for min+max / 2 counts)
+    int parity;
+};
+
+template <int NT>
+RFI_DEVINL void scratch_init(BlockScratch<NT>& s) {
+    if (threadIdx.x == 0) s.parity = 0;
+}
+
+// Sum of one u32 per thread over the block, returned to every thread.
+template <int NT>
+RFI_DEVINL uint32_t block_sum(uint32_t v, BlockScratch<NT>& s, int& parity) {
+    constexpr int W = NT / 32;
+    v = __reduce_add_sync(0xffffffffu, v);
+    uint32_t* buf = reinterpret_cast<uint32_t*>(s.w[parity]);
+    if ((threadIdx.x & 31) == 0) buf[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint32_t t = 0;
+#pragma unroll
+    for (int i = 0; i < W; i += 4) {
+        uint4 q = *reinterpret_cast<const uint4*>(buf + i);
+        t += q.x + q.y + q.z + q.w;
+    }
+    parity ^= 1;
+    return t;
+}
+
+// Two u32 sums at once.
+template <int NT>
+RFI_DEVINL void block_sum2(uint32_t& a, uint32_t& b, BlockScratch<NT>& s, int& parity) {
+    constexpr int W = NT / 32;
+    a = __reduce_add_sync(0xffffffffu, a);
+    b = __reduce_add_sync(0xffffffffu, b);
+    uint32_t* buf = reinterpret_cast<uint32_t*>(s.w[parity]);
+    if ((threadIdx.x & 31) == 0) {
+        buf[threadIdx.x >> 5] = a;
+        buf[W + (threadIdx.x >> 5)] = b;
+    }
+    __syncthreads();
+    uint32_t ta = 0, tb = 0;
+#pragma unroll
+    for (int i = 0; i < W; i += 4) {
+        uint4 q = *reinterpret_cast<const uint4*>(buf + i);
+        uint4 r = *reinterpret_cast<const uint4*>(buf + W + i);
+        ta += q.x + q.y + q.z + q.w;
+        tb += r.x + r.y + r.z + r.w;
+    }
+    a = ta;
+    b = tb;
+    parity ^= 1;
+}
+
+RFI_DEVINL uint32_t warp_min(uint32_t v) { return __reduce_min_sync(0xffffffffu, v); }
+RFI_DEVINL uint32_t warp_max(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
+RFI_DEVINL unsigned long long warp_min(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        unsigned long long u = __shfl_xor_sync(0xffffffffu, v, o);
+        v = u < v ? u : v;
+    }
+    return v;
+}
+RFI_DEVINL unsigned long long warp_max(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        unsigned long long u = __shfl_xor_sync(0xffffffffu, v, o);
+        v = u > v ? u : v;
+    }
+    return v;
+}
+
+// min and max of one key per thread (keys are unsigned); result to every thread.
+template <int NT, typename K>
+RFI_DEVINL void block_minmax_key(K& lo, K& hi, BlockScratch<NT>& s, int& parity) {
+    constexpr int W = NT / 32;
+    lo = warp_min(lo);
+    hi = warp_max(hi);
+    unsigned long long* buf = s.w[parity];
+    if ((threadIdx.x & 31) == 0) {
+        buf[threadIdx.x >> 5] = (unsigned long long)lo;
+        buf[W + (threadIdx.x >> 5)] = (unsigned long long)hi;
+    }
+    __syncthreads();
+    unsigned long long a = buf[0], b = buf[W];
+#pragma unroll
+    for (int i = 1; i < W; ++i) {
+        unsigned long long x = buf[i], y = buf[W + i];
+        a = x < a ? x : a;
+        b = y > b ? y : b;
+    }
+    lo = (K)a;
+    hi = (K)b;
+    parity ^= 1;
+}
+
+// NaN-ignoring min / max of one value per thread (nanmin / nanmax); NaN iff all NaN.
+template <int NT, typename T>
+RFI_DEVINL void block_nanminmax(T& lo, T& hi, BlockScratch<NT>& s, int& parity) {
+    constexpr int W = NT / 32;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        lo = Scalar<T>::fmin_nan(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = Scalar<T>::fmax_nan(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    double* buf = reinterpret_cast<double*>(s.w[parity]);
+    if ((threadIdx.x & 31) == 0) {
+        buf[threadIdx.x >> 5] = (double)lo;
+        buf[W + (threadIdx.x >> 5)] = (double)hi;
+    }
+    __syncthreads();
+    double a = buf[0], b = buf[W];
+#pragma unroll
+    for (int i = 1; i < W; ++i) {
+        a = ::fmin(a, buf[i]);
+        b = ::fmax(b, buf[W + i]);
+    }
+    lo = (T)a;
+    hi = (T)b;
+    parity ^= 1;
+}
+
+// ----------------------------------------------------------------------------------------
+// Register-resident exact selection.
+//
+// Each of the NT threads holds E keys; excluded samples carry the all-ones key and are not
+// counted in n.  block_select2 returns the keys of 0-based ranks k and min(k+1, n-1)... the
+// caller asks for the two middle order statistics of NumPy's median.
+//
+// Method: MSB-first binary radix select ("bit bisection").  Round b asks how many keys are
+// below prefix|1<<b; a round costs 2 instructions per key and one block reduction, no
+// shared-memory atomics (ATOMS retires ~0.5 key/clk/SM on Blackwell, 20x slower than this).
+// The leading bits shared by min and max are skipped.
+template <int NT, int E, typename K>
+RFI_DEVINL void block_select2(const K (&key)[E], uint32_t n, uint32_t k1, uint32_t k2,
+                              K& out1, K& out2, BlockScratch<NT>& s, int& parity) {
+    constexpr K kExcl = ~K(0);
+    constexpr int kBits = sizeof(K) * 8;
+    if (n == 0) {  // uniform: n comes from a block reduction
+        out1 = out2 = kExcl;
+        return;
+    }
+    K lo = kExcl, hi = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        K x = key[e];
+        lo = x < lo ? x : lo;
+        K y = (x == kExcl) ? K(0) : x;
+        hi = y > hi ? y : hi;
+    }
+    block_minmax_key<NT, K>(lo, hi, s, parity);
+    K prefix = lo;
+    K diff = lo ^ hi;
+    if (diff != 0) {
+        int hb = (kBits - 1) - (sizeof(K) == 8 ? __clzll((long long)diff) : __clz((int)diff));
+        K below = (hb == kBits - 1) ? K(0) : (lo >> (hb + 1)) << (hb + 1);
+        prefix = below;
+        for (int b = hb; b >= 0; --b) {
+            K trial = prefix | (K(1) << b);
+            uint32_t c = 0;
+#pragma unroll
+            for (int e = 0; e < E; ++e) c += (key[e] < trial) ? 1u : 0u;
+            c = block_sum<NT>(c, s, parity);
+            if (c <= k1) prefix = trial;
+        }
+    }
+    out1 = prefix;
+    if (k2 == k1) {
+        out2 = prefix;
+        return;
+    }
+    // rank k1+1: same key if duplicates reach it, else the smallest key above.
+    uint32_t cle = 0;
+    K nxt = kExcl;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        K x = key[e];
+        cle += (x <= prefix) ? 1u : 0u;
+        K y = (x > prefix) ? x : kExcl;
+        nxt = y < nxt ? y : nxt;
+    }
+    cle = block_sum<NT>(cle, s, parity);
+    K dummy = 0;
+    block_minmax_key<NT, K>(nxt, dummy, s, parity);
+    out2 = (k2 < cle) ? prefix : nxt;
+}
+
+// NumPy median of the n valid keys held by the block: mean of the two middle order
+// statistics in T ((a + b) / 2 with one rounding of the sum), NaN when n == 0.
+template <typename T, int NT, int E>
+RFI_DEVINL T block_median(const typename Scalar<T>::key_t (&key)[E], uint32_t n,
+                          BlockScratch<NT>& s, int& parity) {
+    using K = typename Scalar<T>::key_t;
+    if (n == 0) return Scalar<T>::nan();
+    K a, b;
+    block_select2<NT, E, K>(key, n, (n - 1) >> 1, n >> 1, a, b, s, parity);
+    T va = from_key<T>(a), vb = from_key<T>(b);
+    if (((n - 1) >> 1) == (n >> 1)) return va;
+    T sum = va + vb;
+    return sum * T(0.5);
+}
+
+}  // namespace rfi

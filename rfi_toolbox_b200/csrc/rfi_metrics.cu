@@ -1,0 +1,230 @@
+// rfi_metrics.cu -- confusion counts for evaluate_segmentation on sm_100a.
+//
+// Replaces the 12 astype(bool) copies and 17 boolean reduction passes of
+// rfi_toolbox/evaluation/metrics.py:25-172 with one streaming pass: 128-bit loads of both
+// masks, per-thread popcounts, warp-shuffle + block reduction, one 64-bit atomic per CTA.
+// The five ratios are formed on the host in float64 exactly as the reference does.
+#include "rfi_common.cuh"
+
+namespace rfi {
+
+// "truthiness" of one element, as ndarray.astype(bool): non-zero (NaN included) is True.
+template <int ELEM, bool FLT> struct Truth;
+template <> struct Truth<1, false> { using V = uint8_t;  RFI_DEVINL static bool nz(V x) { return x != 0; } };
+template <> struct Truth<2, false> { using V = uint16_t; RFI_DEVINL static bool nz(V x) { return x != 0; } };
+template <> struct Truth<4, false> { using V = uint32_t; RFI_DEVINL static bool nz(V x) { return x != 0; } };
+template <> struct Truth<8, false> { using V = unsigned long long; RFI_DEVINL static bool nz(V x) { return x != 0; } };
+// IEEE: +-0 is False, everything else (NaN too) True -> test the magnitude bits
+template <> struct Truth<2, true> { using V = uint16_t; RFI_DEVINL static bool nz(V x) { return (x & 0x7fffu) != 0; } };
+template <> struct Truth<4, true> { using V = uint32_t; RFI_DEVINL static bool nz(V x) { return (x & 0x7fffffffu) != 0; } };
+template <> struct Truth<8, true> { using V = unsigned long long; RFI_DEVINL static bool nz(V x) { return (x & 0x7fffffffffffffffull) != 0; } };
+
+// bit mask (one bit per element) of the non-zero elements among the 16 bytes at p;
+// returns the number of elements covered (16 / ELEM).
+template <int ELEM, bool FLT>
+RFI_DEVINL uint32_t nz_mask16(const uint4& q) {
+    if constexpr (ELEM == 1) {
+        // high bit of every byte set iff the byte is non-zero, then gather those bits
+        auto hb = [](uint32_t v) { return (((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u; };
+        auto pack = [](uint32_t h) {  // bits 7,15,23,31 -> 0..3
+            return ((h >> 7) & 1u) | ((h >> 14) & 2u) | ((h >> 21) & 4u) | ((h >> 28) & 8u);
+        };
+        return pack(hb(q.x)) | (pack(hb(q.y)) << 4) | (pack(hb(q.z)) << 8) | (pack(hb(q.w)) << 12);
+    } else if constexpr (ELEM == 2) {
+        using TR = Truth<2, FLT>;
+        uint32_t w[4] = {q.x, q.y, q.z, q.w}, m = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            m |= (TR::nz((uint16_t)(w[i] & 0xffffu)) ? 1u : 0u) << (2 * i);
+            m |= (TR::nz((uint16_t)(w[i] >> 16)) ? 1u : 0u) << (2 * i + 1);
+        }
+        return m;
+    } else if constexpr (ELEM == 4) {
+        using TR = Truth<4, FLT>;
+        return (TR::nz(q.x) ? 1u : 0u) | (TR::nz(q.y) ? 2u : 0u) | (TR::nz(q.z) ? 4u : 0u) | (TR::nz(q.w) ? 8u : 0u);
+    } else {
+        using TR = Truth<8, FLT>;
+        unsigned long long a = ((unsigned long long)q.y << 32) | q.x, b = ((unsigned long long)q.w << 32) | q.z;
+        return (TR::nz(a) ? 1u : 0u) | (TR::nz(b) ? 2u : 0u);
+    }
+}
+
+template <int ELEM, bool FLT>
+RFI_DEVINL bool nz_scalar(const void* base, long long i) {
+    using TR = Truth<ELEM, FLT>;
+    return TR::nz(static_cast<const typename TR::V*>(base)[i]);
+}
+
+// Both masks with the SAME element size: the common case (uint8/bool vs uint8/bool).
+// `n` elements starting at (pred, truth); segment handled by the calling block(s).
+template <int EP, bool FP, int ET, bool FT>
+RFI_DEVINL void count_range(const void* pred, const void* truth, long long begin, long long end,
+                            long long tid, long long nthreads,
+                            unsigned long long& tp, unsigned long long& fp, unsigned long long& fn) {
+    constexpr int VP = 16 / EP, VT = 16 / ET;          // elements per 128-bit load
+    constexpr int V = VP > VT ? VP : VT;               // elements per step (coarser of the two)
+    const uintptr_t ap = reinterpret_cast<uintptr_t>(pred) + (uintptr_t)begin * EP;
+    const uintptr_t at = reinterpret_cast<uintptr_t>(truth) + (uintptr_t)begin * ET;
+    const long long n = end - begin;
+    // scalar head until BOTH operands sit on a 16-byte boundary; if no such head exists
+    // (the two arrays have different phases) the whole range goes through the scalar path
+    long long head = n;
+    for (int h = 0; h < 16; ++h) {
+        if ((((ap + (uintptr_t)h * EP) | (at + (uintptr_t)h * ET)) & 15) == 0) { head = h; break; }
+    }
+    if (head > n) head = n;
+    unsigned tpc = 0, fpc = 0, fnc = 0;
+    for (long long i = tid; i < head; i += nthreads) {
+        bool p = nz_scalar<EP, FP>(pred, begin + i), t = nz_scalar<ET, FT>(truth, begin + i);
+        tpc += (p && t); fpc += (p && !t); fnc += (!p && t);
+    }
+    const long long body = (n - head) / V;
+    const uint4* vp = reinterpret_cast<const uint4*>(ap + (uintptr_t)head * EP);
+    const uint4* vt = reinterpret_cast<const uint4*>(at + (uintptr_t)head * ET);
+    constexpr int LP = V / VP, LT = V / VT;  // 128-bit loads per step for each operand
+    unsigned iter = 0;
+    for (long long s = tid; s < body; s += nthreads) {
+        uint32_t mp = 0, mt = 0;
+#pragma unroll
+        for (int k = 0; k < LP; ++k) mp |= nz_mask16<EP, FP>(__ldg(vp + s * LP + k)) << (k * VP);
+#pragma unroll
+        for (int k = 0; k < LT; ++k) mt |= nz_mask16<ET, FT>(__ldg(vt + s * LT + k)) << (k * VT);
+        tpc += __popc(mp & mt); fpc += __popc(mp & ~mt); fnc += __popc(~mp & mt);
+        if ((++iter & 1023) == 0) { tp += tpc; fp += fpc; fn += fnc; tpc = fpc = fnc = 0; }
+    }
+    for (long long i = head + body * V + tid; i < n; i += nthreads) {
+        bool p = nz_scalar<EP, FP>(pred, begin + i), t = nz_scalar<ET, FT>(truth, begin + i);
+        tpc += (p && t); fpc += (p && !t); fnc += (!p && t);
+    }
+    tp += tpc; fp += fpc; fn += fnc;
+}
+
+RFI_DEVINL unsigned long long warp_sum64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int NT>
+RFI_DEVINL void block_sum3(unsigned long long& a, unsigned long long& b, unsigned long long& c) {
+    __shared__ unsigned long long sh[3][NT / 32];
+    a = warp_sum64(a); b = warp_sum64(b); c = warp_sum64(c);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sh[0][warp] = a; sh[1][warp] = b; sh[2][warp] = c; }
+    __syncthreads();
+    if (warp == 0) {
+        a = lane < NT / 32 ? sh[0][lane] : 0; b = lane < NT / 32 ? sh[1][lane] : 0; c = lane < NT / 32 ? sh[2][lane] : 0;
+        a = warp_sum64(a); b = warp_sum64(b); c = warp_sum64(c);
+    }
+}
+
+constexpr int kMetricThreads = 256;
+
+template <int EP, bool FP, int ET, bool FT>
+__global__ void __launch_bounds__(kMetricThreads)
+confusion_kernel(const void* __restrict__ pred, const void* __restrict__ truth, long long n,
+                 unsigned long long* __restrict__ counts) {
+    unsigned long long tp = 0, fp = 0, fn = 0;
+    count_range<EP, FP, ET, FT>(pred, truth, 0, n, (long long)blockIdx.x * kMetricThreads + threadIdx.x,
+                                (long long)gridDim.x * kMetricThreads, tp, fp, fn);
+    block_sum3<kMetricThreads>(tp, fp, fn);
+    if (threadIdx.x == 0) {
+        if (tp) atomicAdd(counts + 0, tp);
+        if (fp) atomicAdd(counts + 1, fp);
+        if (fn) atomicAdd(counts + 2, fn);
+    }
+}
+
+// one CTA per segment (a 128 x 128 pair is 16 KiB per mask)
+template <int EP, bool FP, int ET, bool FT>
+__global__ void __launch_bounds__(kMetricThreads)
+confusion_segmented_kernel(const void* __restrict__ pred, const void* __restrict__ truth, long long n_seg,
+                           long long seg, unsigned long long* __restrict__ counts) {
+    for (long long s = blockIdx.x; s < n_seg; s += gridDim.x) {
+        unsigned long long tp = 0, fp = 0, fn = 0;
+        count_range<EP, FP, ET, FT>(pred, truth, s * seg, (s + 1) * seg, threadIdx.x, kMetricThreads, tp, fp, fn);
+        block_sum3<kMetricThreads>(tp, fp, fn);
+        if (threadIdx.x == 0) { counts[s * 3 + 0] = tp; counts[s * 3 + 1] = fp; counts[s * 3 + 2] = fn; }
+        __syncthreads();
+    }
+}
+
+template <int EP, bool FP, int ET, bool FT>
+static int launch_confusion(const void* pred, const void* truth, long long n, long long n_seg, long long seg,
+                            unsigned long long* counts, cudaStream_t st) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (n_seg < 0) {
+        long long want = (n / (16 / (EP < ET ? EP : ET)) + kMetricThreads * 8 - 1) / (kMetricThreads * 8);
+        long long cap = (long long)sms * 8;  // 8 resident CTAs of 256 threads per SM
+        unsigned grid = (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
+        confusion_kernel<EP, FP, ET, FT><<<grid, kMetricThreads, 0, st>>>(pred, truth, n, counts);
+    } else {
+        long long cap = (long long)sms * 8;
+        unsigned grid = (unsigned)(n_seg < cap ? n_seg : cap);
+        confusion_segmented_kernel<EP, FP, ET, FT><<<grid, kMetricThreads, 0, st>>>(pred, truth, n_seg, seg, counts);
+    }
+    RFI_CUDA_TRY(cudaGetLastError());
+    return RFI_OK;
+}
+
+template <int EP, bool FP>
+static int dispatch_true(const void* pred, const void* truth, int et, int ft, long long n, long long n_seg,
+                         long long seg, unsigned long long* counts, cudaStream_t st) {
+    switch (et * 2 + (ft ? 1 : 0)) {
+        case 2:  return launch_confusion<EP, FP, 1, false>(pred, truth, n, n_seg, seg, counts, st);
+        case 4:  return launch_confusion<EP, FP, 2, false>(pred, truth, n, n_seg, seg, counts, st);
+        case 5:  return launch_confusion<EP, FP, 2, true>(pred, truth, n, n_seg, seg, counts, st);
+        case 8:  return launch_confusion<EP, FP, 4, false>(pred, truth, n, n_seg, seg, counts, st);
+        case 9:  return launch_confusion<EP, FP, 4, true>(pred, truth, n, n_seg, seg, counts, st);
+        case 16: return launch_confusion<EP, FP, 8, false>(pred, truth, n, n_seg, seg, counts, st);
+        case 17: return launch_confusion<EP, FP, 8, true>(pred, truth, n, n_seg, seg, counts, st);
+    }
+    set_error("unsupported truth element size %d (float=%d)", et, ft);
+    return RFI_E_INVALID;
+}
+
+static int dispatch(const void* pred, int ep, int fpf, const void* truth, int et, int ft, long long n,
+                    long long n_seg, long long seg, unsigned long long* counts, cudaStream_t st) {
+    if (!counts) { set_error("counts is NULL"); return RFI_E_INVALID; }
+    if (n == 0 || n_seg == 0) return RFI_OK;
+    if (!pred || !truth) { set_error("pred / truth is NULL"); return RFI_E_INVALID; }
+    switch (ep * 2 + (fpf ? 1 : 0)) {
+        case 2:  return dispatch_true<1, false>(pred, truth, et, ft, n, n_seg, seg, counts, st);
+        case 4:  return dispatch_true<2, false>(pred, truth, et, ft, n, n_seg, seg, counts, st);
+        case 5:  return dispatch_true<2, true>(pred, truth, et, ft, n, n_seg, seg, counts, st);
+        case 8:  return dispatch_true<4, false>(pred, truth, et, ft, n, n_seg, seg, counts, st);
+        case 9:  return dispatch_true<4, true>(pred, truth, et, ft, n, n_seg, seg, counts, st);
+        case 16: return dispatch_true<8, false>(pred, truth, et, ft, n, n_seg, seg, counts, st);
+        case 17: return dispatch_true<8, true>(pred, truth, et, ft, n, n_seg, seg, counts, st);
+    }
+    set_error("unsupported pred element size %d (float=%d)", ep, fpf);
+    return RFI_E_INVALID;
+}
+
+}  // namespace rfi
+
+extern "C" int rfi_confusion_counts(const void* pred, int elem_pred, int is_float_pred, const void* truth,
+                                    int elem_true, int is_float_true, int64_t n, unsigned long long* counts,
+                                    void* stream) {
+    if (n < 0) { rfi::set_error("n < 0"); return RFI_E_INVALID; }
+    return rfi::dispatch(pred, elem_pred, is_float_pred, truth, elem_true, is_float_true, n, -1, 0, counts,
+                         (cudaStream_t)stream);
+}
+
+extern "C" int rfi_confusion_counts_segmented(const void* pred, int elem_pred, int is_float_pred,
+                                              const void* truth, int elem_true, int is_float_true,
+                                              int64_t n_seg, int64_t seg, unsigned long long* counts,
+                                              void* stream) {
+    if (n_seg < 0 || seg < 0) { rfi::set_error("negative segment count / size"); return RFI_E_INVALID; }
+    if (seg == 0) {
+        if (n_seg && counts) {
+            cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * 3 * n_seg, (cudaStream_t)stream);
+            if (e != cudaSuccess) return rfi::cuda_fail(e, "cudaMemsetAsync");
+        }
+        return RFI_OK;
+    }
+    return rfi::dispatch(pred, elem_pred, is_float_pred, truth, elem_true, is_float_true, n_seg * seg, n_seg,
+                         seg, counts, (cudaStream_t)stream);
+}

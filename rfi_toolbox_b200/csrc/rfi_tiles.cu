@@ -1,0 +1,599 @@
+// rfi_tiles.cu -- the create_dataset hot path on sm_100a.
+//
+//   phase 1  tile_stats_kernel   one CTA per ORIGINAL P x P tile: load (complex -> magnitude
+//            fused into the 128-bit load), exact median / MAD by register-resident binary
+//            radix select, flag thresholds, flagged-sample count.
+//   (host)   keep mask -> np.random.permutation -> dest_slot[]        (Python)
+//   phase 2  write_patches_kernel one CTA per original tile: recompute the processed tile from
+//            the phase-1 statistics, log-amplitude tile in shared memory, gradient min/max,
+//            then every kept rotation is written as (P, P, 3) float32 + (P, P) uint8 with
+//            full-sector 128-bit stores.
+//
+// Reference semantics: rfi_toolbox/preprocessing/preprocessor.py:22-42, 413-446, 562-783
+// (restated in SURVEY.md Appendix A).  Statistics are rotation invariant for dims divisible
+// by P, so they are computed once per original tile and shared by the R rotated patches.
+#include "rfi_common.cuh"
+
+namespace rfi {
+
+constexpr int kP = 128;  // tile edge handled by one CTA
+
+struct PlanDev {
+    long long n_waterfalls, channels, times;
+    int nh, nw;  // tiles per waterfall along channels / times
+    int rotations, stretch, norm_before, norm_after, flag_mode, magnitude;
+    double sigma;
+};
+
+template <int DT> struct In;
+template <> struct In<RFI_F32>  { using T = float;  static constexpr bool cplx = false; };
+template <> struct In<RFI_F64>  { using T = double; static constexpr bool cplx = false; };
+template <> struct In<RFI_C64>  { using T = float;  static constexpr bool cplx = true; };
+template <> struct In<RFI_C128> { using T = double; static constexpr bool cplx = true; };
+
+// ------------------------------------------------------------------------------------------
+// loads.  `p` points at 4 consecutive samples of one waterfall row.
+template <int DT>
+RFI_DEVINL void load4_mag(const void* base, size_t idx, typename In<DT>::T (&out)[4]) {
+    using T = typename In<DT>::T;
+    if constexpr (DT == RFI_F32) {
+        float4 q = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(base) + idx));
+        out[0] = q.x; out[1] = q.y; out[2] = q.z; out[3] = q.w;
+    } else if constexpr (DT == RFI_F64) {
+        const double2* p = reinterpret_cast<const double2*>(static_cast<const double*>(base) + idx);
+        double2 a = __ldg(p), b = __ldg(p + 1);
+        out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
+    } else if constexpr (DT == RFI_C64) {
+        const float4* p = reinterpret_cast<const float4*>(static_cast<const float2*>(base) + idx);
+        float4 a = __ldg(p), b = __ldg(p + 1);  // two 128-bit loads = four complex64
+        out[0] = cabs_np<T>(a.x, a.y); out[1] = cabs_np<T>(a.z, a.w);
+        out[2] = cabs_np<T>(b.x, b.y); out[3] = cabs_np<T>(b.z, b.w);
+    } else {
+        const double2* p = static_cast<const double2*>(base) + idx;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double2 z = __ldg(p + i);
+            out[i] = cabs_np<T>(z.x, z.y);
+        }
+    }
+}
+
+// one sample: magnitude (or the real value) and, for the complex branch, the phase.
+template <int DT, bool kPhase>
+RFI_DEVINL void load1(const void* base, size_t idx, typename In<DT>::T& mag, typename In<DT>::T& ph) {
+    using T = typename In<DT>::T;
+    ph = T(0);
+    if constexpr (DT == RFI_F32) {
+        mag = __ldg(static_cast<const float*>(base) + idx);
+    } else if constexpr (DT == RFI_F64) {
+        mag = __ldg(static_cast<const double*>(base) + idx);
+    } else if constexpr (DT == RFI_C64) {
+        float2 z = __ldg(static_cast<const float2*>(base) + idx);
+        mag = cabs_np<T>(z.x, z.y);
+        if constexpr (kPhase) ph = Scalar<T>::atan2_(z.y, z.x);
+    } else {
+        double2 z = __ldg(static_cast<const double2*>(base) + idx);
+        mag = cabs_np<T>(z.x, z.y);
+        if constexpr (kPhase) ph = Scalar<T>::atan2_(z.y, z.x);
+    }
+}
+
+template <typename T>
+RFI_DEVINL T apply_stretch(T a, int stretch) {
+    if (stretch == RFI_STRETCH_SQRT) return Scalar<T>::sqrt_rn(fabs_(a));
+    if (stretch == RFI_STRETCH_LOG10) return Scalar<T>::log10_(fabs_(a));
+    return a;
+}
+
+// raw sample -> processed sample, given the tile statistics (identical ops in both phases).
+template <typename T>
+RFI_DEVINL T process_sample(T a, const PlanDev& p, T med_before, T inf_fill, T med_after) {
+    if (p.norm_before && med_before > T(0)) a = a / med_before;
+    if (p.stretch != RFI_STRETCH_NONE) {
+        a = apply_stretch<T>(a, p.stretch);
+        if (is_inf(a)) a = inf_fill;
+    }
+    if (p.norm_after && med_after > T(0)) a = a / med_after;
+    return a;
+}
+
+// ------------------------------------------------------------------------------------------
+// phase 1
+//
+// The tile lives in ONE register array that holds order-preserving keys; values are
+// recovered with from_key() when arithmetic is needed (the map is a bijection on non-NaN
+// floats), so a select never doubles the register footprint.  Shared memory is only a
+// stash for the processed values while the |x - median| keys occupy the registers.
+template <int DT, int NT>
+__global__ void __launch_bounds__(NT, (sizeof(typename In<DT>::T) == 4) ? 2 : 1)
+tile_stats_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __restrict__ flags,
+                  rfi_tile_stat_t* __restrict__ stats) {
+    using T = typename In<DT>::T;
+    using K = typename Scalar<T>::key_t;
+    constexpr int E = kP * kP / NT;  // samples per thread
+    constexpr int G = E / 4;         // groups of 4 consecutive samples
+    constexpr int RS = NT / 32;      // rows covered per group step
+    constexpr K kExcl = ~K(0);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    K* stash = reinterpret_cast<K*>(smem_raw);  // [E][NT]
+    __shared__ BlockScratch<NT> scr;
+    int parity = 0;
+
+    const long long tile = blockIdx.x;
+    const int per = p.nh * p.nw;
+    const long long w = tile / per;
+    const int ti = (int)((tile % per) / p.nw), tj = (int)(tile % p.nw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t origin = ((size_t)w * p.channels + (size_t)ti * kP) * p.times + (size_t)tj * kP;
+
+    K a[E];  // keys of the current values
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        size_t idx = origin + (size_t)(g * RS + warp) * p.times + lane * 4;
+        T q[4];
+        load4_mag<DT>(data, idx, q);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[g * 4 + i] = to_key<T>(q[i]);
+    }
+
+    rfi_tile_stat_t st;
+    st.median_before = st.inf_fill = st.median_after = 0.0;
+    st.centre = st.mad = st.thr_lo = st.thr_hi = 0.0;
+    st.n_inf = 0; st.n_flagged = 0; st.reserved = 0;
+
+    // non-NaN samples (recounted before every median: inf / inf can create a NaN)
+    auto count_valid = [&]() {
+        uint32_t c = 0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) c += (a[e] != kExcl) ? 1u : 0u;
+        return block_sum<NT>(c, scr, parity);
+    };
+    uint32_t nv = count_valid();
+    st.n_valid = (int)nv;
+
+    const bool real_branch = !In<DT>::cplx || p.magnitude;
+
+    if (real_branch) {
+        // ---- normalise by the median (preprocessor.py:646-670)
+        if (p.norm_before) {
+            T m = block_median<T, NT, E>(a, nv, scr, parity);
+            st.median_before = (double)m;
+            if (m > T(0)) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) a[e] = to_key<T>(from_key<T>(a[e]) / m);
+            }
+        }
+        // ---- stretch, +-inf := MAD of the finite values (preprocessor.py:672-706)
+        if (p.stretch != RFI_STRETCH_NONE) {
+            uint32_t ninf = 0, nfin = 0;
+            constexpr K kPosInf = to_key_const_inf<T>(false), kNegInf = to_key_const_inf<T>(true);
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                a[e] = to_key<T>(apply_stretch<T>(from_key<T>(a[e]), p.stretch));
+                const bool inf = (a[e] == kPosInf || a[e] == kNegInf);
+                ninf += inf ? 1u : 0u;
+                nfin += (!inf && a[e] != kExcl) ? 1u : 0u;
+            }
+            block_sum2<NT>(ninf, nfin, scr, parity);
+            st.n_inf = (int)ninf;
+            if (ninf > 0) {
+                T fill = T(0);
+                if (nfin > 0) {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) stash[e * NT + threadIdx.x] = a[e];
+#pragma unroll
+                    for (int e = 0; e < E; ++e) a[e] = (a[e] == kPosInf || a[e] == kNegInf) ? kExcl : a[e];
+                    T c = block_median<T, NT, E>(a, nfin, scr, parity);
+#pragma unroll
+                    for (int e = 0; e < E; ++e)
+                        a[e] = (a[e] == kExcl) ? kExcl : to_key<T>(fabs_(from_key<T>(a[e]) - c));
+                    fill = block_median<T, NT, E>(a, nfin, scr, parity);
+#pragma unroll
+                    for (int e = 0; e < E; ++e) a[e] = stash[e * NT + threadIdx.x];
+                }
+                st.inf_fill = (double)fill;
+                const K kfill = to_key<T>(fill);
+#pragma unroll
+                for (int e = 0; e < E; ++e) a[e] = (a[e] == kPosInf || a[e] == kNegInf) ? kfill : a[e];
+            }
+        }
+        // ---- normalise again (preprocessor.py:309-311)
+        if (p.norm_after) {
+            T m2 = block_median<T, NT, E>(a, count_valid(), scr, parity);
+            st.median_after = (double)m2;
+            if (m2 > T(0)) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) a[e] = to_key<T>(from_key<T>(a[e]) / m2);
+            }
+        }
+    }
+
+    if (p.flag_mode == RFI_FLAGS_MAD) {
+        // ---- MAD flags on the processed tile (preprocessor.py:708-745; |z| first for
+        //      complex input, :126-127)
+        const uint32_t nn = count_valid();
+        T c = block_median<T, NT, E>(a, nn, scr, parity);
+#pragma unroll
+        for (int e = 0; e < E; ++e) stash[e * NT + threadIdx.x] = a[e];
+#pragma unroll
+        for (int e = 0; e < E; ++e) a[e] = to_key<T>(fabs_(from_key<T>(a[e]) - c));
+        T d = block_median<T, NT, E>(a, nn, scr, parity);
+        T ds = d * (T)p.sigma;
+        T hi = c + ds, lo = c - ds;
+        uint32_t nf = 0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            T x = from_key<T>(stash[e * NT + threadIdx.x]);
+            nf += ((x > hi) || (x < lo)) ? 1u : 0u;
+        }
+        nf = block_sum<NT>(nf, scr, parity);
+        st.centre = (double)c; st.mad = (double)d;
+        st.thr_lo = (double)lo; st.thr_hi = (double)hi;
+        st.n_flagged = (int)nf;
+    } else if (p.flag_mode == RFI_FLAGS_CUSTOM) {
+        uint32_t nf = 0;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            size_t idx = origin + (size_t)(g * RS + warp) * p.times + lane * 4;
+            uint32_t f4 = __ldg(reinterpret_cast<const uint32_t*>(flags + idx));
+            uint32_t nz = (((f4 & 0x7f7f7f7fu) + 0x7f7f7f7fu) | f4) & 0x80808080u;
+            nf += __popc(nz);
+        }
+        nf = block_sum<NT>(nf, scr, parity);
+        st.n_flagged = (int)nf;
+    }
+    if (threadIdx.x == 0) stats[tile] = st;
+}
+
+// custom flags / inference with nothing to measure on the data: flags only.
+template <int NT>
+__global__ void __launch_bounds__(NT)
+flags_count_kernel(PlanDev p, const uint8_t* __restrict__ flags, rfi_tile_stat_t* __restrict__ stats) {
+    constexpr int G = kP * kP / NT / 4, RS = NT / 32;
+    __shared__ BlockScratch<NT> scr;
+    int parity = 0;
+    const long long tile = blockIdx.x;
+    const int per = p.nh * p.nw;
+    const long long w = tile / per;
+    const int ti = (int)((tile % per) / p.nw), tj = (int)(tile % p.nw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t origin = ((size_t)w * p.channels + (size_t)ti * kP) * p.times + (size_t)tj * kP;
+    uint32_t nf = 0;
+    if (flags != nullptr) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            size_t idx = origin + (size_t)(g * RS + warp) * p.times + lane * 4;
+            uint32_t f4 = __ldg(reinterpret_cast<const uint32_t*>(flags + idx));
+            uint32_t nz = (((f4 & 0x7f7f7f7fu) + 0x7f7f7f7fu) | f4) & 0x80808080u;
+            nf += __popc(nz);
+        }
+    }
+    nf = block_sum<NT>(nf, scr, parity);
+    if (threadIdx.x == 0) {
+        rfi_tile_stat_t st;
+        st.median_before = st.inf_fill = st.median_after = 0.0;
+        st.centre = st.mad = st.thr_lo = st.thr_hi = 0.0;
+        st.n_valid = kP * kP; st.n_inf = 0; st.n_flagged = (int)nf; st.reserved = 0;
+        stats[tile] = st;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// phase 2
+template <typename T> struct Phase2Smem {
+    static constexpr int kPitch = kP + 1;    // conflict-free row AND column access
+    static constexpr int kFlagPitch = kP + 4;  // bytes; 33 words -> column reads hit 32 banks
+};
+
+template <int DT, int NT, bool kComplexBranch>
+__global__ void __launch_bounds__(NT, (sizeof(typename In<DT>::T) == 4 && !kComplexBranch) ? 2 : 1)
+write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __restrict__ flags,
+                     const rfi_tile_stat_t* __restrict__ stats, const long long* __restrict__ dest_slot,
+                     float* __restrict__ images, uint8_t* __restrict__ labels) {
+    using T = typename In<DT>::T;
+    constexpr int E = kP * kP / NT;
+    constexpr int RS = NT / 32;      // rows per step (one warp per row)
+    constexpr int STEPS = kP / RS;   // row steps
+    constexpr int Q = kP / 32;       // columns per lane per row (4)
+    constexpr int LP = Phase2Smem<T>::kPitch;
+    constexpr int FP = Phase2Smem<T>::kFlagPitch;
+    static_assert(E == STEPS * Q, "tile / thread mapping");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* Ls = reinterpret_cast<T*>(smem_raw);                                    // [kP][LP]
+    float* Ph = reinterpret_cast<float*>(Ls + (size_t)kP * LP);               // [kP][LP] (complex branch)
+    unsigned char* Fb = reinterpret_cast<unsigned char*>(Ph + (kComplexBranch ? (size_t)kP * LP : 0));
+    float* stage = reinterpret_cast<float*>(Fb + (size_t)kP * FP);            // [warps][3*kP]
+    unsigned char* lstage = reinterpret_cast<unsigned char*>(stage + (size_t)RS * 3 * kP);  // [warps][kP]
+    __shared__ BlockScratch<NT> scr;
+    int parity = 0;
+
+    const long long tile = blockIdx.x;
+    const int per = p.nh * p.nw;
+    const long long w = tile / per;
+    const int ti = (int)((tile % per) / p.nw), tj = (int)(tile % p.nw);
+    const int R = p.rotations;
+    const long long base = w * R * per;
+
+    // canonical patch index of each rotation of this tile
+    long long slot[4] = {-1, -1, -1, -1};
+    slot[0] = dest_slot[base + (long long)ti * p.nw + tj];
+    if (R >= 2) slot[1] = dest_slot[base + per + (long long)(p.nh - 1 - ti) * p.nw + tj];
+    if (R >= 4) {
+        slot[2] = dest_slot[base + 2LL * per + (long long)tj * p.nh + ti];
+        slot[3] = dest_slot[base + 3LL * per + (long long)(p.nw - 1 - tj) * p.nh + ti];
+    }
+    if (slot[0] < 0 && slot[1] < 0 && slot[2] < 0 && slot[3] < 0) return;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t origin = ((size_t)w * p.channels + (size_t)ti * kP) * p.times + (size_t)tj * kP;
+    const rfi_tile_stat_t st = stats[tile];
+    const T med_before = (T)st.median_before, inf_fill = (T)st.inf_fill, med_after = (T)st.median_after;
+    const T thr_lo = (T)st.thr_lo, thr_hi = (T)st.thr_hi;
+    const bool real_branch = !kComplexBranch;
+
+    // ---- pass A: processed sample -> log amplitude tile, label tile, min/max of L
+    T llo = Scalar<T>::nan(), lhi = Scalar<T>::nan();
+#pragma unroll
+    for (int s = 0; s < STEPS; ++s) {
+        const int row = s * RS + warp;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int col = lane + 32 * q;
+            const size_t idx = origin + (size_t)row * p.times + col;
+            T a, ph;
+            load1<DT, kComplexBranch>(data, idx, a, ph);
+            T x = a;
+            if (real_branch) x = process_sample<T>(a, p, med_before, inf_fill, med_after);
+            unsigned char f = 0;
+            if (p.flag_mode == RFI_FLAGS_MAD) f = ((x > thr_hi) || (x < thr_lo)) ? 1 : 0;
+            else if (p.flag_mode == RFI_FLAGS_CUSTOM) f = __ldg(flags + idx);
+            T L = Scalar<T>::log10_(fabs_(x) + T(1e-10));
+            Ls[row * LP + col] = L;
+            Fb[row * FP + col] = f;
+            if constexpr (kComplexBranch) {
+                // (phase + pi) / (2 pi) in T, then the reference's cast to float32
+                T c2 = (ph + T(3.141592653589793)) / T(6.283185307179586);
+                Ph[row * LP + col] = (float)c2;
+            } else {
+                llo = Scalar<T>::fmin_nan(llo, L);
+                lhi = Scalar<T>::fmax_nan(lhi, L);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- pass B: min/max of the squared gradient for each distinct rotation variant
+    T s0lo = Scalar<T>::nan(), s0hi = Scalar<T>::nan();
+    T s1lo = Scalar<T>::nan(), s1hi = Scalar<T>::nan();
+    T s3lo = Scalar<T>::nan(), s3hi = Scalar<T>::nan();
+#pragma unroll 2
+    for (int s = 0; s < STEPS; ++s) {
+        const int i = s * RS + warp;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int j = lane + 32 * q;
+            const T c = Ls[i * LP + j];
+            const T bi = (i > 0) ? c - Ls[(i - 1) * LP + j] : T(0);
+            const T bj = (j > 0) ? c - Ls[i * LP + j - 1] : T(0);
+            const T bi2 = bi * bi, bj2 = bj * bj;
+            const T ss0 = bi2 + bj2;
+            s0lo = Scalar<T>::fmin_nan(s0lo, ss0); s0hi = Scalar<T>::fmax_nan(s0hi, ss0);
+            if (R >= 2) {
+                const T fi = (i < kP - 1) ? c - Ls[(i + 1) * LP + j] : T(0);
+                const T ss1 = fi * fi + bj2;
+                s1lo = Scalar<T>::fmin_nan(s1lo, ss1); s1hi = Scalar<T>::fmax_nan(s1hi, ss1);
+            }
+            if (R >= 4) {
+                const T fj = (j < kP - 1) ? c - Ls[i * LP + j + 1] : T(0);
+                const T ss3 = fj * fj + bi2;
+                s3lo = Scalar<T>::fmin_nan(s3lo, ss3); s3hi = Scalar<T>::fmax_nan(s3hi, ss3);
+            }
+        }
+    }
+    block_nanminmax<NT, T>(s0lo, s0hi, scr, parity);
+    if (R >= 2) block_nanminmax<NT, T>(s1lo, s1hi, scr, parity);
+    if (R >= 4) block_nanminmax<NT, T>(s3lo, s3hi, scr, parity);
+    if constexpr (!kComplexBranch) block_nanminmax<NT, T>(llo, lhi, scr, parity);
+
+    // sqrt is monotone: min/max of g = sqrt(min/max of g^2)
+    T glo[4], grng[4];
+    bool gok[4];
+    {
+        T lo0 = Scalar<T>::sqrt_rn(s0lo), hi0 = Scalar<T>::sqrt_rn(s0hi);
+        T lo1 = Scalar<T>::sqrt_rn(s1lo), hi1 = Scalar<T>::sqrt_rn(s1hi);
+        T lo3 = Scalar<T>::sqrt_rn(s3lo), hi3 = Scalar<T>::sqrt_rn(s3hi);
+        glo[0] = lo0; grng[0] = hi0 - lo0; gok[0] = hi0 > lo0;
+        glo[1] = lo1; grng[1] = hi1 - lo1; gok[1] = hi1 > lo1;
+        glo[2] = lo0; grng[2] = hi0 - lo0; gok[2] = hi0 > lo0;
+        glo[3] = lo3; grng[3] = hi3 - lo3; gok[3] = hi3 > lo3;
+    }
+    const T lrng = lhi - llo;
+    const bool lok = lhi > llo;
+
+    const float mean0 = 0.485f, mean1 = 0.456f, mean2 = 0.406f;
+    const float std0 = 0.229f, std1 = 0.224f, std2 = 0.225f;
+    const float ch2_real = (0.0f - mean2) / std2;
+
+    float* wstage = stage + (size_t)warp * 3 * kP;
+    unsigned char* wl = lstage + (size_t)warp * kP;
+
+    // ---- pass C: every kept rotation, one output row per warp per step
+#pragma unroll 1
+    for (int r = 0; r < R; ++r) {
+        const long long sl = slot[r];
+        if (sl < 0) continue;  // uniform across the block
+        float* out_img = images + (size_t)sl * kP * kP * 3;
+        unsigned char* out_lab = labels + (size_t)sl * kP * kP;
+        const T lo_r = glo[r], rng_r = grng[r];
+        const bool ok_r = gok[r];
+#pragma unroll 1
+        for (int s = 0; s < STEPS; ++s) {
+            const int orow = s * RS + warp;  // output row i'
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const int ocol = lane + 32 * q;  // output column j'
+                int i, j, ai, aj, bi_, bj_;
+                // (i, j): source sample; (ai, aj): neighbour of the row-derivative (zero on
+                // output row 0); (bi_, bj_): neighbour of the column-derivative (zero on col 0)
+                if (r == 0) { i = orow; j = ocol; ai = i - 1; aj = j; bi_ = i; bj_ = j - 1; }
+                else if (r == 1) { i = kP - 1 - orow; j = ocol; ai = i + 1; aj = j; bi_ = i; bj_ = j - 1; }
+                else if (r == 2) { i = ocol; j = orow; ai = i; aj = j - 1; bi_ = i - 1; bj_ = j; }
+                else { i = ocol; j = kP - 1 - orow; ai = i; aj = j + 1; bi_ = i - 1; bj_ = j; }
+                const T c = Ls[i * LP + j];
+                const T td = (orow > 0) ? c - Ls[ai * LP + aj] : T(0);
+                const T fd = (ocol > 0) ? c - Ls[bi_ * LP + bj_] : T(0);
+                const T g = Scalar<T>::sqrt_rn(td * td + fd * fd);
+                const T c0 = ok_r ? (g - lo_r) / rng_r : T(0);
+                float o0 = ((float)c0 - mean0) / std0, o1, o2;
+                if constexpr (kComplexBranch) {
+                    T u = (c - T(-3.0)) / T(7.0);
+                    u = u < T(0) ? T(0) : (u > T(1) ? T(1) : u);  // np.clip keeps NaN
+                    o1 = ((float)u - mean1) / std1;
+                    o2 = (Ph[i * LP + j] - mean2) / std2;
+                } else {
+                    const T u = lok ? (c - llo) / lrng : T(0);
+                    o1 = ((float)u - mean1) / std1;
+                    o2 = ch2_real;
+                }
+                wstage[ocol * 3 + 0] = o0;
+                wstage[ocol * 3 + 1] = o1;
+                wstage[ocol * 3 + 2] = o2;
+                wl[ocol] = Fb[i * FP + j];
+            }
+            __syncwarp();
+            float4* dst = reinterpret_cast<float4*>(out_img + (size_t)orow * kP * 3);
+            const float4* src = reinterpret_cast<const float4*>(wstage);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) dst[lane + 32 * k] = src[lane + 32 * k];
+            if (lane < kP / 16)
+                reinterpret_cast<uint4*>(out_lab + (size_t)orow * kP)[lane] =
+                    reinterpret_cast<const uint4*>(wl)[lane];
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+static int make_plan(const rfi_plan_t* plan, PlanDev& d) {
+    if (!plan) { set_error("plan is NULL"); return RFI_E_INVALID; }
+    if (plan->dtype < RFI_F32 || plan->dtype > RFI_C128) { set_error("bad dtype %d", plan->dtype); return RFI_E_INVALID; }
+    if (plan->rotations != 1 && plan->rotations != 2 && plan->rotations != 4) {
+        set_error("rotations must be 1, 2 or 4 (got %d)", plan->rotations); return RFI_E_INVALID; }
+    if (plan->stretch < 0 || plan->stretch > 2) { set_error("bad stretch %d", plan->stretch); return RFI_E_INVALID; }
+    if (plan->flag_mode < 0 || plan->flag_mode > 2) { set_error("bad flag_mode %d", plan->flag_mode); return RFI_E_INVALID; }
+    if (plan->n_waterfalls < 0 || plan->channels <= 0 || plan->times <= 0) { set_error("bad cube shape"); return RFI_E_INVALID; }
+    if (plan->patch != kP) {
+        set_error("patch size %d: only the shared-memory fast path (P = %d) is built", plan->patch, kP);
+        return RFI_E_UNSUPPORTED;
+    }
+    if (plan->channels % kP || plan->times % kP) {
+        set_error("cube %lld x %lld is not a multiple of the patch size (padding path not built)",
+                  (long long)plan->channels, (long long)plan->times);
+        return RFI_E_UNSUPPORTED;
+    }
+    d.n_waterfalls = plan->n_waterfalls; d.channels = plan->channels; d.times = plan->times;
+    d.nh = (int)(plan->channels / kP); d.nw = (int)(plan->times / kP);
+    d.rotations = plan->rotations; d.stretch = plan->stretch;
+    d.norm_before = plan->norm_before; d.norm_after = plan->norm_after;
+    d.flag_mode = plan->flag_mode; d.magnitude = plan->magnitude; d.sigma = plan->sigma;
+    return RFI_OK;
+}
+
+template <int DT, int NT>
+static int launch_stats(const PlanDev& d, long long tiles, const void* data, const uint8_t* flags,
+                        rfi_tile_stat_t* stats, cudaStream_t st) {
+    using K = typename Scalar<typename In<DT>::T>::key_t;
+    auto kern = tile_stats_kernel<DT, NT>;
+    size_t smem = (size_t)kP * kP * sizeof(K);
+    RFI_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)tiles, NT, smem, st>>>(d, data, flags, stats);
+    return RFI_OK;
+}
+
+template <int DT, int NT, bool CB>
+static int launch_write(const PlanDev& d, long long tiles, const void* data, const uint8_t* flags,
+                        const rfi_tile_stat_t* stats, const long long* dest, float* images,
+                        uint8_t* labels, cudaStream_t st) {
+    using T = typename In<DT>::T;
+    auto kern = write_patches_kernel<DT, NT, CB>;
+    size_t smem = (size_t)kP * Phase2Smem<T>::kPitch * sizeof(T) +
+                  (CB ? (size_t)kP * Phase2Smem<T>::kPitch * sizeof(float) : 0) +
+                  (size_t)kP * Phase2Smem<T>::kFlagPitch + (size_t)(NT / 32) * (3 * kP * sizeof(float) + kP);
+    RFI_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)tiles, NT, smem, st>>>(d, data, flags, stats, dest, images, labels);
+    return RFI_OK;
+}
+
+}  // namespace rfi
+
+using namespace rfi;
+
+extern "C" int64_t rfi_plan_num_tiles(const rfi_plan_t* plan) {
+    if (!plan || plan->patch <= 0) return -1;
+    return plan->n_waterfalls * (plan->channels / plan->patch) * (plan->times / plan->patch);
+}
+extern "C" int64_t rfi_plan_num_patches(const rfi_plan_t* plan) {
+    int64_t t = rfi_plan_num_tiles(plan);
+    return t < 0 ? t : t * plan->rotations;
+}
+
+extern "C" int rfi_tile_stats(const rfi_plan_t* plan, const void* data, const uint8_t* flags,
+                              rfi_tile_stat_t* stats, void* stream) {
+    PlanDev d;
+    int rc = make_plan(plan, d);
+    if (rc) return rc;
+    const long long tiles = rfi_plan_num_tiles(plan);
+    if (tiles == 0) return RFI_OK;
+    if (!data || !stats) { set_error("data / stats is NULL"); return RFI_E_INVALID; }
+    if (d.flag_mode == RFI_FLAGS_CUSTOM && !flags) { set_error("custom flag mode needs flags"); return RFI_E_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool cplx = plan->dtype >= RFI_C64;
+    const bool real_branch = !cplx || plan->magnitude;
+    const bool need_data = d.flag_mode == RFI_FLAGS_MAD ||
+                           (real_branch && (d.norm_before || d.norm_after || d.stretch != RFI_STRETCH_NONE));
+    if (!need_data) {
+        flags_count_kernel<512><<<(unsigned)tiles, 512, 0, st>>>(d, d.flag_mode == RFI_FLAGS_CUSTOM ? flags : nullptr, stats);
+    } else {
+        switch (plan->dtype) {
+            case RFI_F32: rc = launch_stats<RFI_F32, 512>(d, tiles, data, flags, stats, st); break;
+            case RFI_C64: rc = launch_stats<RFI_C64, 512>(d, tiles, data, flags, stats, st); break;
+            case RFI_F64: rc = launch_stats<RFI_F64, 512>(d, tiles, data, flags, stats, st); break;
+            default:      rc = launch_stats<RFI_C128, 512>(d, tiles, data, flags, stats, st); break;
+        }
+        if (rc) return rc;
+    }
+    RFI_CUDA_TRY(cudaGetLastError());
+    return RFI_OK;
+}
+
+extern "C" int rfi_write_patches(const rfi_plan_t* plan, const void* data, const uint8_t* flags,
+                                 const rfi_tile_stat_t* stats, const int64_t* dest_slot,
+                                 float* images, uint8_t* labels, void* stream) {
+    PlanDev d;
+    int rc = make_plan(plan, d);
+    if (rc) return rc;
+    const long long tiles = rfi_plan_num_tiles(plan);
+    if (tiles == 0) return RFI_OK;
+    if (!data || !stats || !dest_slot) { set_error("data / stats / dest_slot is NULL"); return RFI_E_INVALID; }
+    if (d.flag_mode == RFI_FLAGS_CUSTOM && !flags) { set_error("custom flag mode needs flags"); return RFI_E_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long* dest = reinterpret_cast<const long long*>(dest_slot);
+    const bool cb = plan->dtype >= RFI_C64 && !plan->magnitude;
+    switch (plan->dtype) {
+        case RFI_F32: rc = launch_write<RFI_F32, 512, false>(d, tiles, data, flags, stats, dest, images, labels, st); break;
+        case RFI_F64: rc = launch_write<RFI_F64, 512, false>(d, tiles, data, flags, stats, dest, images, labels, st); break;
+        case RFI_C64:
+            rc = cb ? launch_write<RFI_C64, 1024, true>(d, tiles, data, flags, stats, dest, images, labels, st)
+                    : launch_write<RFI_C64, 512, false>(d, tiles, data, flags, stats, dest, images, labels, st);
+            break;
+        default:
+            rc = cb ? launch_write<RFI_C128, 256, true>(d, tiles, data, flags, stats, dest, images, labels, st)
+                    : launch_write<RFI_C128, 512, false>(d, tiles, data, flags, stats, dest, images, labels, st);
+            break;
+    }
+    if (rc) return rc;
+    RFI_CUDA_TRY(cudaGetLastError());
+    return RFI_OK;
+}

@@ -1,0 +1,4 @@
+"""Dataset containers (mirror of rfi_toolbox/datasets/__init__.py:7)."""
+from .batched_dataset import TorchDataset
+
+__all__ = ["TorchDataset"]

@@ -1,0 +1,18 @@
+"""Evaluation operators (mirror of rfi_toolbox/evaluation/__init__.py:8-21)."""
+from .metrics import (
+    compute_dice,
+    compute_f1,
+    compute_iou,
+    compute_precision,
+    compute_recall,
+    confusion_counts,
+    evaluate_segmentation,
+    evaluate_segmentation_batch,
+)
+from .statistics import compute_ffi, compute_mad, compute_statistics
+
+__all__ = [
+    "compute_iou", "compute_precision", "compute_recall", "compute_f1", "compute_dice",
+    "evaluate_segmentation", "evaluate_segmentation_batch", "confusion_counts",
+    "compute_statistics", "compute_ffi", "compute_mad",
+]

@@ -1,0 +1,4 @@
+"""Preprocessing operators (mirror of rfi_toolbox/preprocessing/__init__.py:7)."""
+from .preprocessor import Preprocessor, canonical_index_map, patchify
+
+__all__ = ["Preprocessor", "patchify", "canonical_index_map"]

@@ -1,0 +1,245 @@
+"""Preprocessor -- drop-in for rfi_toolbox/preprocessing/preprocessor.py:139-783.
+
+`Preprocessor(data, flags).create_dataset(...)` keeps the reference's signature, defaults,
+metadata dict, error behaviour and RNG consumption (exactly one `np.random.permutation`
+from the global legacy RNG unless `inference_mode`), and returns a `TorchDataset` whose
+`.images (N, P, P, 3) float32` / `.labels (N, P, P) uint8` hold the same values in the same
+order.  What changes is where the work happens:
+
+  phase 1  `rfi_tile_stats`    per-tile median / MAD / thresholds / flag counts   (GPU)
+  host     keep mask -> stable compaction -> np.random.permutation -> dest_slot[] (tiny)
+  phase 2  `rfi_write_patches` rotate + tile + normalise + stretch + flag + 3-channel
+                               + ImageNet normalise, each patch written once to its final
+                               shuffled slot                                        (GPU)
+
+Extensions, all keyword-only and off by default: `magnitude=True` treats complex input as
+the reference treats `np.abs(data)` (the real branch, with |z| fused into the load);
+`device=`; `pin=` for the host->device copy of NumPy input.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+
+import numpy as np
+import torch
+
+from .. import _native
+from ..datasets.batched_dataset import TorchDataset
+from ..utils.device import as_device_tensor, current_stream_ptr, require_cuda
+
+logger = logging.getLogger(__name__)
+
+_DTYPE_CODE = {
+    torch.float32: _native.RFI_F32, torch.float64: _native.RFI_F64,
+    torch.complex64: _native.RFI_C64, torch.complex128: _native.RFI_C128,
+}
+_STRETCH_CODE = {None: _native.RFI_STRETCH_NONE, "SQRT": _native.RFI_STRETCH_SQRT,
+                 "LOG10": _native.RFI_STRETCH_LOG10}
+
+
+def patchify(array, patch_shape, step):
+    """preprocessor.py:22-42: (H, W) -> (n_h, n_w, patch_h, patch_w) windows.
+
+    Pure index arithmetic (a strided view made contiguous) -- kept for API parity and for
+    the reference's own known-answer tests (tests/test_preprocessing.py:14-66); the CUDA
+    path never materialises this array."""
+    ph, pw = patch_shape
+    a = np.asarray(array)
+    nh = (a.shape[0] - ph) // step + 1
+    nw = (a.shape[1] - pw) // step + 1
+    s0, s1 = a.strides
+    view = np.lib.stride_tricks.as_strided(a, (nh, nw, ph, pw), (s0 * step, s1 * step, s0, s1),
+                                           writeable=False)
+    return np.ascontiguousarray(view)
+
+
+def canonical_index_map(n_waterfalls, n_rot, nh, nw):
+    """Canonical (pre-compaction) patch index of rotation r of original tile (i, j) of
+    waterfall w -- the order in which preprocessor.py:413-446 + :478-560 emit patches.
+    int64 [n_waterfalls, n_rot, nh, nw]."""
+    per = nh * nw
+    i = np.arange(nh, dtype=np.int64)[:, None]
+    j = np.arange(nw, dtype=np.int64)[None, :]
+    local = np.empty((n_rot, nh, nw), dtype=np.int64)
+    local[0] = i * nw + j
+    if n_rot >= 2:
+        local[1] = per + (nh - 1 - i) * nw + j
+    if n_rot >= 4:
+        local[2] = 2 * per + j * nh + i
+        local[3] = 3 * per + (nw - 1 - j) * nh + i
+    base = np.arange(n_waterfalls, dtype=np.int64)[:, None, None, None] * (n_rot * per)
+    return base + local[None]
+
+
+class Preprocessor:
+    """Preprocess waterfall data into training patches (preprocessor.py:139-196)."""
+
+    def __init__(self, data, flags=None, *, magnitude=False, device=None, pin=False):
+        ndim = data.ndim
+        if ndim == 3:
+            data = data[None, ...]  # :187-189 -- flags are NOT reshaped (reference quirk Q7)
+        elif ndim != 4:
+            raise ValueError(f"Data must be 3D or 4D, got shape {tuple(data.shape)}")
+        self.data = data
+        self.flags = flags
+        self.patches = None
+        self.patch_flags = None
+        self.dataset = None
+        self.magnitude = bool(magnitude)
+        self._device = device
+        self._pin = pin
+        self.last_tile_stats = None
+
+    # ------------------------------------------------------------------------------ helpers
+    @staticmethod
+    def _effective_rotations(enable_augmentation, augmentation_rotations):
+        """preprocessor.py:240, 436-444."""
+        if not enable_augmentation or augmentation_rotations <= 1:
+            return 1
+        return 4 if augmentation_rotations >= 4 else 2
+
+    def _resolve_device(self):
+        for x in (self.data, self.flags):
+            if isinstance(x, torch.Tensor) and x.is_cuda:
+                return require_cuda(x.device)
+        return require_cuda(self._device)
+
+    # ------------------------------------------------------------------------------ main
+    def create_dataset(
+        self,
+        patch_size=128,
+        stretch=None,
+        flag_sigma=5,
+        use_custom_flags=True,
+        num_patches=None,
+        normalize_before_stretch=True,
+        normalize_after_stretch=False,
+        num_workers=4,
+        enable_augmentation=True,
+        augmentation_rotations=4,
+        inference_mode=False,
+    ):
+        """preprocessor.py:198-411.  `num_workers` is accepted and ignored (there is no
+        process pool on the GPU path)."""
+        lib = _native.load()
+        device = self._resolve_device()
+        if stretch and stretch not in ("SQRT", "LOG10"):
+            raise ValueError(f"Invalid stretch '{stretch}'. Use 'SQRT' or 'LOG10'")
+
+        data = as_device_tensor(self.data, device, pin=self._pin)
+        if data.dtype not in _DTYPE_CODE:
+            raise TypeError(f"unsupported data dtype {data.dtype}: float32/64 or complex64/128")
+        B, npol, C_, T_ = data.shape
+        is_complex = data.is_complex()
+        complex_branch = is_complex and not self.magnitude
+
+        custom = bool(use_custom_flags and self.flags is not None)
+        flags = None
+        if custom and not inference_mode or custom:
+            if self.flags.ndim != 4:
+                # the reference fails unpacking `.shape` of a 1-D row here (quirk Q7)
+                raise ValueError("flags must be 4-D (baselines, pols, channels, times)")
+            if tuple(self.flags.shape) != tuple(data.shape):
+                raise ValueError(f"flags shape {tuple(self.flags.shape)} != data shape {tuple(data.shape)}")
+        if custom and not inference_mode:
+            flags = as_device_tensor(self.flags, device, pin=self._pin)
+            if flags.dtype == torch.bool:
+                flags = flags.view(torch.uint8)
+            elif flags.dtype not in (torch.uint8, torch.int8):
+                raise TypeError(f"unsupported flags dtype {flags.dtype}: bool or uint8")
+            else:
+                flags = flags.view(torch.uint8)
+
+        R = self._effective_rotations(enable_augmentation, augmentation_rotations)
+        P = int(patch_size)
+        skip_patchify = C_ <= P and T_ <= P  # :261
+        if skip_patchify:
+            if R == 4 and C_ != T_:
+                raise ValueError("setting an array element with a sequence: rotated views of a "
+                                 "non-square waterfall cannot be stacked (reference raises here too)")
+        else:
+            # :282 -- one (rows, cols) entry per rotated waterfall
+            shapes = []
+            for _ in range(B * npol):
+                shapes.append((C_, T_))
+                if R >= 2:
+                    shapes.append((C_, T_))
+                if R >= 4:
+                    shapes.extend([(T_, C_), (T_, C_)])
+            self.original_shapes = shapes
+
+        if inference_mode:
+            flag_mode = _native.RFI_FLAGS_INFERENCE
+        elif custom:
+            flag_mode = _native.RFI_FLAGS_CUSTOM
+        else:
+            flag_mode = _native.RFI_FLAGS_MAD
+
+        plan = _native.RfiPlan(
+            dtype=_DTYPE_CODE[data.dtype], magnitude=int(self.magnitude and is_complex),
+            n_waterfalls=B * npol, channels=C_, times=T_, patch=P, rotations=R,
+            stretch=_STRETCH_CODE[stretch] if not complex_branch else _native.RFI_STRETCH_NONE,
+            norm_before=int(bool(normalize_before_stretch) and not complex_branch),
+            norm_after=int(bool(normalize_after_stretch) and not complex_branch),
+            flag_mode=flag_mode, sigma=float(flag_sigma),
+        )
+        n_tiles = int(lib.rfi_plan_num_tiles(C.byref(plan)))
+        n0 = n_tiles * R
+        nh, nw = max(C_ // P, 1), max(T_ // P, 1)
+
+        with torch.cuda.device(device):
+            stream = current_stream_ptr(device)
+            fptr = flags.data_ptr() if flags is not None else None
+            # ---- phase 1: statistics + flag counts per original tile
+            stats = torch.empty((max(n_tiles, 1), _native.TILE_STAT_BYTES), dtype=torch.uint8, device=device)
+            rc = lib.rfi_tile_stats(C.byref(plan), data.data_ptr(), fptr, stats.data_ptr(), stream)
+            _native.check(rc, "rfi_tile_stats")
+            self.last_tile_stats = stats
+
+            # ---- host: blank-patch compaction + shuffle -> destination slot of every patch
+            if inference_mode:
+                order = np.arange(n0, dtype=np.int64)  # :345-353 keeps the canonical order
+            else:
+                nflag = stats[:n_tiles].view(torch.int32)[:, 16].cpu().numpy()  # n_flagged column
+                keep_tile = (nflag > 0).reshape(B * npol, nh, nw)
+                cmap = canonical_index_map(B * npol, R, nh, nw)
+                keep = np.zeros(n0, dtype=bool)
+                keep[cmap.ravel()] = np.broadcast_to(keep_tile[:, None], cmap.shape).ravel()
+                if keep.any():  # :752-756
+                    kept = np.flatnonzero(keep)
+                else:
+                    logger.warning("No flagged patches found - keeping all patches")
+                    kept = np.arange(n0, dtype=np.int64)
+                perm = np.random.permutation(len(kept))  # :760, the one RNG draw
+                order = kept[perm]
+            if num_patches and num_patches < len(order):  # :356-359
+                order = order[:num_patches]
+            n_out = len(order)
+            dest = np.full(max(n0, 1), -1, dtype=np.int64)
+            dest[order] = np.arange(n_out, dtype=np.int64)
+            dest_dev = torch.from_numpy(dest).to(device, non_blocking=True)
+
+            # ---- phase 2: every kept patch written once, at its final position
+            images = torch.empty((n_out, P if not skip_patchify else C_, P if not skip_patchify else T_, 3),
+                                 dtype=torch.float32, device=device)
+            labels = torch.empty(images.shape[:3], dtype=torch.uint8, device=device)
+            rc = lib.rfi_write_patches(C.byref(plan), data.data_ptr(), fptr, stats.data_ptr(),
+                                       dest_dev.data_ptr(), images.data_ptr(), labels.data_ptr(), stream)
+            _native.check(rc, "rfi_write_patches")
+
+        self.order = order  # canonical index of every output patch (not in the reference)
+        self.patch_flags = labels
+        self.patches = None  # processed patches are never materialised on this path
+        metadata = {  # :394-402
+            "patch_size": patch_size,
+            "stretch": stretch,
+            "flag_sigma": flag_sigma,
+            "normalize_before_stretch": normalize_before_stretch,
+            "normalize_after_stretch": normalize_after_stretch,
+            "augmentation_rotations": augmentation_rotations,
+            "original_shapes": getattr(self, "original_shapes", None),
+        }
+        self.dataset = TorchDataset(images, labels, metadata)
+        logger.info("Dataset ready: %d samples", len(self.dataset))
+        return self.dataset

@@ -1,0 +1,44 @@
+"""Device placement helpers.  PyTorch is used for device memory and streams only."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def require_cuda(device=None) -> torch.device:
+    """The product path has no CPU fallback: fail loudly without a CUDA device."""
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "rfi_toolbox_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback"
+        )
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(f"rfi_toolbox_b200 runs on CUDA devices only (got {device})")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
+def current_stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def as_device_tensor(x, device: torch.device, pin: bool = False) -> torch.Tensor:
+    """NumPy array / torch tensor (any device) -> contiguous tensor on `device`.
+    Host arrays go through one H2D copy (from pinned memory when `pin`)."""
+    if isinstance(x, torch.Tensor):
+        t = x.detach()
+    else:
+        a = np.asarray(x)
+        if not a.flags.c_contiguous:
+            a = np.ascontiguousarray(a)
+        if not a.flags.writeable:
+            a = a.copy()
+        t = torch.from_numpy(a)
+    if t.device != device:
+        if pin and t.device.type == "cpu" and not t.is_pinned():
+            t = t.pin_memory()
+        t = t.to(device, non_blocking=True)
+    return t.contiguous()
