@@ -75,6 +75,10 @@ def canonical_index_map(n_waterfalls, n_rot, nh, nw):
 class Preprocessor:
     """Preprocess waterfall data into training patches (preprocessor.py:139-196)."""
 
+    #: when True, CUDA events bracket the two kernels of every call (read by bench.py):
+    #: `self.events = {"stats": (start, stop), "write": (start, stop)}` on the current stream.
+    profile = False
+
     def __init__(self, data, flags=None, *, magnitude=False, device=None, pin=False):
         ndim = data.ndim
         if ndim == 3:
@@ -193,8 +197,13 @@ class Preprocessor:
             fptr = flags.data_ptr() if flags is not None else None
             # ---- phase 1: statistics + flag counts per original tile
             stats = torch.empty((max(n_tiles, 1), _native.TILE_STAT_BYTES), dtype=torch.uint8, device=device)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if self.profile else None
+            if ev:
+                ev[0].record()
             rc = lib.rfi_tile_stats(C.byref(plan), data.data_ptr(), fptr, stats.data_ptr(), stream)
             _native.check(rc, "rfi_tile_stats")
+            if ev:
+                ev[1].record()
             self.last_tile_stats = stats
 
             # ---- host: blank-patch compaction + shuffle -> destination slot of every patch
@@ -224,9 +233,14 @@ class Preprocessor:
             images = torch.empty((n_out, P if not skip_patchify else C_, P if not skip_patchify else T_, 3),
                                  dtype=torch.float32, device=device)
             labels = torch.empty(images.shape[:3], dtype=torch.uint8, device=device)
+            if ev:
+                ev[2].record()
             rc = lib.rfi_write_patches(C.byref(plan), data.data_ptr(), fptr, stats.data_ptr(),
                                        dest_dev.data_ptr(), images.data_ptr(), labels.data_ptr(), stream)
             _native.check(rc, "rfi_write_patches")
+            if ev:
+                ev[3].record()
+                self.events = {"stats": (ev[0], ev[1]), "write": (ev[2], ev[3])}
 
         self.order = order  # canonical index of every output patch (not in the reference)
         self.patch_flags = labels
