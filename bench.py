@@ -99,6 +99,9 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms from before the warm-up;
+    `window()` keeps the samples whose host timestamp falls inside the timed region (or,
+    when the region is shorter than the sampling period, the samples taken under load)."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -109,7 +112,8 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -117,22 +121,35 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc:
             self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+
+    def window(self, t0, t1):
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        rows = [r for t, r in self.rows if len(r) >= 9 and t0 <= t <= t1 + 0.06]
+        scope = "timed region"
+        if not rows:
+            rows = [r for t, r in self.rows if len(r) >= 9 and (num(r[3]) or 0) > 250.0]
+            scope = "under load (warm-up + timed region; region shorter than the sampling period)"
+        sm = [num(r[1]) for r in rows if num(r[1]) is not None]
+        mx = [num(r[2]) for r in rows if num(r[2]) is not None]
+        pw = [num(r[3]) for r in rows if num(r[3]) is not None]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) >= 9:
-                for n, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+        for r in rows:
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm),
+                "scope": scope}
 
 
 # ------------------------------------------------------------------------------------- GPU side
@@ -179,13 +196,13 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- resident-input arm
+    sampler = ClockSampler(local)
+    sampler.start()
     for i in range(args.warmup):
         pre, ds = step(cube, 0)
         evaluate_segmentation(ds.labels, truth, group=group)
         del ds
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern_ms = {"stats": [], "write": []}
     t0 = time.perf_counter()
@@ -198,8 +215,11 @@ def run_ours(args):
         del ds
     e1.record()
     barrier()
-    wall = time.perf_counter() - t0
-    clocks = sampler.stop()
+    t1 = time.perf_counter()
+    wall = t1 - t0
+    time.sleep(0.06)
+    sampler.stop()
+    clocks = sampler.window(t0, t1)
     dev_ms = e0.elapsed_time(e1)
     for ev in evs:
         for k in kern_ms:

@@ -97,6 +97,14 @@ RFI_DEVINL T cabs_np(T re, T im) {
     return Scalar<T>::sqrt_rn(Scalar<T>::fma(r, r, T(1))) * hi;
 }
 
+// NumPy's median of n values whose two middle order statistics are (a, b).
+template <typename T>
+RFI_DEVINL T median_of_pair(T a, T b, uint32_t n) {
+    if (n & 1u) return a;
+    T sum = a + b;
+    return sum * T(0.5);
+}
+
 // keys of +inf / -inf
 template <typename T>
 __host__ __device__ constexpr typename Scalar<T>::key_t to_key_const_inf(bool negative) {
@@ -234,19 +242,63 @@ RFI_DEVINL void block_nanminmax(T& lo, T& hi, BlockScratch<NT>& s, int& parity) 
 }
 
 // ----------------------------------------------------------------------------------------
+// Round counters: block-wide sum of one u32 per thread with ONE barrier and ~6 instructions
+// per thread: warp REDUX, one shared atomic per warp into a rotating counter, barrier, one
+// broadcast load.  Four counters rotate; counter (r+2)&3 is cleared right after round r's
+// barrier (its last readers passed barrier r-1, its next writers start after barrier r+1).
+struct RoundCounter {
+    uint32_t c[4];
+    int pad[4];
+};
+RFI_DEVINL void round_init(RoundCounter& rc) {
+    if (threadIdx.x < 4) rc.c[threadIdx.x] = 0;
+    __syncthreads();
+}
+RFI_DEVINL uint32_t round_sum(uint32_t v, RoundCounter& rc, int& r) {
+    v = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&rc.c[r & 3], v);
+    __syncthreads();
+    const uint32_t t = rc.c[r & 3];
+    if (threadIdx.x == 0) rc.c[(r + 2) & 3] = 0;
+    ++r;
+    return t;
+}
+
+// count += (key < trial), as ISETP (ALU pipe) + predicated FADD (FMA pipe): the two pipes
+// each retire one warp instruction every other cycle per sub-partition, so this pairing
+// issues at full rate where an integer add would serialise on the ALU pipe.
+RFI_DEVINL void count_lt(float& c, uint32_t key, uint32_t trial) {
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p add.f32 %0, %0, 0f3F800000;\n\t}"
+        : "+f"(c) : "r"(key), "r"(trial));
+}
+RFI_DEVINL void count_lt(float& c, unsigned long long key, unsigned long long trial) {
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.u64 p, %1, %2;\n\t@p add.f32 %0, %0, 0f3F800000;\n\t}"
+        : "+f"(c) : "l"(key), "l"(trial));
+}
+RFI_DEVINL void count_le(float& c, uint32_t key, uint32_t trial) {
+    asm("{\n\t.reg .pred p;\n\tsetp.le.u32 p, %1, %2;\n\t@p add.f32 %0, %0, 0f3F800000;\n\t}"
+        : "+f"(c) : "r"(key), "r"(trial));
+}
+RFI_DEVINL void count_le(float& c, unsigned long long key, unsigned long long trial) {
+    asm("{\n\t.reg .pred p;\n\tsetp.le.u64 p, %1, %2;\n\t@p add.f32 %0, %0, 0f3F800000;\n\t}"
+        : "+f"(c) : "l"(key), "l"(trial));
+}
+
+// ----------------------------------------------------------------------------------------
 // Register-resident exact selection.
 //
 // Each of the NT threads holds E keys; excluded samples carry the all-ones key and are not
-// counted in n.  block_select2 returns the keys of 0-based ranks k and min(k+1, n-1)... the
-// caller asks for the two middle order statistics of NumPy's median.
+// counted in n.  block_select2 returns the keys of 0-based ranks k1 and k2 (k2 = k1 or k1+1:
+// the two middle order statistics of NumPy's median).
 //
 // Method: MSB-first binary radix select ("bit bisection").  Round b asks how many keys are
 // below prefix|1<<b; a round costs 2 instructions per key and one block reduction, no
-// shared-memory atomics (ATOMS retires ~0.5 key/clk/SM on Blackwell, 20x slower than this).
-// The leading bits shared by min and max are skipped.
+// shared-memory histogram (ATOMS retires ~0.5 key/clk/SM on Blackwell, ~20x slower than
+// this).  The leading bits shared by min and max are skipped.
 template <int NT, int E, typename K>
 RFI_DEVINL void block_select2(const K (&key)[E], uint32_t n, uint32_t k1, uint32_t k2,
-                              K& out1, K& out2, BlockScratch<NT>& s, int& parity) {
+                              K& out1, K& out2, BlockScratch<NT>& s, int& parity,
+                              RoundCounter& rc, int& round) {
     constexpr K kExcl = ~K(0);
     constexpr int kBits = sizeof(K) * 8;
     if (n == 0) {  // uniform: n comes from a block reduction
@@ -268,12 +320,18 @@ RFI_DEVINL void block_select2(const K (&key)[E], uint32_t n, uint32_t k1, uint32
         int hb = (kBits - 1) - (sizeof(K) == 8 ? __clzll((long long)diff) : __clz((int)diff));
         K below = (hb == kBits - 1) ? K(0) : (lo >> (hb + 1)) << (hb + 1);
         prefix = below;
+#pragma unroll 1
         for (int b = hb; b >= 0; --b) {
-            K trial = prefix | (K(1) << b);
-            uint32_t c = 0;
+            const K trial = prefix | (K(1) << b);
+            float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
 #pragma unroll
-            for (int e = 0; e < E; ++e) c += (key[e] < trial) ? 1u : 0u;
-            c = block_sum<NT>(c, s, parity);
+            for (int e = 0; e < E; e += 4) {
+                count_lt(c0, key[e], trial);
+                count_lt(c1, key[e + 1], trial);
+                count_lt(c2, key[e + 2], trial);
+                count_lt(c3, key[e + 3], trial);
+            }
+            const uint32_t c = round_sum((uint32_t)((c0 + c1) + (c2 + c3)), rc, round);
             if (c <= k1) prefix = trial;
         }
     }
@@ -283,34 +341,44 @@ RFI_DEVINL void block_select2(const K (&key)[E], uint32_t n, uint32_t k1, uint32
         return;
     }
     // rank k1+1: same key if duplicates reach it, else the smallest key above.
-    uint32_t cle = 0;
+    float cle = 0.f;
     K nxt = kExcl;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         K x = key[e];
-        cle += (x <= prefix) ? 1u : 0u;
+        count_le(cle, x, prefix);
         K y = (x > prefix) ? x : kExcl;
         nxt = y < nxt ? y : nxt;
     }
-    cle = block_sum<NT>(cle, s, parity);
+    const uint32_t ncle = round_sum((uint32_t)cle, rc, round);
+    if (k2 < ncle) {  // uniform
+        out2 = prefix;
+        return;
+    }
     K dummy = 0;
     block_minmax_key<NT, K>(nxt, dummy, s, parity);
-    out2 = (k2 < cle) ? prefix : nxt;
+    out2 = nxt;
 }
 
 // NumPy median of the n valid keys held by the block: mean of the two middle order
 // statistics in T ((a + b) / 2 with one rounding of the sum), NaN when n == 0.
+// The two order statistics themselves are returned through lo_key / hi_key.
 template <typename T, int NT, int E>
 RFI_DEVINL T block_median(const typename Scalar<T>::key_t (&key)[E], uint32_t n,
-                          BlockScratch<NT>& s, int& parity) {
+                          BlockScratch<NT>& s, int& parity, RoundCounter& rc, int& round,
+                          typename Scalar<T>::key_t* lo_key = nullptr,
+                          typename Scalar<T>::key_t* hi_key = nullptr) {
     using K = typename Scalar<T>::key_t;
-    if (n == 0) return Scalar<T>::nan();
+    if (n == 0) {
+        if (lo_key) *lo_key = ~K(0);
+        if (hi_key) *hi_key = ~K(0);
+        return Scalar<T>::nan();
+    }
     K a, b;
-    block_select2<NT, E, K>(key, n, (n - 1) >> 1, n >> 1, a, b, s, parity);
-    T va = from_key<T>(a), vb = from_key<T>(b);
-    if (((n - 1) >> 1) == (n >> 1)) return va;
-    T sum = va + vb;
-    return sum * T(0.5);
+    block_select2<NT, E, K>(key, n, (n - 1) >> 1, n >> 1, a, b, s, parity, rc, round);
+    if (lo_key) *lo_key = a;
+    if (hi_key) *hi_key = b;
+    return median_of_pair<T>(from_key<T>(a), from_key<T>(b), n);
 }
 
 }  // namespace rfi

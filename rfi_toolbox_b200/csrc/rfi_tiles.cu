@@ -12,6 +12,8 @@
 // Reference semantics: rfi_toolbox/preprocessing/preprocessor.py:22-42, 413-446, 562-783
 // (restated in SURVEY.md Appendix A).  Statistics are rotation invariant for dims divisible
 // by P, so they are computed once per original tile and shared by the R rotated patches.
+#include <type_traits>
+
 #include "rfi_common.cuh"
 
 namespace rfi {
@@ -104,6 +106,14 @@ RFI_DEVINL T process_sample(T a, const PlanDev& p, T med_before, T inf_fill, T m
 // recovered with from_key() when arithmetic is needed (the map is a bijection on non-NaN
 // floats), so a select never doubles the register footprint.  Shared memory is only a
 // stash for the processed values while the |x - median| keys occupy the registers.
+//
+// Order-statistic shortcut (identity (ii)): for non-negative finite
+// input every stage (x / m with m > 0, sqrt, log10) is monotone non-decreasing after
+// rounding, so the two middle order statistics of the processed tile are the images of the
+// two middle order statistics of the raw tile.  One select on the raw magnitudes then
+// serves the normalisation median AND the flag centre; only the MAD needs a second select.
+// The shortcut is dropped (general selects) as soon as a tile has a negative, infinite or
+// inf-filled sample.
 template <int DT, int NT>
 __global__ void __launch_bounds__(NT, (sizeof(typename In<DT>::T) == 4) ? 2 : 1)
 tile_stats_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __restrict__ flags,
@@ -114,10 +124,14 @@ tile_stats_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __res
     constexpr int G = E / 4;         // groups of 4 consecutive samples
     constexpr int RS = NT / 32;      // rows covered per group step
     constexpr K kExcl = ~K(0);
+    constexpr K kPosInf = to_key_const_inf<T>(false), kNegInf = to_key_const_inf<T>(true);
+    constexpr K kNegZero = (K(1) << (Scalar<T>::kBits - 1)) - 1;  // key(-0.0); key(+0.0) is one above
     extern __shared__ __align__(16) unsigned char smem_raw[];
     K* stash = reinterpret_cast<K*>(smem_raw);  // [E][NT]
     __shared__ BlockScratch<NT> scr;
-    int parity = 0;
+    __shared__ RoundCounter rc;
+    int parity = 0, round = 0;
+    round_init(rc);
 
     const long long tile = blockIdx.x;
     const int per = p.nh * p.nw;
@@ -141,32 +155,47 @@ tile_stats_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __res
     st.centre = st.mad = st.thr_lo = st.thr_hi = 0.0;
     st.n_inf = 0; st.n_flagged = 0; st.reserved = 0;
 
-    // non-NaN samples (recounted before every median: inf / inf can create a NaN)
+    // non-NaN samples (recounted before every general median: inf / inf can create a NaN)
     auto count_valid = [&]() {
         uint32_t c = 0;
 #pragma unroll
         for (int e = 0; e < E; ++e) c += (a[e] != kExcl) ? 1u : 0u;
-        return block_sum<NT>(c, scr, parity);
+        return round_sum(c, rc, round);
     };
-    uint32_t nv = count_valid();
+    uint32_t nv, nodd;  // valid samples; samples that break the shortcut (negative or +inf)
+    {
+        uint32_t c = 0, o = 0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            c += (a[e] != kExcl) ? 1u : 0u;
+            o += (a[e] < kNegZero || a[e] == kPosInf) ? 1u : 0u;
+        }
+        nv = round_sum(c, rc, round);
+        nodd = round_sum(o, rc, round);
+    }
     st.n_valid = (int)nv;
 
     const bool real_branch = !In<DT>::cplx || p.magnitude;
+    bool shortcut = false;  // (v1, v2) are the two middle order statistics of the current tile
+    T v1 = T(0), v2 = T(0);
 
     if (real_branch) {
         // ---- normalise by the median (preprocessor.py:646-670)
         if (p.norm_before) {
-            T m = block_median<T, NT, E>(a, nv, scr, parity);
+            K k1, k2;
+            T m = block_median<T, NT, E>(a, nv, scr, parity, rc, round, &k1, &k2);
             st.median_before = (double)m;
+            shortcut = (nodd == 0) && (nv > 0);
+            v1 = from_key<T>(k1); v2 = from_key<T>(k2);
             if (m > T(0)) {
 #pragma unroll
                 for (int e = 0; e < E; ++e) a[e] = to_key<T>(from_key<T>(a[e]) / m);
+                v1 = v1 / m; v2 = v2 / m;
             }
         }
         // ---- stretch, +-inf := MAD of the finite values (preprocessor.py:672-706)
         if (p.stretch != RFI_STRETCH_NONE) {
             uint32_t ninf = 0, nfin = 0;
-            constexpr K kPosInf = to_key_const_inf<T>(false), kNegInf = to_key_const_inf<T>(true);
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 a[e] = to_key<T>(apply_stretch<T>(from_key<T>(a[e]), p.stretch));
@@ -174,20 +203,23 @@ tile_stats_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __res
                 ninf += inf ? 1u : 0u;
                 nfin += (!inf && a[e] != kExcl) ? 1u : 0u;
             }
-            block_sum2<NT>(ninf, nfin, scr, parity);
+            v1 = apply_stretch<T>(v1, p.stretch); v2 = apply_stretch<T>(v2, p.stretch);
+            ninf = round_sum(ninf, rc, round);
             st.n_inf = (int)ninf;
             if (ninf > 0) {
+                shortcut = false;
+                nfin = round_sum(nfin, rc, round);
                 T fill = T(0);
                 if (nfin > 0) {
 #pragma unroll
                     for (int e = 0; e < E; ++e) stash[e * NT + threadIdx.x] = a[e];
 #pragma unroll
                     for (int e = 0; e < E; ++e) a[e] = (a[e] == kPosInf || a[e] == kNegInf) ? kExcl : a[e];
-                    T c = block_median<T, NT, E>(a, nfin, scr, parity);
+                    T c = block_median<T, NT, E>(a, nfin, scr, parity, rc, round);
 #pragma unroll
                     for (int e = 0; e < E; ++e)
                         a[e] = (a[e] == kExcl) ? kExcl : to_key<T>(fabs_(from_key<T>(a[e]) - c));
-                    fill = block_median<T, NT, E>(a, nfin, scr, parity);
+                    fill = block_median<T, NT, E>(a, nfin, scr, parity, rc, round);
 #pragma unroll
                     for (int e = 0; e < E; ++e) a[e] = stash[e * NT + threadIdx.x];
                 }
@@ -199,11 +231,19 @@ tile_stats_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __res
         }
         // ---- normalise again (preprocessor.py:309-311)
         if (p.norm_after) {
-            T m2 = block_median<T, NT, E>(a, count_valid(), scr, parity);
+            T m2;
+            if (shortcut) {
+                m2 = median_of_pair<T>(v1, v2, nv);
+            } else {
+                K k1, k2;
+                const uint32_t n2 = count_valid();
+                m2 = block_median<T, NT, E>(a, n2, scr, parity, rc, round, &k1, &k2);
+            }
             st.median_after = (double)m2;
             if (m2 > T(0)) {
 #pragma unroll
                 for (int e = 0; e < E; ++e) a[e] = to_key<T>(from_key<T>(a[e]) / m2);
+                v1 = v1 / m2; v2 = v2 / m2;
             }
         }
     }
@@ -211,13 +251,19 @@ tile_stats_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __res
     if (p.flag_mode == RFI_FLAGS_MAD) {
         // ---- MAD flags on the processed tile (preprocessor.py:708-745; |z| first for
         //      complex input, :126-127)
-        const uint32_t nn = count_valid();
-        T c = block_median<T, NT, E>(a, nn, scr, parity);
+        uint32_t nn = nv;
+        T c;
+        if (shortcut) {
+            c = median_of_pair<T>(v1, v2, nv);
+        } else {
+            nn = count_valid();
+            c = block_median<T, NT, E>(a, nn, scr, parity, rc, round);
+        }
 #pragma unroll
         for (int e = 0; e < E; ++e) stash[e * NT + threadIdx.x] = a[e];
 #pragma unroll
         for (int e = 0; e < E; ++e) a[e] = to_key<T>(fabs_(from_key<T>(a[e]) - c));
-        T d = block_median<T, NT, E>(a, nn, scr, parity);
+        T d = block_median<T, NT, E>(a, nn, scr, parity, rc, round);
         T ds = d * (T)p.sigma;
         T hi = c + ds, lo = c - ds;
         uint32_t nf = 0;
@@ -226,7 +272,7 @@ tile_stats_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __res
             T x = from_key<T>(stash[e * NT + threadIdx.x]);
             nf += ((x > hi) || (x < lo)) ? 1u : 0u;
         }
-        nf = block_sum<NT>(nf, scr, parity);
+        nf = round_sum(nf, rc, round);
         st.centre = (double)c; st.mad = (double)d;
         st.thr_lo = (double)lo; st.thr_hi = (double)hi;
         st.n_flagged = (int)nf;
@@ -239,7 +285,7 @@ tile_stats_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __res
             uint32_t nz = (((f4 & 0x7f7f7f7fu) + 0x7f7f7f7fu) | f4) & 0x80808080u;
             nf += __popc(nz);
         }
-        nf = block_sum<NT>(nf, scr, parity);
+        nf = round_sum(nf, rc, round);
         st.n_flagged = (int)nf;
     }
     if (threadIdx.x == 0) stats[tile] = st;
@@ -250,8 +296,9 @@ template <int NT>
 __global__ void __launch_bounds__(NT)
 flags_count_kernel(PlanDev p, const uint8_t* __restrict__ flags, rfi_tile_stat_t* __restrict__ stats) {
     constexpr int G = kP * kP / NT / 4, RS = NT / 32;
-    __shared__ BlockScratch<NT> scr;
-    int parity = 0;
+    __shared__ RoundCounter rc;
+    int round = 0;
+    round_init(rc);
     const long long tile = blockIdx.x;
     const int per = p.nh * p.nw;
     const long long w = tile / per;
@@ -268,7 +315,7 @@ flags_count_kernel(PlanDev p, const uint8_t* __restrict__ flags, rfi_tile_stat_t
             nf += __popc(nz);
         }
     }
-    nf = block_sum<NT>(nf, scr, parity);
+    nf = round_sum(nf, rc, round);
     if (threadIdx.x == 0) {
         rfi_tile_stat_t st;
         st.median_before = st.inf_fill = st.median_after = 0.0;
@@ -280,10 +327,45 @@ flags_count_kernel(PlanDev p, const uint8_t* __restrict__ flags, rfi_tile_stat_t
 
 // ------------------------------------------------------------------------------------------
 // phase 2
+//
+// Numerics of the image channels (DESIGN.md "numerics"): labels depend only on the processed
+// sample and the phase-1 thresholds, and are recomputed here with the very same IEEE ops, so
+// they are bit-exact.  The three image channels are tolerance-class (1e-6 relative) because
+// they sit downstream of log10, which NumPy itself does not compute reproducibly; they use
+//   min-max:   (v - lo) * RN(1 / range)            instead of (v - lo) / range
+//   ImageNet:  fma(u, RN(1 / std), RN(-mean / std)) instead of (u - mean) / std
+//   gradient:  sqrt.approx (<= 1 ulp) of td^2 + fd^2
+// which keeps every value within ~2 ulp of the reference chain at a quarter of the issue slots.
 template <typename T> struct Phase2Smem {
-    static constexpr int kPitch = kP + 1;    // conflict-free row AND column access
+    static constexpr int kPitch = kP + 1;      // conflict-free row AND column access
     static constexpr int kFlagPitch = kP + 4;  // bytes; 33 words -> column reads hit 32 banks
 };
+
+RFI_DEVINL float sqrt_fast(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+RFI_DEVINL double sqrt_fast(double x) { return __dsqrt_rn(x); }
+
+// log10 for the image channel: float32 accurate to 2 ulp (CUDA log10f); fp64 unchanged.
+RFI_DEVINL float log10_img(float x) { return log10f(x); }
+RFI_DEVINL double log10_img(double x) { return ::log10(x); }
+
+template <typename T>
+struct ChanScale {      // u = (v - lo) * inv  (0 when the channel is flat), then ImageNet
+    T lo, inv;
+    bool ok;
+};
+
+template <typename T>
+RFI_DEVINL ChanScale<T> make_scale(T lo, T hi) {
+    ChanScale<T> c;
+    c.ok = hi > lo;     // false for NaN too: nanmin/nanmax of an all-NaN channel
+    c.lo = lo;
+    c.inv = c.ok ? T(1) / (hi - lo) : T(0);
+    return c;
+}
 
 template <int DT, int NT, bool kComplexBranch>
 __global__ void __launch_bounds__(NT, (sizeof(typename In<DT>::T) == 4 && !kComplexBranch) ? 2 : 1)
@@ -316,14 +398,13 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
     const long long base = w * R * per;
 
     // canonical patch index of each rotation of this tile
-    long long slot[4] = {-1, -1, -1, -1};
-    slot[0] = dest_slot[base + (long long)ti * p.nw + tj];
-    if (R >= 2) slot[1] = dest_slot[base + per + (long long)(p.nh - 1 - ti) * p.nw + tj];
+    long long slot0 = dest_slot[base + (long long)ti * p.nw + tj], slot1 = -1, slot2 = -1, slot3 = -1;
+    if (R >= 2) slot1 = dest_slot[base + per + (long long)(p.nh - 1 - ti) * p.nw + tj];
     if (R >= 4) {
-        slot[2] = dest_slot[base + 2LL * per + (long long)tj * p.nh + ti];
-        slot[3] = dest_slot[base + 3LL * per + (long long)(p.nw - 1 - tj) * p.nh + ti];
+        slot2 = dest_slot[base + 2LL * per + (long long)tj * p.nh + ti];
+        slot3 = dest_slot[base + 3LL * per + (long long)(p.nw - 1 - tj) * p.nh + ti];
     }
-    if (slot[0] < 0 && slot[1] < 0 && slot[2] < 0 && slot[3] < 0) return;
+    if (slot0 < 0 && slot1 < 0 && slot2 < 0 && slot3 < 0) return;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t origin = ((size_t)w * p.channels + (size_t)ti * kP) * p.times + (size_t)tj * kP;
@@ -331,6 +412,11 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
     const T med_before = (T)st.median_before, inf_fill = (T)st.inf_fill, med_after = (T)st.median_after;
     const T thr_lo = (T)st.thr_lo, thr_hi = (T)st.thr_hi;
     const bool real_branch = !kComplexBranch;
+
+    const float mean0 = 0.485f, mean1 = 0.456f, mean2 = 0.406f;
+    const float std0 = 0.229f, std1 = 0.224f, std2 = 0.225f;
+    const float is0 = 1.0f / std0, is1 = 1.0f / std1;
+    const float nb0 = (0.0f - mean0) / std0, nb1 = (0.0f - mean1) / std1, nb2 = (0.0f - mean2) / std2;
 
     // ---- pass A: processed sample -> log amplitude tile, label tile, min/max of L
     T llo = Scalar<T>::nan(), lhi = Scalar<T>::nan();
@@ -348,13 +434,13 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
             unsigned char f = 0;
             if (p.flag_mode == RFI_FLAGS_MAD) f = ((x > thr_hi) || (x < thr_lo)) ? 1 : 0;
             else if (p.flag_mode == RFI_FLAGS_CUSTOM) f = __ldg(flags + idx);
-            T L = Scalar<T>::log10_(fabs_(x) + T(1e-10));
+            T L = log10_img(fabs_(x) + T(1e-10));
             Ls[row * LP + col] = L;
             Fb[row * FP + col] = f;
             if constexpr (kComplexBranch) {
-                // (phase + pi) / (2 pi) in T, then the reference's cast to float32
+                // (phase + pi) / (2 pi) in T, cast to float32, then ImageNet (rotation invariant)
                 T c2 = (ph + T(3.141592653589793)) / T(6.283185307179586);
-                Ph[row * LP + col] = (float)c2;
+                Ph[row * LP + col] = ((float)c2 - mean2) / std2;
             } else {
                 llo = Scalar<T>::fmin_nan(llo, L);
                 lhi = Scalar<T>::fmax_nan(lhi, L);
@@ -397,66 +483,52 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
     if constexpr (!kComplexBranch) block_nanminmax<NT, T>(llo, lhi, scr, parity);
 
     // sqrt is monotone: min/max of g = sqrt(min/max of g^2)
-    T glo[4], grng[4];
-    bool gok[4];
-    {
-        T lo0 = Scalar<T>::sqrt_rn(s0lo), hi0 = Scalar<T>::sqrt_rn(s0hi);
-        T lo1 = Scalar<T>::sqrt_rn(s1lo), hi1 = Scalar<T>::sqrt_rn(s1hi);
-        T lo3 = Scalar<T>::sqrt_rn(s3lo), hi3 = Scalar<T>::sqrt_rn(s3hi);
-        glo[0] = lo0; grng[0] = hi0 - lo0; gok[0] = hi0 > lo0;
-        glo[1] = lo1; grng[1] = hi1 - lo1; gok[1] = hi1 > lo1;
-        glo[2] = lo0; grng[2] = hi0 - lo0; gok[2] = hi0 > lo0;
-        glo[3] = lo3; grng[3] = hi3 - lo3; gok[3] = hi3 > lo3;
-    }
-    const T lrng = lhi - llo;
-    const bool lok = lhi > llo;
-
-    const float mean0 = 0.485f, mean1 = 0.456f, mean2 = 0.406f;
-    const float std0 = 0.229f, std1 = 0.224f, std2 = 0.225f;
-    const float ch2_real = (0.0f - mean2) / std2;
+    const ChanScale<T> g0 = make_scale<T>(sqrt_fast(s0lo), sqrt_fast(s0hi));
+    const ChanScale<T> g1 = make_scale<T>(sqrt_fast(s1lo), sqrt_fast(s1hi));
+    const ChanScale<T> g3 = make_scale<T>(sqrt_fast(s3lo), sqrt_fast(s3hi));
+    const ChanScale<T> ls = make_scale<T>(llo, lhi);
 
     float* wstage = stage + (size_t)warp * 3 * kP;
     unsigned char* wl = lstage + (size_t)warp * kP;
 
-    // ---- pass C: every kept rotation, one output row per warp per step
-#pragma unroll 1
-    for (int r = 0; r < R; ++r) {
-        const long long sl = slot[r];
-        if (sl < 0) continue;  // uniform across the block
+    // ---- pass C: every kept rotation, one output row per warp per step.  `rot` is a
+    // compile-time constant so the source / neighbour index arithmetic folds away.
+    auto emit = [&](auto rot_tag, long long sl, const ChanScale<T>& gs) {
+        constexpr int rot = decltype(rot_tag)::value;
+        if (sl < 0) return;  // uniform across the block
         float* out_img = images + (size_t)sl * kP * kP * 3;
         unsigned char* out_lab = labels + (size_t)sl * kP * kP;
-        const T lo_r = glo[r], rng_r = grng[r];
-        const bool ok_r = gok[r];
 #pragma unroll 1
         for (int s = 0; s < STEPS; ++s) {
             const int orow = s * RS + warp;  // output row i'
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
                 const int ocol = lane + 32 * q;  // output column j'
-                int i, j, ai, aj, bi_, bj_;
-                // (i, j): source sample; (ai, aj): neighbour of the row-derivative (zero on
-                // output row 0); (bi_, bj_): neighbour of the column-derivative (zero on col 0)
-                if (r == 0) { i = orow; j = ocol; ai = i - 1; aj = j; bi_ = i; bj_ = j - 1; }
-                else if (r == 1) { i = kP - 1 - orow; j = ocol; ai = i + 1; aj = j; bi_ = i; bj_ = j - 1; }
-                else if (r == 2) { i = ocol; j = orow; ai = i; aj = j - 1; bi_ = i - 1; bj_ = j; }
-                else { i = ocol; j = kP - 1 - orow; ai = i; aj = j + 1; bi_ = i - 1; bj_ = j; }
-                const T c = Ls[i * LP + j];
-                const T td = (orow > 0) ? c - Ls[ai * LP + aj] : T(0);
-                const T fd = (ocol > 0) ? c - Ls[bi_ * LP + bj_] : T(0);
-                const T g = Scalar<T>::sqrt_rn(td * td + fd * fd);
-                const T c0 = ok_r ? (g - lo_r) / rng_r : T(0);
-                float o0 = ((float)c0 - mean0) / std0, o1, o2;
+                // (i, j): source sample; da: offset of the row-derivative neighbour (zero on
+                // output row 0); db: offset of the column-derivative neighbour (zero on col 0)
+                int i, j, da, db;
+                if constexpr (rot == 0) { i = orow; j = ocol; da = -LP; db = -1; }
+                else if constexpr (rot == 1) { i = kP - 1 - orow; j = ocol; da = LP; db = -1; }
+                else if constexpr (rot == 2) { i = ocol; j = orow; da = -1; db = -LP; }
+                else { i = ocol; j = kP - 1 - orow; da = 1; db = -LP; }
+                const int at = i * LP + j;
+                const T c = Ls[at];
+                const T td = (orow > 0) ? c - Ls[at + da] : T(0);
+                const T fd = (ocol > 0) ? c - Ls[at + db] : T(0);
+                const T g = sqrt_fast(td * td + fd * fd);
+                const float u0 = (float)((g - gs.lo) * gs.inv);
+                float o1, o2;
                 if constexpr (kComplexBranch) {
-                    T u = (c - T(-3.0)) / T(7.0);
+                    T u = (c - T(-3.0)) * T(1.0 / 7.0);
                     u = u < T(0) ? T(0) : (u > T(1) ? T(1) : u);  // np.clip keeps NaN
-                    o1 = ((float)u - mean1) / std1;
-                    o2 = (Ph[i * LP + j] - mean2) / std2;
+                    o1 = __fmaf_rn((float)u, is1, nb1);
+                    o2 = Ph[at];
                 } else {
-                    const T u = lok ? (c - llo) / lrng : T(0);
-                    o1 = ((float)u - mean1) / std1;
-                    o2 = ch2_real;
+                    const float u1 = (float)((c - ls.lo) * ls.inv);
+                    o1 = __fmaf_rn(u1, is1, nb1);
+                    o2 = nb2;
                 }
-                wstage[ocol * 3 + 0] = o0;
+                wstage[ocol * 3 + 0] = __fmaf_rn(u0, is0, nb0);
                 wstage[ocol * 3 + 1] = o1;
                 wstage[ocol * 3 + 2] = o2;
                 wl[ocol] = Fb[i * FP + j];
@@ -471,7 +543,11 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
                     reinterpret_cast<const uint4*>(wl)[lane];
             __syncwarp();
         }
-    }
+    };
+    emit(std::integral_constant<int, 0>{}, slot0, g0);
+    emit(std::integral_constant<int, 1>{}, slot1, g1);
+    emit(std::integral_constant<int, 2>{}, slot2, g0);
+    emit(std::integral_constant<int, 3>{}, slot3, g3);
 }
 
 // ------------------------------------------------------------------------------------------
