@@ -162,3 +162,36 @@ def test_tile_statistics_exact(native_lib):
         assert np.float32(st["mad"][k]) == d
         assert np.float32(st["thr_hi"][k]) == c + d * 5
         assert st["n_flagged"][k] == int(((s > c + d * 5) | (s < c - d * 5)).sum())
+
+
+# ---------------------------------------------------------------------------------------------
+# committed golden vectors (outputs of the unmodified reference, tests/golden/make_golden.py)
+from tests.golden_util import CASE_NAMES, HOST_DEPENDENT_LABELS, load_case  # noqa: E402
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_golden_fixture(native_lib, name):
+    from rfi_toolbox_b200 import Preprocessor, compute_ffi, compute_statistics, evaluate_segmentation
+    c = load_case(name)
+    np.random.seed(c["perm_seed"])
+    pre = Preprocessor(c["cube"] if c["info"]["abs"] else c["data"], c["flags"], magnitude=c["info"]["abs"])
+    ds = pre.create_dataset(**c["kwargs"])
+    labels = ds.labels.cpu().numpy()
+    images = ds.images.cpu().numpy()
+    assert labels.shape == c["labels"].shape
+    if name in HOST_DEPENDENT_LABELS:
+        assert (labels != c["labels"]).mean() < 1e-4
+    else:
+        assert np.array_equal(labels, c["labels"])
+    assert np.allclose(images.reshape(-1)[c["image_pos"]], c["image_val"], rtol=1e-6, atol=2e-5, equal_nan=True)
+    assert int(np.isnan(images).sum()) == c["image_nan_count"]
+    pred = c["labels"].astype(bool)
+    truth = pred ^ (np.random.default_rng(9).random(pred.shape) < 0.02)
+    ev = evaluate_segmentation(pred, truth)
+    for k, v in c["evaluation"].items():
+        assert float(ev[k]) == v
+    ffi, st = compute_ffi(c["cube"], c["mask"]), compute_statistics(c["cube"], c["mask"])
+    for k, v in c["ffi"].items():
+        assert ffi[k] == pytest.approx(v, rel=1e-6, abs=1e-9, nan_ok=True)
+    for k, v in c["stats"].items():
+        assert float(st[k]) == pytest.approx(v, rel=1e-6, nan_ok=True)

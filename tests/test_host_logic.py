@@ -1,0 +1,97 @@
+"""Host-side logic of the drop-in API (no GPU): index maps, patchify known answers, metric
+ratios, container behaviour, argument validation, and 'no CPU fallback'."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from rfi_toolbox_b200.datasets import TorchDataset
+from rfi_toolbox_b200.evaluation.metrics import _ratios
+from rfi_toolbox_b200.preprocessing import Preprocessor, canonical_index_map, patchify
+
+
+class TestPatchify:
+    """Same known answers as the reference's tests/test_preprocessing.py:14-66."""
+
+    def test_basic_shape(self):
+        assert patchify(np.arange(16).reshape(4, 4), (2, 2), step=2).shape == (2, 2, 2, 2)
+
+    def test_content(self):
+        p = patchify(np.arange(16).reshape(4, 4), (2, 2), step=2)
+        np.testing.assert_array_equal(p[0, 0], [[0, 1], [4, 5]])
+        np.testing.assert_array_equal(p[1, 1], [[10, 11], [14, 15]])
+
+    def test_large(self):
+        assert patchify(np.random.rand(1024, 1024), (128, 128), step=128).shape == (8, 8, 128, 128)
+
+    def test_non_square(self):
+        assert patchify(np.arange(24).reshape(6, 4), (2, 2), step=2).shape == (3, 2, 2, 2)
+
+    def test_single(self):
+        a = np.arange(4).reshape(2, 2)
+        p = patchify(a, (2, 2), step=2)
+        assert p.shape == (1, 1, 2, 2)
+        np.testing.assert_array_equal(p[0, 0], a)
+
+    def test_dtype(self):
+        assert patchify(np.array([[1.5, 2.5], [3.5, 4.5]], dtype=np.float32), (2, 2), step=2).dtype == np.float32
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1, 1), (3, 4, 2, 3), (2, 2, 8, 1)])
+@pytest.mark.parametrize("rot", [1, 2, 4])
+def test_canonical_index_map(shape, rot):
+    nwf, _, nh, nw = shape
+    a = canonical_index_map(nwf, rot, nh, nw)
+    assert np.array_equal(a, oracle.canonical_index_map(nwf, rot, nh, nw))
+    assert sorted(a.ravel().tolist()) == list(range(nwf * rot * nh * nw))  # a permutation
+
+
+def test_effective_rotations():
+    f = Preprocessor._effective_rotations
+    assert [f(True, r) for r in (0, 1, 2, 3, 4, 8)] == [1, 1, 2, 2, 4, 4]
+    assert f(False, 4) == 1
+
+
+def test_ratios_match_oracle_formulas():
+    rng = np.random.default_rng(0)
+    triples = [(0, 0, 0), (0, 5, 0), (0, 0, 7), (3, 0, 0), (1, 2, 3), (2**40, 2**41, 3)]
+    triples += [tuple(int(v) for v in rng.integers(0, 1000, 3)) for _ in range(200)]
+    for tp, fp, fn in triples:
+        a, b = _ratios(tp, fp, fn), oracle.metrics_from_counts(tp, fp, fn)
+        assert a == b and all(type(a[k]) is type(b[k]) for k in a)
+
+
+def test_torch_dataset_contract(tmp_path):
+    img = torch.zeros((3, 4, 4, 3), dtype=torch.float32)
+    lab = torch.ones((3, 4, 4), dtype=torch.uint8)
+    ds = TorchDataset(img, lab, {"patch_size": 4})
+    assert len(ds) == 3 and set(ds[0]) == {"image", "label"} and ds[0]["image"].shape == (4, 4, 3)
+    assert ds["data"].shape == (3, 3, 4, 4) and ds["labels"] is ds.labels and ds["metadata"]["patch_size"] == 4
+    with pytest.raises(AssertionError):
+        TorchDataset(img.double(), lab)
+    with pytest.raises(AssertionError):
+        TorchDataset(img, lab.int())
+    with pytest.raises(AssertionError):
+        TorchDataset(img[:2], lab)
+    ds.save_to_disk(tmp_path / "d.pt")
+    back = TorchDataset.load_from_disk(tmp_path / "d.pt")
+    assert torch.equal(back.images, img) and back.metadata == {"patch_size": 4}
+
+
+def test_preprocessor_argument_errors():
+    with pytest.raises(ValueError):
+        Preprocessor(np.zeros((4, 4)))  # ndim not in {3, 4} (preprocessor.py:191)
+    p = Preprocessor(np.zeros((2, 128, 128), dtype=np.float32))
+    assert p.data.shape == (1, 2, 128, 128)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only check")
+def test_no_cpu_fallback():
+    """Without a CUDA device every operator raises instead of silently computing on the host."""
+    from rfi_toolbox_b200 import compute_ffi, evaluate_segmentation
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Preprocessor(np.ones((1, 1, 128, 128), dtype=np.float32)).create_dataset()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        evaluate_segmentation(np.zeros(8, bool), np.zeros(8, bool))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        compute_ffi(np.ones(8, np.float32), np.zeros(8, bool))
