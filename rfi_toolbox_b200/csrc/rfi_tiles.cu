@@ -80,6 +80,35 @@ RFI_DEVINL void load1(const void* base, size_t idx, typename In<DT>::T& mag, typ
     }
 }
 
+// one raw sample as loaded (prefetchable), converted to magnitude / phase later
+template <int DT> struct RawSample;
+template <> struct RawSample<RFI_F32>  { float v; };
+template <> struct RawSample<RFI_F64>  { double v; };
+template <> struct RawSample<RFI_C64>  { float2 v; };
+template <> struct RawSample<RFI_C128> { double2 v; };
+
+template <int DT>
+RFI_DEVINL RawSample<DT> load_raw(const void* base, size_t idx) {
+    RawSample<DT> r;
+    if constexpr (DT == RFI_F32) r.v = __ldg(static_cast<const float*>(base) + idx);
+    else if constexpr (DT == RFI_F64) r.v = __ldg(static_cast<const double*>(base) + idx);
+    else if constexpr (DT == RFI_C64) r.v = __ldg(static_cast<const float2*>(base) + idx);
+    else r.v = __ldg(static_cast<const double2*>(base) + idx);
+    return r;
+}
+
+template <int DT, bool kPhase>
+RFI_DEVINL void raw_to_mag(const RawSample<DT>& r, typename In<DT>::T& mag, typename In<DT>::T& ph) {
+    using T = typename In<DT>::T;
+    ph = T(0);
+    if constexpr (DT == RFI_F32 || DT == RFI_F64) {
+        mag = r.v;
+    } else {
+        mag = cabs_np<T>(r.v.x, r.v.y);
+        if constexpr (kPhase) ph = Scalar<T>::atan2_(r.v.y, r.v.x);
+    }
+}
+
 template <typename T>
 RFI_DEVINL T apply_stretch(T a, int stretch) {
     if (stretch == RFI_STRETCH_SQRT) return Scalar<T>::sqrt_rn(fabs_(a));
@@ -384,9 +413,9 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* Ls = reinterpret_cast<T*>(smem_raw);                                    // [kP][LP]
     float* Ph = reinterpret_cast<float*>(Ls + (size_t)kP * LP);               // [kP][LP] (complex branch)
-    unsigned char* Fb = reinterpret_cast<unsigned char*>(Ph + (kComplexBranch ? (size_t)kP * LP : 0));
-    float* stage = reinterpret_cast<float*>(Fb + (size_t)kP * FP);            // [warps][3*kP]
-    unsigned char* lstage = reinterpret_cast<unsigned char*>(stage + (size_t)RS * 3 * kP);  // [warps][kP]
+    // transposed label tile (rotations 2, 3); rotations 0, 1 store their label rows from pass A
+    unsigned char* FbT = reinterpret_cast<unsigned char*>(Ph + (kComplexBranch ? (size_t)kP * LP : 0));
+    float* stage = reinterpret_cast<float*>(FbT + (size_t)kP * FP);           // [warps][3*kP]
     __shared__ BlockScratch<NT> scr;
     int parity = 0;
 
@@ -418,33 +447,56 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
     const float is0 = 1.0f / std0, is1 = 1.0f / std1;
     const float nb0 = (0.0f - mean0) / std0, nb1 = (0.0f - mean1) / std1, nb2 = (0.0f - mean2) / std2;
 
-    // ---- pass A: processed sample -> log amplitude tile, label tile, min/max of L
+    // ---- pass A: processed sample -> log amplitude tile, label tiles, min/max of L.
+    // One row per warp per step; the next step's samples are prefetched into registers while
+    // the current ones go through magnitude / normalise / stretch / log10 (the loop is NOT
+    // unrolled over steps: the body is ~400 instructions and must stay inside the I-cache).
     T llo = Scalar<T>::nan(), lhi = Scalar<T>::nan();
+    {
+        RawSample<DT> cur[Q], nxt[Q];
 #pragma unroll
-    for (int s = 0; s < STEPS; ++s) {
-        const int row = s * RS + warp;
+        for (int q = 0; q < Q; ++q)
+            cur[q] = load_raw<DT>(data, origin + (size_t)warp * p.times + lane + 32 * q);
+#pragma unroll 1
+        for (int s = 0; s < STEPS; ++s) {
+            const int row = s * RS + warp;
+            if (s + 1 < STEPS) {
 #pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            const int col = lane + 32 * q;
-            const size_t idx = origin + (size_t)row * p.times + col;
-            T a, ph;
-            load1<DT, kComplexBranch>(data, idx, a, ph);
-            T x = a;
-            if (real_branch) x = process_sample<T>(a, p, med_before, inf_fill, med_after);
-            unsigned char f = 0;
-            if (p.flag_mode == RFI_FLAGS_MAD) f = ((x > thr_hi) || (x < thr_lo)) ? 1 : 0;
-            else if (p.flag_mode == RFI_FLAGS_CUSTOM) f = __ldg(flags + idx);
-            T L = log10_img(fabs_(x) + T(1e-10));
-            Ls[row * LP + col] = L;
-            Fb[row * FP + col] = f;
-            if constexpr (kComplexBranch) {
-                // (phase + pi) / (2 pi) in T, cast to float32, then ImageNet (rotation invariant)
-                T c2 = (ph + T(3.141592653589793)) / T(6.283185307179586);
-                Ph[row * LP + col] = ((float)c2 - mean2) / std2;
-            } else {
-                llo = Scalar<T>::fmin_nan(llo, L);
-                lhi = Scalar<T>::fmax_nan(lhi, L);
+                for (int q = 0; q < Q; ++q)
+                    nxt[q] = load_raw<DT>(data, origin + (size_t)(row + RS) * p.times + lane + 32 * q);
             }
+            unsigned char fl[Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                fl[q] = 0;
+                if (p.flag_mode == RFI_FLAGS_CUSTOM) fl[q] = __ldg(flags + origin + (size_t)row * p.times + lane + 32 * q);
+            }
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const int col = lane + 32 * q;
+                T a, ph;
+                raw_to_mag<DT, kComplexBranch>(cur[q], a, ph);
+                T x = a;
+                if (real_branch) x = process_sample<T>(a, p, med_before, inf_fill, med_after);
+                unsigned char f = fl[q];
+                if (p.flag_mode == RFI_FLAGS_MAD) f = ((x > thr_hi) || (x < thr_lo)) ? 1 : 0;
+                T L = log10_img(fabs_(x) + T(1e-10));
+                Ls[row * LP + col] = L;
+                FbT[col * FP + row] = f;
+                // label rows of the untransposed rotations go out now: 32 lanes x 1 byte = one full sector
+                if (slot0 >= 0) labels[(size_t)slot0 * kP * kP + (size_t)row * kP + col] = f;
+                if (slot1 >= 0) labels[(size_t)slot1 * kP * kP + (size_t)(kP - 1 - row) * kP + col] = f;
+                if constexpr (kComplexBranch) {
+                    // (phase + pi) / (2 pi) in T, cast to float32, then ImageNet (rotation invariant)
+                    T c2 = (ph + T(3.141592653589793)) / T(6.283185307179586);
+                    Ph[row * LP + col] = ((float)c2 - mean2) / std2;
+                } else {
+                    llo = Scalar<T>::fmin_nan(llo, L);
+                    lhi = Scalar<T>::fmax_nan(lhi, L);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < Q; ++q) cur[q] = nxt[q];
         }
     }
     __syncthreads();
@@ -453,7 +505,7 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
     T s0lo = Scalar<T>::nan(), s0hi = Scalar<T>::nan();
     T s1lo = Scalar<T>::nan(), s1hi = Scalar<T>::nan();
     T s3lo = Scalar<T>::nan(), s3hi = Scalar<T>::nan();
-#pragma unroll 2
+#pragma unroll 1
     for (int s = 0; s < STEPS; ++s) {
         const int i = s * RS + warp;
 #pragma unroll
@@ -489,32 +541,40 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
     const ChanScale<T> ls = make_scale<T>(llo, lhi);
 
     float* wstage = stage + (size_t)warp * 3 * kP;
-    unsigned char* wl = lstage + (size_t)warp * kP;
 
-    // ---- pass C: every kept rotation, one output row per warp per step.  `rot` is a
-    // compile-time constant so the source / neighbour index arithmetic folds away.
+    // ---- pass C: every kept rotation.  A warp owns STEPS CONSECUTIVE output rows, so the
+    // row-derivative neighbour of row r is the centre value of row r-1, carried in registers;
+    // only the centre and the column-derivative neighbour are read from shared memory.
+    // `rot` is a compile-time constant so the source / neighbour index arithmetic folds away.
     auto emit = [&](auto rot_tag, long long sl, const ChanScale<T>& gs) {
         constexpr int rot = decltype(rot_tag)::value;
         if (sl < 0) return;  // uniform across the block
         float* out_img = images + (size_t)sl * kP * kP * 3;
-        unsigned char* out_lab = labels + (size_t)sl * kP * kP;
+        [[maybe_unused]] unsigned char* out_lab = labels + (size_t)sl * kP * kP;
+        // source index of output (orow, ocol) = base_at + orow * srow + ocol * scol;
+        // db = offset of the column-derivative neighbour (output column - 1)
+        constexpr int srow = (rot == 0) ? LP : (rot == 1) ? -LP : (rot == 2) ? 1 : -1;
+        constexpr int scol = (rot <= 1) ? 1 : LP;
+        constexpr int base_at = (rot == 0) ? 0 : (rot == 1) ? (kP - 1) * LP : (rot == 2) ? 0 : (kP - 1);
+        constexpr int db = -scol;
+        const int row0 = warp * STEPS;
+        T prev[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int at = base_at + (row0 - 1) * srow + (lane + 32 * q) * scol;
+            prev[q] = (row0 > 0) ? Ls[at] : T(0);
+        }
 #pragma unroll 1
         for (int s = 0; s < STEPS; ++s) {
-            const int orow = s * RS + warp;  // output row i'
+            const int orow = row0 + s;  // output row i'
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
                 const int ocol = lane + 32 * q;  // output column j'
-                // (i, j): source sample; da: offset of the row-derivative neighbour (zero on
-                // output row 0); db: offset of the column-derivative neighbour (zero on col 0)
-                int i, j, da, db;
-                if constexpr (rot == 0) { i = orow; j = ocol; da = -LP; db = -1; }
-                else if constexpr (rot == 1) { i = kP - 1 - orow; j = ocol; da = LP; db = -1; }
-                else if constexpr (rot == 2) { i = ocol; j = orow; da = -1; db = -LP; }
-                else { i = ocol; j = kP - 1 - orow; da = 1; db = -LP; }
-                const int at = i * LP + j;
+                const int at = base_at + orow * srow + ocol * scol;
                 const T c = Ls[at];
-                const T td = (orow > 0) ? c - Ls[at + da] : T(0);
+                const T td = (orow > 0) ? c - prev[q] : T(0);
                 const T fd = (ocol > 0) ? c - Ls[at + db] : T(0);
+                prev[q] = c;
                 const T g = sqrt_fast(td * td + fd * fd);
                 const float u0 = (float)((g - gs.lo) * gs.inv);
                 float o1, o2;
@@ -531,16 +591,17 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
                 wstage[ocol * 3 + 0] = __fmaf_rn(u0, is0, nb0);
                 wstage[ocol * 3 + 1] = o1;
                 wstage[ocol * 3 + 2] = o2;
-                wl[ocol] = Fb[i * FP + j];
             }
             __syncwarp();
             float4* dst = reinterpret_cast<float4*>(out_img + (size_t)orow * kP * 3);
             const float4* src = reinterpret_cast<const float4*>(wstage);
 #pragma unroll
             for (int k = 0; k < 3; ++k) dst[lane + 32 * k] = src[lane + 32 * k];
-            if (lane < kP / 16)
-                reinterpret_cast<uint4*>(out_lab + (size_t)orow * kP)[lane] =
-                    reinterpret_cast<const uint4*>(wl)[lane];
+            if constexpr (rot >= 2) {  // label row = row of the transposed label tile (flipped for rot 3)
+                const unsigned char* lrow = FbT + ((rot == 2) ? orow : (kP - 1 - orow)) * FP;
+                reinterpret_cast<uint32_t*>(out_lab + (size_t)orow * kP)[lane] =
+                    reinterpret_cast<const uint32_t*>(lrow)[lane];
+            }
             __syncwarp();
         }
     };
@@ -596,7 +657,7 @@ static int launch_write(const PlanDev& d, long long tiles, const void* data, con
     auto kern = write_patches_kernel<DT, NT, CB>;
     size_t smem = (size_t)kP * Phase2Smem<T>::kPitch * sizeof(T) +
                   (CB ? (size_t)kP * Phase2Smem<T>::kPitch * sizeof(float) : 0) +
-                  (size_t)kP * Phase2Smem<T>::kFlagPitch + (size_t)(NT / 32) * (3 * kP * sizeof(float) + kP);
+                  (size_t)kP * Phase2Smem<T>::kFlagPitch + (size_t)(NT / 32) * (3 * kP * sizeof(float));
     RFI_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)tiles, NT, smem, st>>>(d, data, flags, stats, dest, images, labels);
     return RFI_OK;

@@ -72,6 +72,22 @@ def canonical_index_map(n_waterfalls, n_rot, nh, nw):
     return base + local[None]
 
 
+def _keep_in_canonical_order(keep_tile, n_rot):
+    """Per-tile keep mask (W, nh, nw) -> per-patch mask in the reference's patch order: the
+    rotated waterfalls of w are tiled row-major, so rotation 1 lists the tiles with the row
+    blocks reversed, rotation 2 lists the transposed grid, rotation 3 the transposed grid with
+    its row blocks reversed (same map as `canonical_index_map`, without building indices)."""
+    w = keep_tile.shape[0]
+    parts = [keep_tile.reshape(w, -1)]
+    if n_rot >= 2:
+        parts.append(keep_tile[:, ::-1, :].reshape(w, -1))
+    if n_rot >= 4:
+        t = keep_tile.transpose(0, 2, 1)
+        parts.append(t.reshape(w, -1))
+        parts.append(t[:, ::-1, :].reshape(w, -1))
+    return np.concatenate(parts, axis=1).reshape(-1)
+
+
 class Preprocessor:
     """Preprocess waterfall data into training patches (preprocessor.py:139-196)."""
 
@@ -211,10 +227,7 @@ class Preprocessor:
                 order = np.arange(n0, dtype=np.int64)  # :345-353 keeps the canonical order
             else:
                 nflag = stats[:n_tiles].view(torch.int32)[:, 16].cpu().numpy()  # n_flagged column
-                keep_tile = (nflag > 0).reshape(B * npol, nh, nw)
-                cmap = canonical_index_map(B * npol, R, nh, nw)
-                keep = np.zeros(n0, dtype=bool)
-                keep[cmap.ravel()] = np.broadcast_to(keep_tile[:, None], cmap.shape).ravel()
+                keep = _keep_in_canonical_order((nflag > 0).reshape(B * npol, nh, nw), R)
                 if keep.any():  # :752-756
                     kept = np.flatnonzero(keep)
                 else:

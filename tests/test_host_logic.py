@@ -95,3 +95,14 @@ def test_no_cpu_fallback():
         evaluate_segmentation(np.zeros(8, bool), np.zeros(8, bool))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         compute_ffi(np.ones(8, np.float32), np.zeros(8, bool))
+
+
+@pytest.mark.parametrize("rot", [1, 2, 4])
+def test_keep_mask_in_canonical_order(rot):
+    from rfi_toolbox_b200.preprocessing.preprocessor import _keep_in_canonical_order
+    rng = np.random.default_rng(4)
+    kt = rng.random((5, 3, 7)) < 0.5
+    cmap = canonical_index_map(5, rot, 3, 7)
+    want = np.zeros(cmap.size, dtype=bool)
+    want[cmap.ravel()] = np.broadcast_to(kt[:, None], cmap.shape).ravel()
+    assert np.array_equal(_keep_in_canonical_order(kt, rot), want)
