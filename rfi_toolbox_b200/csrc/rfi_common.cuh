@@ -9,6 +9,8 @@
 #include <stdint.h>
 #include <math.h>
 
+#include <type_traits>
+
 #include "../../include/rfi_b200.h"
 
 #define RFI_DEVINL __device__ __forceinline__
@@ -66,20 +68,28 @@ template <typename T> RFI_DEVINL bool is_inf(T x) { return fabs_(x) == Scalar<T>
 
 // Order-preserving key: ascending float order == ascending unsigned order; every NaN maps
 // to the all-ones key, which doubles as the "excluded" marker (nanmedian drops NaNs).
+// Branch-free: 2 logic ops + the NaN canonicalisation (3 ops); from_key needs no special case
+// (the all-ones key decodes to the canonical quiet NaN).
 template <typename T>
 RFI_DEVINL typename Scalar<T>::key_t to_key(T x) {
     using K = typename Scalar<T>::key_t;
-    constexpr K kSign = K(1) << (Scalar<T>::kBits - 1);
-    K b = Scalar<T>::bits(x);
-    K k = (b & kSign) ? ~b : (b | kSign);
-    return is_nan(x) ? ~K(0) : k;
+    using SK = typename std::make_signed<K>::type;
+    constexpr int kB = Scalar<T>::kBits;
+    constexpr K kSign = K(1) << (kB - 1);
+    constexpr K kInfBits = sizeof(T) == 4 ? K(0x7f800000u) : (K(0x7ff00000u) << 32);
+    const K b = Scalar<T>::bits(x);
+    const K m = (K)((SK)b >> (kB - 1));  // all ones for negative values
+    const K k = b ^ (m | kSign);
+    return ((b & ~kSign) > kInfBits) ? ~K(0) : k;
 }
 template <typename T>
 RFI_DEVINL T from_key(typename Scalar<T>::key_t k) {
     using K = typename Scalar<T>::key_t;
-    constexpr K kSign = K(1) << (Scalar<T>::kBits - 1);
-    K b = (k & kSign) ? (k & ~kSign) : ~k;
-    return (k == ~K(0)) ? Scalar<T>::nan() : Scalar<T>::from_bits(b);
+    using SK = typename std::make_signed<K>::type;
+    constexpr int kB = Scalar<T>::kBits;
+    constexpr K kSign = K(1) << (kB - 1);
+    const K m = (K)((SK)k >> (kB - 1));  // all ones for keys of non-negative values
+    return Scalar<T>::from_bits(k ^ (~m | kSign));
 }
 
 // |re + i*im| exactly as NumPy's SIMD complex absolute computes it (verified bit-for-bit
@@ -256,9 +266,10 @@ RFI_DEVINL void round_init(RoundCounter& rc) {
 }
 RFI_DEVINL uint32_t round_sum(uint32_t v, RoundCounter& rc, int& r) {
     v = __reduce_add_sync(0xffffffffu, v);
-    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&rc.c[r & 3], v);
+    uint32_t* slot = rc.c + (r & 3);
+    if ((threadIdx.x & 31) == 0) atomicAdd(slot, v);
     __syncthreads();
-    const uint32_t t = rc.c[r & 3];
+    const uint32_t t = *slot;
     if (threadIdx.x == 0) rc.c[(r + 2) & 3] = 0;
     ++r;
     return t;
@@ -295,33 +306,54 @@ RFI_DEVINL void count_le(float& c, unsigned long long key, unsigned long long tr
 // below prefix|1<<b; a round costs 2 instructions per key and one block reduction, no
 // shared-memory histogram (ATOMS retires ~0.5 key/clk/SM on Blackwell, ~20x slower than
 // this).  The leading bits shared by min and max are skipped.
+// Candidate compaction: once at most kSelCap keys still share the decided prefix they are
+// copied to a shared list and the remaining bits are resolved two per round on <= kSelCap/NT
+// keys per thread (three trial keys per round, their counts packed 10 bits each into one
+// word), instead of sweeping all E keys per thread for every remaining bit.
+constexpr int kSelCap = 1023;  // counts must fit 10 bits
+
+template <typename K>
+struct SelectScratch {
+    K list[kSelCap + 1];
+    uint32_t cursor;
+};
+
 template <int NT, int E, typename K>
 RFI_DEVINL void block_select2(const K (&key)[E], uint32_t n, uint32_t k1, uint32_t k2,
                               K& out1, K& out2, BlockScratch<NT>& s, int& parity,
-                              RoundCounter& rc, int& round) {
+                              RoundCounter& rc, int& round, SelectScratch<K>& ss) {
     constexpr K kExcl = ~K(0);
     constexpr int kBits = sizeof(K) * 8;
+    constexpr int CE = (kSelCap + NT) / NT;  // compacted keys per thread
     if (n == 0) {  // uniform: n comes from a block reduction
         out1 = out2 = kExcl;
         return;
     }
     K lo = kExcl, hi = 0;
+    uint32_t lt_upper = 0;  // this thread's keys below prefix + 2^(b+1) (initially: its valid keys)
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         K x = key[e];
         lo = x < lo ? x : lo;
-        K y = (x == kExcl) ? K(0) : x;
+        const bool ex = (x == kExcl);
+        K y = ex ? K(0) : x;
         hi = y > hi ? y : hi;
+        lt_upper += ex ? 0u : 1u;
     }
     block_minmax_key<NT, K>(lo, hi, s, parity);
     K prefix = lo;
-    K diff = lo ^ hi;
+    const K diff = lo ^ hi;
+    bool compacted = false;
+    uint32_t below = 0, upper = n;  // keys < prefix ; keys < prefix + 2^(b+1)
+    uint32_t lt_below = 0;          // this thread's keys below prefix
+    K ck[CE];
     if (diff != 0) {
-        int hb = (kBits - 1) - (sizeof(K) == 8 ? __clzll((long long)diff) : __clz((int)diff));
-        K below = (hb == kBits - 1) ? K(0) : (lo >> (hb + 1)) << (hb + 1);
-        prefix = below;
+        const int hb = (kBits - 1) - (sizeof(K) == 8 ? __clzll((long long)diff) : __clz((int)diff));
+        prefix = (hb == kBits - 1) ? K(0) : (lo >> (hb + 1)) << (hb + 1);
+        int b = hb;
 #pragma unroll 1
-        for (int b = hb; b >= 0; --b) {
+        for (; b >= 0; --b) {
+            if (upper - below <= (uint32_t)kSelCap && b >= 1) break;  // uniform
             const K trial = prefix | (K(1) << b);
             float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
 #pragma unroll
@@ -331,8 +363,55 @@ RFI_DEVINL void block_select2(const K (&key)[E], uint32_t n, uint32_t k1, uint32
                 count_lt(c2, key[e + 2], trial);
                 count_lt(c3, key[e + 3], trial);
             }
-            const uint32_t c = round_sum((uint32_t)((c0 + c1) + (c2 + c3)), rc, round);
-            if (c <= k1) prefix = trial;
+            const uint32_t lt = (uint32_t)((c0 + c1) + (c2 + c3));
+            const uint32_t c = round_sum(lt, rc, round);
+            if (c <= k1) { prefix = trial; below = c; lt_below = lt; } else { upper = c; lt_upper = lt; }
+        }
+        if (b >= 0) {
+            // ---- compact the keys whose bits above b equal the prefix
+            compacted = true;
+            if (threadIdx.x == 0) ss.cursor = 0;
+            __syncthreads();
+            // this thread's candidates = its keys in [prefix, prefix + 2^(b+1)), already counted
+            // by the rounds that last moved the two bounds -> no counting pass
+            const uint32_t mine = lt_upper - lt_below;
+            uint32_t at = mine ? atomicAdd(&ss.cursor, mine) : 0u;
+            const int sh = b + 1;  // undecided low bits
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const K x = key[e] ^ prefix;
+                const bool is = (sh >= kBits || (x >> sh) == 0) && key[e] != kExcl;
+                if (is) ss.list[at++] = key[e];
+            }
+            __syncthreads();
+            const uint32_t ncand = upper - below;
+#pragma unroll
+            for (int j = 0; j < CE; ++j) {
+                const uint32_t idx = threadIdx.x + j * NT;
+                ck[j] = idx < ncand ? ss.list[idx] : kExcl;
+            }
+            const uint32_t kk = k1 - below;  // rank inside the candidate list
+            // ---- two bits per round
+#pragma unroll 1
+            for (; b >= 1; b -= 2) {
+                const K t1 = prefix | (K(1) << (b - 1)), t2 = prefix | (K(2) << (b - 1)),
+                        t3 = prefix | (K(3) << (b - 1));
+                uint32_t c = 0;
+#pragma unroll
+                for (int j = 0; j < CE; ++j)
+                    c += (ck[j] < t1 ? 1u : 0u) + (ck[j] < t2 ? 1u << 10 : 0u) + (ck[j] < t3 ? 1u << 20 : 0u);
+                c = round_sum(c, rc, round);
+                const uint32_t n1 = c & 1023u, n2 = (c >> 10) & 1023u, n3 = c >> 20;
+                prefix = (n3 <= kk) ? t3 : (n2 <= kk) ? t2 : (n1 <= kk) ? t1 : prefix;
+            }
+            if (b == 0) {  // odd number of remaining bits: one single-bit round
+                const K t1 = prefix | K(1);
+                uint32_t c = 0;
+#pragma unroll
+                for (int j = 0; j < CE; ++j) c += (ck[j] < t1) ? 1u : 0u;
+                c = round_sum(c, rc, round);
+                if (c <= kk) prefix = t1;
+            }
         }
     }
     out1 = prefix;
@@ -341,19 +420,42 @@ RFI_DEVINL void block_select2(const K (&key)[E], uint32_t n, uint32_t k1, uint32
         return;
     }
     // rank k1+1: same key if duplicates reach it, else the smallest key above.
-    float cle = 0.f;
+    if (compacted) {
+        uint32_t cle = 0;
+        K nxt = kExcl;
+#pragma unroll
+        for (int j = 0; j < CE; ++j) {
+            cle += (ck[j] <= prefix) ? 1u : 0u;
+            const K y = (ck[j] > prefix) ? ck[j] : kExcl;
+            nxt = y < nxt ? y : nxt;
+        }
+        cle = round_sum(cle, rc, round);
+        if (k2 < below + cle) {  // uniform
+            out2 = prefix;
+            return;
+        }
+        K dummy = 0;
+        block_minmax_key<NT, K>(nxt, dummy, s, parity);
+        if (nxt != kExcl) {  // a candidate above: smaller than every key outside the list
+            out2 = nxt;
+            return;
+        }
+        // the answer is the largest candidate: the next key lies outside the list (below)
+    } else {
+        float cle = 0.f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) count_le(cle, key[e], prefix);
+        const uint32_t ncle = round_sum((uint32_t)cle, rc, round);
+        if (k2 < ncle) {  // uniform
+            out2 = prefix;
+            return;
+        }
+    }
     K nxt = kExcl;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-        K x = key[e];
-        count_le(cle, x, prefix);
-        K y = (x > prefix) ? x : kExcl;
+        const K y = (key[e] > prefix) ? key[e] : kExcl;
         nxt = y < nxt ? y : nxt;
-    }
-    const uint32_t ncle = round_sum((uint32_t)cle, rc, round);
-    if (k2 < ncle) {  // uniform
-        out2 = prefix;
-        return;
     }
     K dummy = 0;
     block_minmax_key<NT, K>(nxt, dummy, s, parity);
@@ -366,6 +468,7 @@ RFI_DEVINL void block_select2(const K (&key)[E], uint32_t n, uint32_t k1, uint32
 template <typename T, int NT, int E>
 RFI_DEVINL T block_median(const typename Scalar<T>::key_t (&key)[E], uint32_t n,
                           BlockScratch<NT>& s, int& parity, RoundCounter& rc, int& round,
+                          SelectScratch<typename Scalar<T>::key_t>& ss,
                           typename Scalar<T>::key_t* lo_key = nullptr,
                           typename Scalar<T>::key_t* hi_key = nullptr) {
     using K = typename Scalar<T>::key_t;
@@ -375,7 +478,7 @@ RFI_DEVINL T block_median(const typename Scalar<T>::key_t (&key)[E], uint32_t n,
         return Scalar<T>::nan();
     }
     K a, b;
-    block_select2<NT, E, K>(key, n, (n - 1) >> 1, n >> 1, a, b, s, parity, rc, round);
+    block_select2<NT, E, K>(key, n, (n - 1) >> 1, n >> 1, a, b, s, parity, rc, round, ss);
     if (lo_key) *lo_key = a;
     if (hi_key) *hi_key = b;
     return median_of_pair<T>(from_key<T>(a), from_key<T>(b), n);

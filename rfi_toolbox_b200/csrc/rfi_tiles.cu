@@ -159,6 +159,7 @@ tile_stats_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __res
     K* stash = reinterpret_cast<K*>(smem_raw);  // [E][NT]
     __shared__ BlockScratch<NT> scr;
     __shared__ RoundCounter rc;
+    __shared__ SelectScratch<K> sel;
     int parity = 0, round = 0;
     round_init(rc);
 
@@ -179,10 +180,14 @@ tile_stats_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __res
         for (int i = 0; i < 4; ++i) a[g * 4 + i] = to_key<T>(q[i]);
     }
 
-    rfi_tile_stat_t st;
-    st.median_before = st.inf_fill = st.median_after = 0.0;
-    st.centre = st.mad = st.thr_lo = st.thr_hi = 0.0;
-    st.n_inf = 0; st.n_flagged = 0; st.reserved = 0;
+    // results go straight to shared memory (thread 0) so they do not occupy registers across
+    // the selects; copied out once at the end
+    __shared__ rfi_tile_stat_t st;
+    if (threadIdx.x == 0) {
+        st.median_before = st.inf_fill = st.median_after = 0.0;
+        st.centre = st.mad = st.thr_lo = st.thr_hi = 0.0;
+        st.n_valid = 0; st.n_inf = 0; st.n_flagged = 0; st.reserved = 0;
+    }
 
     // non-NaN samples (recounted before every general median: inf / inf can create a NaN)
     auto count_valid = [&]() {
@@ -202,60 +207,63 @@ tile_stats_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __res
         nv = round_sum(c, rc, round);
         nodd = round_sum(o, rc, round);
     }
-    st.n_valid = (int)nv;
+    if (threadIdx.x == 0) st.n_valid = (int)nv;
 
     const bool real_branch = !In<DT>::cplx || p.magnitude;
     bool shortcut = false;  // (v1, v2) are the two middle order statistics of the current tile
     T v1 = T(0), v2 = T(0);
 
     if (real_branch) {
-        // ---- normalise by the median (preprocessor.py:646-670)
+        // ---- normalise by the median (preprocessor.py:646-670), then stretch; +-inf := MAD of
+        //      the finite values (preprocessor.py:672-706).  One decode / encode per sample.
+        T m = T(0);
         if (p.norm_before) {
             K k1, k2;
-            T m = block_median<T, NT, E>(a, nv, scr, parity, rc, round, &k1, &k2);
-            st.median_before = (double)m;
+            m = block_median<T, NT, E>(a, nv, scr, parity, rc, round, sel, &k1, &k2);
+            if (threadIdx.x == 0) st.median_before = (double)m;
             shortcut = (nodd == 0) && (nv > 0);
             v1 = from_key<T>(k1); v2 = from_key<T>(k2);
-            if (m > T(0)) {
-#pragma unroll
-                for (int e = 0; e < E; ++e) a[e] = to_key<T>(from_key<T>(a[e]) / m);
-                v1 = v1 / m; v2 = v2 / m;
-            }
         }
-        // ---- stretch, +-inf := MAD of the finite values (preprocessor.py:672-706)
-        if (p.stretch != RFI_STRETCH_NONE) {
+        const bool divide = p.norm_before && (m > T(0));
+        if (divide || p.stretch != RFI_STRETCH_NONE) {
             uint32_t ninf = 0, nfin = 0;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                a[e] = to_key<T>(apply_stretch<T>(from_key<T>(a[e]), p.stretch));
+                T x = from_key<T>(a[e]);
+                if (divide) x = x / m;
+                if (p.stretch != RFI_STRETCH_NONE) x = apply_stretch<T>(x, p.stretch);
+                a[e] = to_key<T>(x);
                 const bool inf = (a[e] == kPosInf || a[e] == kNegInf);
                 ninf += inf ? 1u : 0u;
                 nfin += (!inf && a[e] != kExcl) ? 1u : 0u;
             }
-            v1 = apply_stretch<T>(v1, p.stretch); v2 = apply_stretch<T>(v2, p.stretch);
-            ninf = round_sum(ninf, rc, round);
-            st.n_inf = (int)ninf;
-            if (ninf > 0) {
-                shortcut = false;
-                nfin = round_sum(nfin, rc, round);
-                T fill = T(0);
-                if (nfin > 0) {
+            if (divide) { v1 = v1 / m; v2 = v2 / m; }
+            if (p.stretch != RFI_STRETCH_NONE) {
+                v1 = apply_stretch<T>(v1, p.stretch); v2 = apply_stretch<T>(v2, p.stretch);
+                ninf = round_sum(ninf, rc, round);
+                if (threadIdx.x == 0) st.n_inf = (int)ninf;
+                if (ninf > 0) {
+                    shortcut = false;
+                    nfin = round_sum(nfin, rc, round);
+                    T fill = T(0);
+                    if (nfin > 0) {
 #pragma unroll
-                    for (int e = 0; e < E; ++e) stash[e * NT + threadIdx.x] = a[e];
+                        for (int e = 0; e < E; ++e) stash[e * NT + threadIdx.x] = a[e];
 #pragma unroll
-                    for (int e = 0; e < E; ++e) a[e] = (a[e] == kPosInf || a[e] == kNegInf) ? kExcl : a[e];
-                    T c = block_median<T, NT, E>(a, nfin, scr, parity, rc, round);
+                        for (int e = 0; e < E; ++e) a[e] = (a[e] == kPosInf || a[e] == kNegInf) ? kExcl : a[e];
+                        T c = block_median<T, NT, E>(a, nfin, scr, parity, rc, round, sel);
 #pragma unroll
-                    for (int e = 0; e < E; ++e)
-                        a[e] = (a[e] == kExcl) ? kExcl : to_key<T>(fabs_(from_key<T>(a[e]) - c));
-                    fill = block_median<T, NT, E>(a, nfin, scr, parity, rc, round);
+                        for (int e = 0; e < E; ++e)
+                            a[e] = (a[e] == kExcl) ? kExcl : to_key<T>(fabs_(from_key<T>(a[e]) - c));
+                        fill = block_median<T, NT, E>(a, nfin, scr, parity, rc, round, sel);
 #pragma unroll
-                    for (int e = 0; e < E; ++e) a[e] = stash[e * NT + threadIdx.x];
+                        for (int e = 0; e < E; ++e) a[e] = stash[e * NT + threadIdx.x];
+                    }
+                    if (threadIdx.x == 0) st.inf_fill = (double)fill;
+                    const K kfill = to_key<T>(fill);
+#pragma unroll
+                    for (int e = 0; e < E; ++e) a[e] = (a[e] == kPosInf || a[e] == kNegInf) ? kfill : a[e];
                 }
-                st.inf_fill = (double)fill;
-                const K kfill = to_key<T>(fill);
-#pragma unroll
-                for (int e = 0; e < E; ++e) a[e] = (a[e] == kPosInf || a[e] == kNegInf) ? kfill : a[e];
             }
         }
         // ---- normalise again (preprocessor.py:309-311)
@@ -264,11 +272,10 @@ tile_stats_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __res
             if (shortcut) {
                 m2 = median_of_pair<T>(v1, v2, nv);
             } else {
-                K k1, k2;
                 const uint32_t n2 = count_valid();
-                m2 = block_median<T, NT, E>(a, n2, scr, parity, rc, round, &k1, &k2);
+                m2 = block_median<T, NT, E>(a, n2, scr, parity, rc, round, sel);
             }
-            st.median_after = (double)m2;
+            if (threadIdx.x == 0) st.median_after = (double)m2;
             if (m2 > T(0)) {
 #pragma unroll
                 for (int e = 0; e < E; ++e) a[e] = to_key<T>(from_key<T>(a[e]) / m2);
@@ -286,25 +293,28 @@ tile_stats_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __res
             c = median_of_pair<T>(v1, v2, nv);
         } else {
             nn = count_valid();
-            c = block_median<T, NT, E>(a, nn, scr, parity, rc, round);
+            c = block_median<T, NT, E>(a, nn, scr, parity, rc, round, sel);
         }
 #pragma unroll
-        for (int e = 0; e < E; ++e) stash[e * NT + threadIdx.x] = a[e];
-#pragma unroll
-        for (int e = 0; e < E; ++e) a[e] = to_key<T>(fabs_(from_key<T>(a[e]) - c));
-        T d = block_median<T, NT, E>(a, nn, scr, parity, rc, round);
+        for (int e = 0; e < E; ++e) {
+            stash[e * NT + threadIdx.x] = a[e];
+            a[e] = to_key<T>(fabs_(from_key<T>(a[e]) - c));
+        }
+        T d = block_median<T, NT, E>(a, nn, scr, parity, rc, round, sel);
         T ds = d * (T)p.sigma;
         T hi = c + ds, lo = c - ds;
         uint32_t nf = 0;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            T x = from_key<T>(stash[e * NT + threadIdx.x]);
+            const T x = from_key<T>(stash[e * NT + threadIdx.x]);
             nf += ((x > hi) || (x < lo)) ? 1u : 0u;
         }
         nf = round_sum(nf, rc, round);
-        st.centre = (double)c; st.mad = (double)d;
-        st.thr_lo = (double)lo; st.thr_hi = (double)hi;
-        st.n_flagged = (int)nf;
+        if (threadIdx.x == 0) {
+            st.centre = (double)c; st.mad = (double)d;
+            st.thr_lo = (double)lo; st.thr_hi = (double)hi;
+            st.n_flagged = (int)nf;
+        }
     } else if (p.flag_mode == RFI_FLAGS_CUSTOM) {
         uint32_t nf = 0;
 #pragma unroll
@@ -315,7 +325,7 @@ tile_stats_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __res
             nf += __popc(nz);
         }
         nf = round_sum(nf, rc, round);
-        st.n_flagged = (int)nf;
+        if (threadIdx.x == 0) st.n_flagged = (int)nf;
     }
     if (threadIdx.x == 0) stats[tile] = st;
 }
