@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RFI_B200_ABI_VERSION 1
+#define RFI_B200_ABI_VERSION 2
 
 /* status codes */
 #define RFI_OK 0
@@ -49,7 +49,12 @@ extern "C" {
 #define RFI_FLAGS_INFERENCE 2 /* all-zero labels */
 
 /* Plan of one create_dataset call over a cube (B, Npol, C, T), C-order.
- * Fast path: C and T multiples of P (no padding), P = 128. */
+ * Fast path (one CTA per tile, tile resident on chip): P = 128, C and T multiples of P.
+ * Every other geometry -- P = 256 / 512 / 1024 or any other size, C or T not a multiple of
+ * P (the reference zero-pads bottom/right after the rotation, preprocessor.py:527-550),
+ * waterfalls no larger than the patch (patchify skipped, preprocessor.py:261-269) -- runs
+ * on the generic path (segmented multi-pass radix select over global memory) and needs the
+ * workspace rfi_plan_workspace_bytes() reports. */
 typedef struct rfi_plan {
     int32_t dtype;       /* RFI_F32 .. RFI_C128 */
     int32_t magnitude;   /* complex input only: 1 = take |z| on load and run the real branch
@@ -85,29 +90,40 @@ typedef struct rfi_tile_stat {
     int32_t reserved;
 } rfi_tile_stat_t;
 
-/* Number of original tiles / output patches of a plan (host arithmetic only). */
+/* Host arithmetic only.
+ * rfi_plan_num_tiles    entries of the statistics array = statistic groups: one per original
+ *                       tile when C and T are multiples of P (the R rotated patches share
+ *                       their statistics), one per output patch (canonical order) when the
+ *                       reference pads, because the pad follows the flip;
+ * rfi_plan_num_patches  patches before blank removal = R * B * Npol * ceil(C/P) * ceil(T/P)
+ *                       (R * B * Npol when patchify is skipped);
+ * rfi_plan_workspace_bytes  device scratch the two phases share (0 on the fast path). */
 int64_t rfi_plan_num_tiles(const rfi_plan_t* plan);
-int64_t rfi_plan_num_patches(const rfi_plan_t* plan); /* rotations * tiles */
+int64_t rfi_plan_num_patches(const rfi_plan_t* plan);
+size_t rfi_plan_workspace_bytes(const rfi_plan_t* plan);
 
 /* Phase 1 -- replaces _normalize / _apply_stretch statistics / _generate_mad_flags
  * (preprocessor.py:646-745) and the `any()` of _remove_blank_patches (:749).
  *   data   device, cube in the plan's dtype
  *   flags  device, uint8/bool cube of the same shape (RFI_FLAGS_CUSTOM) or NULL
  *   stats  device, rfi_plan_num_tiles() entries, written
+ *   workspace device, rfi_plan_workspace_bytes() bytes (NULL when that is 0); the same buffer,
+ *          untouched in between, must be passed to rfi_write_patches
  * One CTA per original tile; tile resident in registers, order statistics by
  * register-resident MSB-first binary radix select. */
 int rfi_tile_stats(const rfi_plan_t* plan, const void* data, const uint8_t* flags,
-                   rfi_tile_stat_t* stats, void* stream);
+                   rfi_tile_stat_t* stats, void* workspace, void* stream);
 
 /* Phase 2 -- replaces _apply_rotations, patchify, _normalize, _apply_stretch, flag
  * application, _extract_channels_from_{real,complex}, ImageNet normalisation and the
  * compaction + shuffle gathers (preprocessor.py:22-42, 413-446, 562-783).
  *   dest_slot device int64[rfi_plan_num_patches()], canonical patch index -> output slot,
  *             -1 = dropped (blank / beyond num_patches)
- *   images    device float32 (N, P, P, 3), labels device uint8 (N, P, P) */
+ *   images    device float32 (N, P, P, 3), labels device uint8 (N, P, P)
+ *             ((N, C, T, 3) / (N, C, T) when patchify is skipped) */
 int rfi_write_patches(const rfi_plan_t* plan, const void* data, const uint8_t* flags,
                       const rfi_tile_stat_t* stats, const int64_t* dest_slot,
-                      float* images, uint8_t* labels, void* stream);
+                      float* images, uint8_t* labels, void* workspace, void* stream);
 
 /* Confusion counts -- replaces the boolean reductions of evaluation/metrics.py:36-40,
  * 63-68, 95-99, 142-147.  `elem_*` is the element size in bytes (1, 2, 4 or 8) and

@@ -15,7 +15,7 @@ RFI_F32, RFI_F64, RFI_C64, RFI_C128 = 0, 1, 2, 3
 RFI_STRETCH_NONE, RFI_STRETCH_SQRT, RFI_STRETCH_LOG10 = 0, 1, 2
 RFI_FLAGS_CUSTOM, RFI_FLAGS_MAD, RFI_FLAGS_INFERENCE = 0, 1, 2
 RFI_E_INVALID, RFI_E_UNSUPPORTED, RFI_E_CUDA = -1, -2, -3
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class RfiPlan(C.Structure):
@@ -51,8 +51,9 @@ _VP, _I, _I64 = C.c_void_p, C.c_int, C.c_int64
 SYMBOLS = {
     "rfi_plan_num_tiles": (_I64, [C.POINTER(RfiPlan)]),
     "rfi_plan_num_patches": (_I64, [C.POINTER(RfiPlan)]),
-    "rfi_tile_stats": (_I, [C.POINTER(RfiPlan), _VP, _VP, _VP, _VP]),
-    "rfi_write_patches": (_I, [C.POINTER(RfiPlan), _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "rfi_plan_workspace_bytes": (C.c_size_t, [C.POINTER(RfiPlan)]),
+    "rfi_tile_stats": (_I, [C.POINTER(RfiPlan), _VP, _VP, _VP, _VP, _VP]),
+    "rfi_write_patches": (_I, [C.POINTER(RfiPlan), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "rfi_confusion_counts": (_I, [_VP, _I, _I, _VP, _I, _I, _I64, _VP, _VP]),
     "rfi_confusion_counts_segmented": (_I, [_VP, _I, _I, _VP, _I, _I, _I64, _I64, _VP, _VP]),
     "rfi_statistics_workspace_bytes": (C.c_size_t, []),

@@ -12,121 +12,9 @@
 // Reference semantics: rfi_toolbox/preprocessing/preprocessor.py:22-42, 413-446, 562-783
 // (restated in SURVEY.md Appendix A).  Statistics are rotation invariant for dims divisible
 // by P, so they are computed once per original tile and shared by the R rotated patches.
-#include <type_traits>
-
-#include "rfi_common.cuh"
+#include "rfi_tiles.cuh"
 
 namespace rfi {
-
-constexpr int kP = 128;  // tile edge handled by one CTA
-
-struct PlanDev {
-    long long n_waterfalls, channels, times;
-    int nh, nw;  // tiles per waterfall along channels / times
-    int rotations, stretch, norm_before, norm_after, flag_mode, magnitude;
-    double sigma;
-};
-
-template <int DT> struct In;
-template <> struct In<RFI_F32>  { using T = float;  static constexpr bool cplx = false; };
-template <> struct In<RFI_F64>  { using T = double; static constexpr bool cplx = false; };
-template <> struct In<RFI_C64>  { using T = float;  static constexpr bool cplx = true; };
-template <> struct In<RFI_C128> { using T = double; static constexpr bool cplx = true; };
-
-// ------------------------------------------------------------------------------------------
-// loads.  `p` points at 4 consecutive samples of one waterfall row.
-template <int DT>
-RFI_DEVINL void load4_mag(const void* base, size_t idx, typename In<DT>::T (&out)[4]) {
-    using T = typename In<DT>::T;
-    if constexpr (DT == RFI_F32) {
-        float4 q = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(base) + idx));
-        out[0] = q.x; out[1] = q.y; out[2] = q.z; out[3] = q.w;
-    } else if constexpr (DT == RFI_F64) {
-        const double2* p = reinterpret_cast<const double2*>(static_cast<const double*>(base) + idx);
-        double2 a = __ldg(p), b = __ldg(p + 1);
-        out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
-    } else if constexpr (DT == RFI_C64) {
-        const float4* p = reinterpret_cast<const float4*>(static_cast<const float2*>(base) + idx);
-        float4 a = __ldg(p), b = __ldg(p + 1);  // two 128-bit loads = four complex64
-        out[0] = cabs_np<T>(a.x, a.y); out[1] = cabs_np<T>(a.z, a.w);
-        out[2] = cabs_np<T>(b.x, b.y); out[3] = cabs_np<T>(b.z, b.w);
-    } else {
-        const double2* p = static_cast<const double2*>(base) + idx;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            double2 z = __ldg(p + i);
-            out[i] = cabs_np<T>(z.x, z.y);
-        }
-    }
-}
-
-// one sample: magnitude (or the real value) and, for the complex branch, the phase.
-template <int DT, bool kPhase>
-RFI_DEVINL void load1(const void* base, size_t idx, typename In<DT>::T& mag, typename In<DT>::T& ph) {
-    using T = typename In<DT>::T;
-    ph = T(0);
-    if constexpr (DT == RFI_F32) {
-        mag = __ldg(static_cast<const float*>(base) + idx);
-    } else if constexpr (DT == RFI_F64) {
-        mag = __ldg(static_cast<const double*>(base) + idx);
-    } else if constexpr (DT == RFI_C64) {
-        float2 z = __ldg(static_cast<const float2*>(base) + idx);
-        mag = cabs_np<T>(z.x, z.y);
-        if constexpr (kPhase) ph = Scalar<T>::atan2_(z.y, z.x);
-    } else {
-        double2 z = __ldg(static_cast<const double2*>(base) + idx);
-        mag = cabs_np<T>(z.x, z.y);
-        if constexpr (kPhase) ph = Scalar<T>::atan2_(z.y, z.x);
-    }
-}
-
-// one raw sample as loaded (prefetchable), converted to magnitude / phase later
-template <int DT> struct RawSample;
-template <> struct RawSample<RFI_F32>  { float v; };
-template <> struct RawSample<RFI_F64>  { double v; };
-template <> struct RawSample<RFI_C64>  { float2 v; };
-template <> struct RawSample<RFI_C128> { double2 v; };
-
-template <int DT>
-RFI_DEVINL RawSample<DT> load_raw(const void* base, size_t idx) {
-    RawSample<DT> r;
-    if constexpr (DT == RFI_F32) r.v = __ldg(static_cast<const float*>(base) + idx);
-    else if constexpr (DT == RFI_F64) r.v = __ldg(static_cast<const double*>(base) + idx);
-    else if constexpr (DT == RFI_C64) r.v = __ldg(static_cast<const float2*>(base) + idx);
-    else r.v = __ldg(static_cast<const double2*>(base) + idx);
-    return r;
-}
-
-template <int DT, bool kPhase>
-RFI_DEVINL void raw_to_mag(const RawSample<DT>& r, typename In<DT>::T& mag, typename In<DT>::T& ph) {
-    using T = typename In<DT>::T;
-    ph = T(0);
-    if constexpr (DT == RFI_F32 || DT == RFI_F64) {
-        mag = r.v;
-    } else {
-        mag = cabs_np<T>(r.v.x, r.v.y);
-        if constexpr (kPhase) ph = Scalar<T>::atan2_(r.v.y, r.v.x);
-    }
-}
-
-template <typename T>
-RFI_DEVINL T apply_stretch(T a, int stretch) {
-    if (stretch == RFI_STRETCH_SQRT) return Scalar<T>::sqrt_rn(fabs_(a));
-    if (stretch == RFI_STRETCH_LOG10) return Scalar<T>::log10_(fabs_(a));
-    return a;
-}
-
-// raw sample -> processed sample, given the tile statistics (identical ops in both phases).
-template <typename T>
-RFI_DEVINL T process_sample(T a, const PlanDev& p, T med_before, T inf_fill, T med_after) {
-    if (p.norm_before && med_before > T(0)) a = a / med_before;
-    if (p.stretch != RFI_STRETCH_NONE) {
-        a = apply_stretch<T>(a, p.stretch);
-        if (is_inf(a)) a = inf_fill;
-    }
-    if (p.norm_after && med_after > T(0)) a = a / med_after;
-    return a;
-}
 
 // ------------------------------------------------------------------------------------------
 // phase 1
@@ -380,32 +268,6 @@ template <typename T> struct Phase2Smem {
     static constexpr int kFlagPitch = kP + 4;  // bytes; 33 words -> column reads hit 32 banks
 };
 
-RFI_DEVINL float sqrt_fast(float x) {
-    float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-RFI_DEVINL double sqrt_fast(double x) { return __dsqrt_rn(x); }
-
-// log10 for the image channel: float32 accurate to 2 ulp (CUDA log10f); fp64 unchanged.
-RFI_DEVINL float log10_img(float x) { return log10f(x); }
-RFI_DEVINL double log10_img(double x) { return ::log10(x); }
-
-template <typename T>
-struct ChanScale {      // u = (v - lo) * inv  (0 when the channel is flat), then ImageNet
-    T lo, inv;
-    bool ok;
-};
-
-template <typename T>
-RFI_DEVINL ChanScale<T> make_scale(T lo, T hi) {
-    ChanScale<T> c;
-    c.ok = hi > lo;     // false for NaN too: nanmin/nanmax of an all-NaN channel
-    c.lo = lo;
-    c.inv = c.ok ? T(1) / (hi - lo) : T(0);
-    return c;
-}
-
 template <int DT, int NT, bool kComplexBranch>
 __global__ void __launch_bounds__(NT, (sizeof(typename In<DT>::T) == 4 && !kComplexBranch) ? 2 : 1)
 write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __restrict__ flags,
@@ -631,15 +493,8 @@ static int make_plan(const rfi_plan_t* plan, PlanDev& d) {
     if (plan->stretch < 0 || plan->stretch > 2) { set_error("bad stretch %d", plan->stretch); return RFI_E_INVALID; }
     if (plan->flag_mode < 0 || plan->flag_mode > 2) { set_error("bad flag_mode %d", plan->flag_mode); return RFI_E_INVALID; }
     if (plan->n_waterfalls < 0 || plan->channels <= 0 || plan->times <= 0) { set_error("bad cube shape"); return RFI_E_INVALID; }
-    if (plan->patch != kP) {
-        set_error("patch size %d: only the shared-memory fast path (P = %d) is built", plan->patch, kP);
-        return RFI_E_UNSUPPORTED;
-    }
-    if (plan->channels % kP || plan->times % kP) {
-        set_error("cube %lld x %lld is not a multiple of the patch size (padding path not built)",
-                  (long long)plan->channels, (long long)plan->times);
-        return RFI_E_UNSUPPORTED;
-    }
+    if (plan->patch <= 0) { set_error("bad patch size %d", plan->patch); return RFI_E_INVALID; }
+    if (!plan_is_fast(plan)) { set_error("internal: plan is not a fast-path plan"); return RFI_E_INVALID; }
     d.n_waterfalls = plan->n_waterfalls; d.channels = plan->channels; d.times = plan->times;
     d.nh = (int)(plan->channels / kP); d.nw = (int)(plan->times / kP);
     d.rotations = plan->rotations; d.stretch = plan->stretch;
@@ -679,15 +534,25 @@ using namespace rfi;
 
 extern "C" int64_t rfi_plan_num_tiles(const rfi_plan_t* plan) {
     if (!plan || plan->patch <= 0) return -1;
-    return plan->n_waterfalls * (plan->channels / plan->patch) * (plan->times / plan->patch);
+    if (plan_is_fast(plan)) return plan->n_waterfalls * (plan->channels / plan->patch) * (plan->times / plan->patch);
+    return generic_num_groups(plan);
 }
 extern "C" int64_t rfi_plan_num_patches(const rfi_plan_t* plan) {
-    int64_t t = rfi_plan_num_tiles(plan);
-    return t < 0 ? t : t * plan->rotations;
+    if (!plan || plan->patch <= 0) return -1;
+    if (plan_is_fast(plan)) return rfi_plan_num_tiles(plan) * plan->rotations;
+    return generic_num_patches(plan);
+}
+extern "C" size_t rfi_plan_workspace_bytes(const rfi_plan_t* plan) {
+    if (!plan || plan->patch <= 0 || plan_is_fast(plan)) return 0;
+    return generic_workspace_bytes(plan);
 }
 
 extern "C" int rfi_tile_stats(const rfi_plan_t* plan, const void* data, const uint8_t* flags,
-                              rfi_tile_stat_t* stats, void* stream) {
+                              rfi_tile_stat_t* stats, void* workspace, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (plan && plan->patch > 0 && !plan_is_fast(plan)) {
+        return generic_tile_stats(plan, data, flags, stats, workspace, st);
+    }
     PlanDev d;
     int rc = make_plan(plan, d);
     if (rc) return rc;
@@ -695,7 +560,6 @@ extern "C" int rfi_tile_stats(const rfi_plan_t* plan, const void* data, const ui
     if (tiles == 0) return RFI_OK;
     if (!data || !stats) { set_error("data / stats is NULL"); return RFI_E_INVALID; }
     if (d.flag_mode == RFI_FLAGS_CUSTOM && !flags) { set_error("custom flag mode needs flags"); return RFI_E_INVALID; }
-    cudaStream_t st = (cudaStream_t)stream;
     const bool cplx = plan->dtype >= RFI_C64;
     const bool real_branch = !cplx || plan->magnitude;
     const bool need_data = d.flag_mode == RFI_FLAGS_MAD ||
@@ -717,7 +581,11 @@ extern "C" int rfi_tile_stats(const rfi_plan_t* plan, const void* data, const ui
 
 extern "C" int rfi_write_patches(const rfi_plan_t* plan, const void* data, const uint8_t* flags,
                                  const rfi_tile_stat_t* stats, const int64_t* dest_slot,
-                                 float* images, uint8_t* labels, void* stream) {
+                                 float* images, uint8_t* labels, void* workspace, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long* dest = reinterpret_cast<const long long*>(dest_slot);
+    if (plan && plan->patch > 0 && !plan_is_fast(plan))
+        return generic_write_patches(plan, data, flags, stats, dest, images, labels, workspace, st);
     PlanDev d;
     int rc = make_plan(plan, d);
     if (rc) return rc;
@@ -725,8 +593,6 @@ extern "C" int rfi_write_patches(const rfi_plan_t* plan, const void* data, const
     if (tiles == 0) return RFI_OK;
     if (!data || !stats || !dest_slot) { set_error("data / stats / dest_slot is NULL"); return RFI_E_INVALID; }
     if (d.flag_mode == RFI_FLAGS_CUSTOM && !flags) { set_error("custom flag mode needs flags"); return RFI_E_INVALID; }
-    cudaStream_t st = (cudaStream_t)stream;
-    const long long* dest = reinterpret_cast<const long long*>(dest_slot);
     const bool cb = plan->dtype >= RFI_C64 && !plan->magnitude;
     switch (plan->dtype) {
         case RFI_F32: rc = launch_write<RFI_F32, 512, false>(d, tiles, data, flags, stats, dest, images, labels, st); break;

@@ -204,9 +204,15 @@ class Preprocessor:
             norm_after=int(bool(normalize_after_stretch) and not complex_branch),
             flag_mode=flag_mode, sigma=float(flag_sigma),
         )
+        # statistic groups: one per original tile (shared by its R rotations) when the dims are
+        # multiples of P, one per output patch when the reference pads (the pad follows the flip)
         n_tiles = int(lib.rfi_plan_num_tiles(C.byref(plan)))
-        n0 = n_tiles * R
-        nh, nw = max(C_ // P, 1), max(T_ // P, 1)
+        n0 = int(lib.rfi_plan_num_patches(C.byref(plan)))
+        if n_tiles < 0 or n0 < 0:
+            _native.check(_native.RFI_E_INVALID, "rfi_plan_num_tiles")
+        padded = (not skip_patchify) and (C_ % P != 0 or T_ % P != 0)
+        nh, nw = (1, 1) if skip_patchify else (-(-C_ // P), -(-T_ // P))
+        ws_bytes = int(lib.rfi_plan_workspace_bytes(C.byref(plan)))
 
         with torch.cuda.device(device):
             stream = current_stream_ptr(device)
@@ -216,7 +222,9 @@ class Preprocessor:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if self.profile else None
             if ev:
                 ev[0].record()
-            rc = lib.rfi_tile_stats(C.byref(plan), data.data_ptr(), fptr, stats.data_ptr(), stream)
+            work = torch.empty(ws_bytes, dtype=torch.uint8, device=device) if ws_bytes else None
+            wptr = work.data_ptr() if work is not None else None
+            rc = lib.rfi_tile_stats(C.byref(plan), data.data_ptr(), fptr, stats.data_ptr(), wptr, stream)
             _native.check(rc, "rfi_tile_stats")
             if ev:
                 ev[1].record()
@@ -227,7 +235,10 @@ class Preprocessor:
                 order = np.arange(n0, dtype=np.int64)  # :345-353 keeps the canonical order
             else:
                 nflag = stats[:n_tiles].view(torch.int32)[:, 16].cpu().numpy()  # n_flagged column
-                keep = _keep_in_canonical_order((nflag > 0).reshape(B * npol, nh, nw), R)
+                if padded:
+                    keep = nflag > 0  # groups ARE the patches, already in canonical order
+                else:
+                    keep = _keep_in_canonical_order((nflag > 0).reshape(B * npol, nh, nw), R)
                 if keep.any():  # :752-756
                     kept = np.flatnonzero(keep)
                 else:
@@ -249,7 +260,7 @@ class Preprocessor:
             if ev:
                 ev[2].record()
             rc = lib.rfi_write_patches(C.byref(plan), data.data_ptr(), fptr, stats.data_ptr(),
-                                       dest_dev.data_ptr(), images.data_ptr(), labels.data_ptr(), stream)
+                                       dest_dev.data_ptr(), images.data_ptr(), labels.data_ptr(), wptr, stream)
             _native.check(rc, "rfi_write_patches")
             if ev:
                 ev[3].record()

@@ -1,0 +1,19 @@
+#!/bin/bash
+# One GPU visit: tests, bench, host profile, ncu launch list, ncu full captures of the two kernels.
+# usage: scripts/gpu_round.sh <tag>   (outputs under gpurun_out/<tag>_*)
+tag=${1:-r01}
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_tests.log 2>&1; echo "tests rc=$?"
+tail -3 gpurun_out/${tag}_tests.log
+python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
+cat gpurun_out/${tag}_bench.json
+python scripts/hostprof.py > gpurun_out/${tag}_hostprof.log 2>&1
+if [ -z "$NO_NCU" ]; then
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
+    python bench.py --steps 2 --warmup 3 > gpurun_out/${tag}_ncu_list.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:write_patches -s 3 -c 1 -f -o gpurun_out/${tag}_write \
+    python bench.py --steps 1 --warmup 3 > gpurun_out/${tag}_ncu_write.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:tile_stats -s 3 -c 1 -f -o gpurun_out/${tag}_stats \
+    python bench.py --steps 1 --warmup 3 > gpurun_out/${tag}_ncu_stats.log 2>&1
+fi
+ls -la gpurun_out | tail -12

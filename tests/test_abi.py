@@ -35,10 +35,24 @@ def test_struct_layout_and_pure_host_calls(native_lib):
     assert native_lib.rfi_statistics_workspace_bytes() > 0
     # argument validation happens before any CUDA call
     plan.rotations = 3
-    assert native_lib.rfi_tile_stats(C.byref(plan), None, None, None, None) == _native.RFI_E_INVALID
+    assert native_lib.rfi_tile_stats(C.byref(plan), None, None, None, None, None) == _native.RFI_E_INVALID
     assert b"rotations" in native_lib.rfi_last_error_string()
+    assert native_lib.rfi_plan_workspace_bytes(C.byref(plan)) == 0  # fast path: P = 128, dims divisible
+    # generic geometries: statistic groups, patches and workspace (host arithmetic only)
     plan.rotations, plan.patch = 4, 256
-    assert native_lib.rfi_tile_stats(C.byref(plan), None, None, None, None) == _native.RFI_E_UNSUPPORTED
+    assert native_lib.rfi_plan_num_tiles(C.byref(plan)) == 8 * 4 * 8
+    assert native_lib.rfi_plan_num_patches(C.byref(plan)) == 8 * 4 * 8 * 4
+    assert native_lib.rfi_plan_workspace_bytes(C.byref(plan)) > 0
+    assert native_lib.rfi_tile_stats(C.byref(plan), None, None, None, None, None) == _native.RFI_E_INVALID
+    assert b"NULL" in native_lib.rfi_last_error_string()
+    plan.patch, plan.channels, plan.times = 100, 250, 330  # padded: one group per output patch
+    assert native_lib.rfi_plan_num_patches(C.byref(plan)) == 8 * 4 * 3 * 4
+    assert native_lib.rfi_plan_num_tiles(C.byref(plan)) == 8 * 4 * 3 * 4
+    plan.patch = 512  # patchify skipped: one patch per rotated waterfall; R = 4 needs a square one
+    assert native_lib.rfi_plan_num_patches(C.byref(plan)) == -1
+    plan.rotations = 2
+    assert native_lib.rfi_plan_num_patches(C.byref(plan)) == 8 * 2
+    assert native_lib.rfi_plan_num_tiles(C.byref(plan)) == 8
 
 
 def test_sass_is_sm100a(native_lib):
