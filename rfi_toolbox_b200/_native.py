@@ -58,6 +58,7 @@ SYMBOLS = {
     "rfi_confusion_counts_segmented": (_I, [_VP, _I, _I, _VP, _I, _I, _I64, _I64, _VP, _VP]),
     "rfi_statistics_workspace_bytes": (C.c_size_t, []),
     "rfi_statistics": (_I, [_VP, _I, _VP, _I64, _VP, _VP, _VP]),
+    "rfi_legacy_permutation": (_I, [_VP, C.POINTER(C.c_int32), _I64, _VP]),
     "rfi_last_error_string": (C.c_char_p, []),
     "rfi_abi_version": (_I, []),
 }
@@ -88,6 +89,24 @@ def load():
         raise NativeError(f"ABI mismatch: library {lib.rfi_abi_version()} != binding {ABI_VERSION}")
     _lib = lib
     return lib
+
+
+def legacy_permutation(n: int):
+    """`np.random.permutation(n)` of the GLOBAL legacy generator (same values, same stream
+    position afterwards), computed by the native helper.  Falls back to NumPy itself when the
+    global generator is not MT19937."""
+    import numpy as np
+
+    state = np.random.get_state()
+    if state[0] != "MT19937" or n < 2:
+        return np.random.permutation(n)
+    key = np.array(state[1], dtype=np.uint32, copy=True)
+    pos = C.c_int32(int(state[2]))
+    out = np.empty(n, dtype=np.int64)
+    rc = load().rfi_legacy_permutation(key.ctypes.data, C.byref(pos), n, out.ctypes.data)
+    check(rc, "rfi_legacy_permutation")
+    np.random.set_state(("MT19937", key, int(pos.value), state[3], state[4]))
+    return out
 
 
 def check(rc: int, what: str):

@@ -244,7 +244,7 @@ class Preprocessor:
                 else:
                     logger.warning("No flagged patches found - keeping all patches")
                     kept = np.arange(n0, dtype=np.int64)
-                perm = np.random.permutation(len(kept))  # :760, the one RNG draw
+                perm = _native.legacy_permutation(len(kept))  # :760, the one RNG draw (global legacy stream)
                 order = kept[perm]
             if num_patches and num_patches < len(order):  # :356-359
                 order = order[:num_patches]

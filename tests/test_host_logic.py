@@ -106,3 +106,19 @@ def test_keep_mask_in_canonical_order(rot):
     want = np.zeros(cmap.size, dtype=bool)
     want[cmap.ravel()] = np.broadcast_to(kt[:, None], cmap.shape).ravel()
     assert np.array_equal(_keep_in_canonical_order(kt, rot), want)
+
+
+def test_legacy_permutation_matches_numpy(native_lib):
+    """The native shuffle (csrc/rfi_host.cu) reproduces np.random.permutation of the global
+    legacy generator -- values AND stream position -- so create_dataset consumes the RNG
+    exactly like preprocessor.py:758-763."""
+    import numpy as np
+    from rfi_toolbox_b200 import _native
+    for seed in range(6):
+        for n in [0, 1, 2, 3, 5, 8, 9, 100, 623, 624, 625, 1248, 4097, 44368, 65537]:
+            np.random.seed(seed); np.random.random(seed * 13)
+            a = np.random.permutation(n); ra = np.random.random(5); ga = np.random.standard_normal(3)
+            np.random.seed(seed); np.random.random(seed * 13)
+            b = _native.legacy_permutation(n); rb = np.random.random(5); gb = np.random.standard_normal(3)
+            assert a.dtype == b.dtype and np.array_equal(a, b), (seed, n)
+            assert np.array_equal(ra, rb) and np.array_equal(ga, gb), (seed, n)
