@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RFI_B200_ABI_VERSION 2
+#define RFI_B200_ABI_VERSION 3
 
 /* status codes */
 #define RFI_OK 0
@@ -75,7 +75,7 @@ typedef struct rfi_plan {
 /* Per ORIGINAL tile statistics produced by rfi_tile_stats and consumed by
  * rfi_write_patches (they are rotation invariant, SURVEY.md section 8 identity (i)).
  * Stored as doubles; for float32/complex64 input each holds an exactly representable
- * float32 value. */
+ * float32 value.  88 bytes. */
 typedef struct rfi_tile_stat {
     double median_before; /* nanmedian of the raw tile           (preprocessor.py:663) */
     double inf_fill;      /* MAD of the finite stretched values  (preprocessor.py:697-702) */
@@ -87,8 +87,17 @@ typedef struct rfi_tile_stat {
     int32_t n_valid;      /* non-NaN samples of the raw tile */
     int32_t n_inf;        /* +-inf samples after the stretch */
     int32_t n_flagged;    /* samples flagged (MAD mode) or non-zero custom flags */
-    int32_t reserved;
+    int32_t route;        /* RFI_TILE_* bits: how the tile was measured, what phase 2 may use */
+    double raw_lo;        /* RFI_TILE_RAW_THRESHOLDS: a sample is flagged iff raw < raw_lo ... */
+    double raw_hi;        /* ... or raw > raw_hi, raw = the loaded value (|z| for magnitude) */
 } rfi_tile_stat_t;
+
+/* rfi_tile_stat_t.route */
+#define RFI_TILE_RAW_THRESHOLDS 1 /* all samples >= +0 and finite after the stretch: every stage is
+                                     monotone, so thr_lo / thr_hi were mapped back EXACTLY to the raw
+                                     domain (raw_lo / raw_hi) and phase 2 labels without normalising */
+#define RFI_TILE_GENERAL 2        /* measured by the general kernel (negative, infinite or inf-filled
+                                     samples, or a sampled bracket that missed) */
 
 /* Host arithmetic only.
  * rfi_plan_num_tiles    entries of the statistics array = statistic groups: one per original

@@ -15,7 +15,7 @@ RFI_F32, RFI_F64, RFI_C64, RFI_C128 = 0, 1, 2, 3
 RFI_STRETCH_NONE, RFI_STRETCH_SQRT, RFI_STRETCH_LOG10 = 0, 1, 2
 RFI_FLAGS_CUSTOM, RFI_FLAGS_MAD, RFI_FLAGS_INFERENCE = 0, 1, 2
 RFI_E_INVALID, RFI_E_UNSUPPORTED, RFI_E_CUDA = -1, -2, -3
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class RfiPlan(C.Structure):
@@ -32,7 +32,8 @@ class RfiTileStat(C.Structure):
     _fields_ = [
         ("median_before", C.c_double), ("inf_fill", C.c_double), ("median_after", C.c_double),
         ("centre", C.c_double), ("mad", C.c_double), ("thr_lo", C.c_double), ("thr_hi", C.c_double),
-        ("n_valid", C.c_int32), ("n_inf", C.c_int32), ("n_flagged", C.c_int32), ("reserved", C.c_int32),
+        ("n_valid", C.c_int32), ("n_inf", C.c_int32), ("n_flagged", C.c_int32), ("route", C.c_int32),
+        ("raw_lo", C.c_double), ("raw_hi", C.c_double),
     ]
 
 
@@ -44,7 +45,7 @@ class RfiStats(C.Structure):
 
 
 TILE_STAT_BYTES = C.sizeof(RfiTileStat)
-assert TILE_STAT_BYTES == 72
+assert TILE_STAT_BYTES == 88
 
 # every symbol include/rfi_b200.h declares: name -> (restype, argtypes)
 _VP, _I, _I64 = C.c_void_p, C.c_int, C.c_int64

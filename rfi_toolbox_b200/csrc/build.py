@@ -17,7 +17,7 @@ PKG = HERE.parent
 LIB = PKG / "_lib" / "librfi_b200.so"
 OBJ = HERE / "build"
 SOURCES = ["rfi_error.cu", "rfi_tiles.cu", "rfi_generic.cu", "rfi_metrics.cu", "rfi_stats.cu", "rfi_host.cu"]
-HEADERS = [HERE / "rfi_common.cuh", HERE / "rfi_tiles.cuh", PKG.parent / "include" / "rfi_b200.h"]
+HEADERS = sorted(HERE.glob("*.cuh")) + [PKG.parent / "include" / "rfi_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

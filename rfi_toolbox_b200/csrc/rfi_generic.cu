@@ -410,7 +410,7 @@ __global__ void gstats_init_kernel(GGeom g, rfi_tile_stat_t* __restrict__ stats,
     rfi_tile_stat_t st;
     st.median_before = st.inf_fill = st.median_after = 0.0;
     st.centre = st.mad = st.thr_lo = st.thr_hi = 0.0;
-    st.n_valid = g.Pr * g.Pc; st.n_inf = 0; st.n_flagged = 0; st.reserved = 0;
+    st.n_valid = g.Pr * g.Pc; st.n_inf = 0; st.n_flagged = 0; st.route = 0; st.raw_lo = st.raw_hi = 0.0;
     stats[grp] = st;
     GSel s;
     s.prefix = 0; s.nxt = ~0ull; s.cle = s.n = s.k1 = s.k2 = 0; s.shift = 0; s.pad = 0;

@@ -1,0 +1,658 @@
+// rfi_stats_mono.cuh -- phase 1 of create_dataset for the common tile: every sample >= +0 and
+// finite after the stretch (magnitudes; no exact zero under LOG10).
+//
+// For such a tile every stage of the reference chain -- x / m (m > 0), sqrt, log10, / m2 -- is
+// monotone non-decreasing after rounding, so the whole job can be done on the RAW samples:
+//
+//   * median: the normalisation median is an order statistic of the raw tile, and the flag
+//     centre is the image of the same two middle order statistics;
+//   * MAD: d(a) = |proc(a) - c| is V-shaped in the raw value a, so "the r smallest deviations"
+//     is a contiguous window of the raw order around the centre;
+//   * labels: proc(a) > thr_hi  <=>  a > raw_hi, with raw_hi = max{a : proc(a) <= thr_hi} found
+//     exactly by a 32-ary search that evaluates proc() itself -- phase 2 then labels a pixel
+//     with two compares on the raw sample, no division or square root.
+//
+// Selection is Floyd-Rivest style instead of bit-by-bit: a stratified 512-sample (every row and
+// every column of the tile contributes 4 samples) is sorted by ONE warp in registers (bitonic,
+// shuffles); two sample ranks 3 sigma either side of the target bracket it; one pass over
+// the 16384 keys in shared memory counts what lies below the bracket and compacts the ~2300
+// keys inside it; the exact rank inside that list is resolved by a 512-bucket linear
+// histogram + one <= 64 element ranking.  All brackets are validated (the answer must fall
+// strictly inside what was proven), otherwise the tile is handed to the general kernel
+// (tile_stats_kernel, RFI_TILE_GENERAL) -- results are exact either way.
+//
+// Cost: ~45 k warp instructions per tile instead of ~150 k for the 32-round register
+// bisection; keys live in shared memory (64 KB per float32 tile, 2 CTAs / SM).
+#pragma once
+#include "rfi_tiles.cuh"
+
+namespace rfi {
+
+constexpr int kMonoNT = 512;     // threads = sample size
+constexpr int kMonoCap = 4096;   // candidate list capacity (expected ~2300 at 3 sigma)
+constexpr int kMonoBuckets = 512;
+constexpr int kMonoSmall = 64;   // max elements of the bucket that holds the answer
+
+template <typename K>
+struct MonoShared {          // static part (must stay small: 3 CTAs / SM)
+    uint32_t hist[kMonoBuckets];
+    K small_a[kMonoSmall], small_b[kMonoSmall];
+    uint32_t cursor, below, n_small_a, n_small_b;
+    uint32_t acc[4];
+    K kmin, kmax;
+    K res1, res2;
+    uint32_t b1, b2, pre1, pre2, cnt1, cnt2;
+    int win[4];
+    int fail;
+};
+
+// ---- one warp sorts 512 keys held 16 per lane, element index e = r * 32 + lane ------------
+template <typename K>
+RFI_DEVINL K shfl_xor_key(K v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+template <typename K>
+RFI_DEVINL void warp_sort512(K (&v)[16], int lane) {
+#pragma unroll
+    for (int k = 2; k <= 512; k <<= 1) {
+        // in-lane stages: partner register r ^ (j / 32); direction fixed by r at compile time
+#pragma unroll
+        for (int j = k >> 1; j >= 32; j >>= 1) {
+            const int jr = j >> 5;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                if ((r & jr) == 0) {
+                    const int r2 = r | jr;
+                    const bool up = (((r << 5) & k) == 0);
+                    const K a = v[r], b = v[r2];
+                    const K mn = a < b ? a : b, mx = a < b ? b : a;
+                    v[r] = up ? mn : mx;
+                    v[r2] = up ? mx : mn;
+                }
+            }
+        }
+        // cross-lane stages
+        const int jstart = (k >> 1) < 16 ? (k >> 1) : 16;
+#pragma unroll 1
+        for (int j = jstart; j > 0; j >>= 1) {
+            const bool lower = (lane & j) == 0;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const bool up = ((((r << 5) | lane) & k) == 0);
+                const K o = shfl_xor_key<K>(v[r], j);
+                const bool keep_min = (lower == up);
+                const K mn = v[r] < o ? v[r] : o, mx = v[r] < o ? o : v[r];
+                v[r] = keep_min ? mn : mx;
+            }
+        }
+    }
+}
+
+// raw key of a non-negative sample: its bit pattern (orders like the value); NaN -> all ones
+template <typename T>
+RFI_DEVINL typename Scalar<T>::key_t raw_key(T a) {
+    using K = typename Scalar<T>::key_t;
+    return is_nan(a) ? ~K(0) : Scalar<T>::bits(a);
+}
+template <typename T>
+RFI_DEVINL T raw_val(typename Scalar<T>::key_t k) { return Scalar<T>::from_bits(k); }
+
+// processed sample WITHOUT the inf fill (the searches walk outside the tile's value range)
+template <typename T>
+RFI_DEVINL T proc_nofill(T a, const PlanDev& p, T m, T m2) {
+    if (p.norm_before && m > T(0)) a = a / m;
+    if (p.stretch != RFI_STRETCH_NONE) a = apply_stretch<T>(a, p.stretch);
+    if (p.norm_after && m2 > T(0)) a = a / m2;
+    return a;
+}
+
+// Exact rank resolution inside the candidate list cand[0 .. M): keys of ranks q1 <= q2 <= q1 + 1.
+// Block-wide, uniform control flow.  Rank q1 by a linear 512-bucket histogram over the list's
+// key range, refined on the answer's bucket until that bucket holds <= 64 keys (ranked by one
+// warp) or a single key value (duplicates); rank q2 = q1 + 1 is then either the same key or the
+// smallest key above it.
+template <typename K, int NT>
+RFI_DEVINL void mono_resolve(const K* cand, uint32_t M, uint32_t q1, uint32_t q2, K& out1, K& out2,
+                             MonoShared<K>& sh) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kBitsK = (int)sizeof(K) * 8;
+    // ---- range of the list
+    K lo = ~K(0), hi = 0;
+    for (uint32_t i = tid; i < M; i += NT) {
+        const K x = cand[i];
+        lo = x < lo ? x : lo;
+        hi = x > hi ? x : hi;
+    }
+    lo = warp_min(lo);
+    hi = warp_max(hi);
+    if (tid == 0) { sh.kmin = ~K(0); sh.kmax = 0; }
+    __syncthreads();
+    if (lane == 0) {
+        if (sizeof(K) == 8) {
+            atomicMin(reinterpret_cast<unsigned long long*>(&sh.kmin), (unsigned long long)lo);
+            atomicMax(reinterpret_cast<unsigned long long*>(&sh.kmax), (unsigned long long)hi);
+        } else {
+            atomicMin(reinterpret_cast<unsigned int*>(&sh.kmin), (unsigned int)lo);
+            atomicMax(reinterpret_cast<unsigned int*>(&sh.kmax), (unsigned int)hi);
+        }
+    }
+    __syncthreads();
+    K klo = sh.kmin, khi = sh.kmax;
+    uint32_t q = q1;  // rank inside [klo, khi]
+    K answer = klo;
+    for (int iter = 0; iter < 8; ++iter) {  // <= ceil(64 / 9) refinements
+        const K width = khi - klo;
+        const int wbits = width == 0 ? 0 : kBitsK - (sizeof(K) == 8 ? __clzll((long long)width) : __clz((int)width));
+        const int shf = wbits > 9 ? wbits - 9 : 0;  // <= 512 buckets
+        for (int b = tid; b < kMonoBuckets; b += NT) sh.hist[b] = 0;
+        if (tid == 0) sh.n_small_a = 0;
+        __syncthreads();
+        for (uint32_t i = tid; i < M; i += NT) {
+            const K x = cand[i];
+            if ((K)(x - klo) <= width) atomicAdd(&sh.hist[(uint32_t)((x - klo) >> shf)], 1u);
+        }
+        __syncthreads();
+        if (warp == 0) {  // bucket of rank q
+            uint32_t local[16], sum = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { local[i] = sh.hist[lane * 16 + i]; sum += local[i]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            uint32_t pre = incl - sum;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const uint32_t c = local[i];
+                if (q >= pre && q < pre + c) { sh.b1 = lane * 16 + i; sh.pre1 = pre; sh.cnt1 = c; }
+                pre += c;
+            }
+        }
+        __syncthreads();
+        const uint32_t b = sh.b1, pre = sh.pre1, cnt = sh.cnt1;
+        const K blo = klo + ((K)b << shf);
+        if (shf == 0) { answer = blo; break; }  // one key value per bucket
+        const K bw = (K(1) << shf) - 1;
+        if (cnt <= (uint32_t)kMonoSmall) {
+            for (uint32_t i = tid; i < M; i += NT) {
+                const K x = cand[i];
+                if ((K)(x - blo) <= bw) sh.small_a[atomicAdd(&sh.n_small_a, 1u)] = x;
+            }
+            __syncthreads();
+            if (warp == 0) {  // element with exactly (q - pre) smaller-or-earlier elements
+                const uint32_t n = sh.n_small_a, want = q - pre;
+                for (uint32_t i = lane; i < n; i += 32) {
+                    const K x = sh.small_a[i];
+                    uint32_t rank = 0;
+                    for (uint32_t j = 0; j < n; ++j) {
+                        const K y = sh.small_a[j];
+                        rank += (y < x || (y == x && j < i)) ? 1u : 0u;
+                    }
+                    if (rank == want) sh.res1 = x;
+                }
+            }
+            __syncthreads();
+            answer = sh.res1;
+            break;
+        }
+        klo = blo; khi = blo + bw; q -= pre;  // refine on the answer's bucket
+        __syncthreads();
+    }
+    out1 = answer;
+    out2 = answer;
+    if (q2 != q1) {  // rank q1 + 1: the same key if duplicates reach it, else the smallest key above
+        uint32_t cle = 0;
+        K nxt = ~K(0);
+        for (uint32_t i = tid; i < M; i += NT) {
+            const K x = cand[i];
+            cle += (x <= answer) ? 1u : 0u;
+            const K y = x > answer ? x : ~K(0);
+            nxt = y < nxt ? y : nxt;
+        }
+        cle = __reduce_add_sync(0xffffffffu, cle);
+        nxt = warp_min(nxt);
+        if (tid == 0) { sh.cnt2 = 0; sh.kmin = ~K(0); }
+        __syncthreads();
+        if (lane == 0) {
+            atomicAdd(&sh.cnt2, cle);
+            if (sizeof(K) == 8) atomicMin(reinterpret_cast<unsigned long long*>(&sh.kmin), (unsigned long long)nxt);
+            else atomicMin(reinterpret_cast<unsigned int*>(&sh.kmin), (unsigned int)nxt);
+        }
+        __syncthreads();
+        if (q2 >= sh.cnt2) out2 = sh.kmin;
+    }
+    __syncthreads();
+}
+
+template <int DT, int NT>
+__global__ void __launch_bounds__(NT, (sizeof(typename In<DT>::T) == 4) ? 2 : 1)
+tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __restrict__ flags,
+                       rfi_tile_stat_t* __restrict__ stats) {
+    using T = typename In<DT>::T;
+    using K = typename Scalar<T>::key_t;
+    static_assert(NT == kMonoNT, "one sample per thread");
+    constexpr int E = kP * kP / NT;  // 32 keys per thread
+    constexpr int G = E / 4;
+    constexpr int RS = NT / 32;
+    constexpr K kExcl = ~K(0);
+    constexpr K kInfKey = sizeof(T) == 4 ? K(0x7f800000u) : (K(0x7ff00000u) << 32);
+    constexpr K kSignBit = K(1) << (Scalar<T>::kBits - 1);
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    K* keys = reinterpret_cast<K*>(smem_raw);   // [E/4][NT][4]
+    K* cand = keys + kP * kP;                   // [kMonoCap]
+    K* samp = cand + kMonoCap;                  // [NT] sorted raw sample
+    __shared__ MonoShared<K> sh;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long tile = blockIdx.x;
+    const int per = p.nh * p.nw;
+    const long long w = tile / per;
+    const int ti = (int)((tile % per) / p.nw), tj = (int)(tile % p.nw);
+    const size_t origin = ((size_t)w * p.channels + (size_t)ti * kP) * p.times + (size_t)tj * kP;
+
+    // uniform early-out helper: hand the tile to the general kernel
+    // (the reason is kept in the upper bits of `route` until the general kernel overwrites it;
+    //  scripts/diag_stats.py reads it)
+    auto give_up = [&](int reason) {
+        if (tid == 0) stats[tile].route = RFI_TILE_GENERAL | (reason << 8);
+    };
+
+    // ---- load: magnitude fused into the 128-bit loads, raw keys to shared memory
+    if (tid < 4) sh.acc[tid] = 0;
+    if (tid == 0) { sh.cursor = 0; sh.below = 0; }
+    __syncthreads();
+    uint32_t nvalid = 0, nodd = 0;
+    // this thread's sample, element e_s = g * 4 + i of its 32 (row g * 16 + warp, column
+    // 4 * lane + i): stratified so that every row AND every column of the tile gives 4 samples
+    const int e_s = (((lane + warp * 3) & 7) << 2) | (((lane >> 3) + warp) & 3);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const size_t idx = origin + (size_t)(g * RS + warp) * p.times + lane * 4;
+        T q[4];
+        load4_mag<DT>(data, idx, q);
+        K k4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const K b = Scalar<T>::bits(q[i]);
+            const bool nan = (b & ~kSignBit) > kInfKey;
+            // odd: negative (sign bit, -0.0 included) or +inf -> not a monotone tile
+            nodd += (!nan && ((b & kSignBit) != 0 || b == kInfKey)) ? 1u : 0u;
+            nvalid += nan ? 0u : 1u;
+            k4[i] = nan ? kExcl : b;
+        }
+        if (sizeof(K) == 4) {
+            *reinterpret_cast<uint4*>(keys + ((size_t)g * NT + tid) * 4) =
+                make_uint4((uint32_t)k4[0], (uint32_t)k4[1], (uint32_t)k4[2], (uint32_t)k4[3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) keys[((size_t)g * NT + tid) * 4 + i] = k4[i];
+        }
+    }
+    samp[tid] = keys[((size_t)(e_s >> 2) * NT + tid) * 4 + (e_s & 3)];  // own store, no barrier needed
+    {
+        const uint32_t a = __reduce_add_sync(0xffffffffu, nvalid), b = __reduce_add_sync(0xffffffffu, nodd);
+        if (lane == 0) { atomicAdd(&sh.acc[0], a); if (b) atomicAdd(&sh.acc[1], b); }
+    }
+    __syncthreads();
+    const uint32_t nv = sh.acc[0];
+    if (sh.acc[1] != 0 || nv < 64) { give_up(1); return; }
+
+    // ---- warp 0 sorts the sample
+    if (warp == 0) {
+        K v[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = samp[r * 32 + lane];
+        warp_sort512<K>(v, lane);
+        uint32_t sv = 0;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) { samp[r * 32 + lane] = v[r]; sv += (v[r] != kExcl) ? 1u : 0u; }
+        sv = __reduce_add_sync(0xffffffffu, sv);
+        if (lane == 0) sh.acc[2] = sv;
+    }
+    __syncthreads();
+    const int sv = (int)sh.acc[2];  // valid samples (sorted first)
+    if (sv < 64) { give_up(2); return; }
+    const int delta = (int)(1.5f * sqrtf((float)sv)) + 2;  // 3 sigma of a sample rank
+
+    const bool real_branch = !In<DT>::cplx || p.magnitude;
+    const bool need_median = real_branch && (p.norm_before || p.norm_after) || p.flag_mode == RFI_FLAGS_MAD;
+    const uint32_t k1 = (nv - 1) >> 1, k2 = nv >> 1;
+
+    // ================= median of the raw tile (two middle order statistics) =================
+    K v1k = 0, v2k = 0;
+    if (need_median) {
+        const int rho = (int)(((float)(2 * k1 + 1) * (float)sv) / (float)(2 * nv));
+        const int ilo = rho - delta, ihi = rho + delta + 1;
+        const K lo = ilo < 0 ? K(0) : samp[ilo];
+        const K hi = ihi >= sv ? kExcl - 1 : samp[ihi];
+        const K span = hi - lo;
+        uint32_t below = 0, mine = 0;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            K k4[4];
+            if (sizeof(K) == 4) {
+                const uint4 q = *reinterpret_cast<const uint4*>(keys + ((size_t)g * NT + tid) * 4);
+                k4[0] = q.x; k4[1] = q.y; k4[2] = q.z; k4[3] = q.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) k4[i] = keys[((size_t)g * NT + tid) * 4 + i];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                below += (k4[i] < lo) ? 1u : 0u;
+                mine += ((K)(k4[i] - lo) <= span) ? 1u : 0u;
+            }
+        }
+        // warp scan of `mine` -> write offsets; block totals through two shared atomics per warp
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        uint32_t base = 0;
+        const uint32_t wb = __reduce_add_sync(0xffffffffu, below);
+        if (lane == 31) { base = atomicAdd(&sh.cursor, incl); atomicAdd(&sh.below, wb); }
+        base = __shfl_sync(0xffffffffu, base, 31);
+        uint32_t at = base + incl - mine;
+        __syncthreads();
+        const uint32_t M = sh.cursor, B = sh.below;
+        if (M > (uint32_t)kMonoCap || B > k1 || k2 >= B + M) { give_up(3); return; }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            K k4[4];
+            if (sizeof(K) == 4) {
+                const uint4 q = *reinterpret_cast<const uint4*>(keys + ((size_t)g * NT + tid) * 4);
+                k4[0] = q.x; k4[1] = q.y; k4[2] = q.z; k4[3] = q.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) k4[i] = keys[((size_t)g * NT + tid) * 4 + i];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if ((K)(k4[i] - lo) <= span) cand[at++] = k4[i];
+        }
+        __syncthreads();
+        mono_resolve<K, NT>(cand, M, k1 - B, k2 - B, v1k, v2k, sh);
+    }
+
+    // ================= statistics in the processed domain =================
+    T m = T(0), m2 = T(0);
+    T v1 = raw_val<T>(v1k), v2 = raw_val<T>(v2k);
+    if (real_branch && p.norm_before) m = median_of_pair<T>(v1, v2, nv);
+    // processed images of the two middle order statistics (monotone chain)
+    T s1 = v1, s2 = v2;
+    if (real_branch) {
+        if (p.norm_before && m > T(0)) { s1 = s1 / m; s2 = s2 / m; }
+        if (p.stretch != RFI_STRETCH_NONE) { s1 = apply_stretch<T>(s1, p.stretch); s2 = apply_stretch<T>(s2, p.stretch); }
+        if (p.norm_after) {
+            m2 = median_of_pair<T>(s1, s2, nv);
+            if (m2 > T(0)) { s1 = s1 / m2; s2 = s2 / m2; }
+        }
+    }
+    const PlanDev pp = [&]() { PlanDev q = p; if (!real_branch) { q.norm_before = q.norm_after = 0; q.stretch = RFI_STRETCH_NONE; } return q; }();
+    // the extreme samples must stay finite through the chain (else: inf fill -> general kernel)
+    {
+        // min / max raw key over the tile -> finite after the stretch?
+        K lo = kExcl, hi = 0;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const K x = keys[((size_t)g * NT + tid) * 4 + i];
+                lo = x < lo ? x : lo;
+                const K y = x == kExcl ? K(0) : x;
+                hi = y > hi ? y : hi;
+            }
+        }
+        lo = warp_min(lo);
+        hi = warp_max(hi);
+        if (tid == 0) { sh.kmin = kExcl; sh.kmax = 0; }
+        __syncthreads();
+        if (lane == 0) {
+            if (sizeof(K) == 8) {
+                atomicMin(reinterpret_cast<unsigned long long*>(&sh.kmin), (unsigned long long)lo);
+                atomicMax(reinterpret_cast<unsigned long long*>(&sh.kmax), (unsigned long long)hi);
+            } else {
+                atomicMin(reinterpret_cast<unsigned int*>(&sh.kmin), (unsigned int)lo);
+                atomicMax(reinterpret_cast<unsigned int*>(&sh.kmax), (unsigned int)hi);
+            }
+        }
+        __syncthreads();
+        const T pmin = proc_nofill<T>(raw_val<T>(sh.kmin), pp, m, m2);
+        const T pmax = proc_nofill<T>(raw_val<T>(sh.kmax), pp, m, m2);
+        __syncthreads();
+        if (is_inf(pmin) || is_inf(pmax) || is_nan(pmin) || is_nan(pmax)) { give_up(5); return; }
+    }
+
+    T c = T(0), d = T(0), thr_lo = T(0), thr_hi = T(0);
+    T raw_lo = T(0), raw_hi = Scalar<T>::inf();
+    uint32_t nflag = 0;
+    if (p.flag_mode == RFI_FLAGS_MAD) {
+        c = median_of_pair<T>(s1, s2, nv);
+        // ---- deviations of the sorted raw sample: V-shaped in the sample index
+        K* dsamp = cand;  // [NT], free until the candidates are compacted
+        bool below_c = false;
+        if (tid < sv) {
+            const T ps = proc_nofill<T>(raw_val<T>(samp[tid]), pp, m, m2);
+            below_c = ps < c;
+            dsamp[tid] = to_key<T>(fabs_(ps - c));
+        }
+        if (tid == 0) { sh.win[0] = sh.win[1] = sh.win[2] = sh.win[3] = -1; sh.acc[3] = 0; sh.cursor = 0; sh.below = 0; }
+        __syncthreads();
+        {
+            const uint32_t nb = __popc(__ballot_sync(0xffffffffu, below_c));
+            if (lane == 0 && nb) atomicAdd(&sh.acc[3], nb);
+        }
+        __syncthreads();
+        const int ju = (int)sh.acc[3];  // first sample on the upper arm (proc >= c)
+        const int rho = (int)(((float)(2 * k1 + 1) * (float)sv) / (float)(2 * nv));
+        const int r_in = rho - delta, r_out = rho + delta + 2;  // samples inside the inner / outer window
+        if (r_in < 1 || r_out > sv - 1) { give_up(6); return; }
+        // window of r consecutive samples holding the r smallest deviations: smallest start i
+        // with (i + r past the end) or (d[i] <= d[i + r] and i + r on the upper arm)
+        for (int which = 0; which < 2; ++which) {
+            const int r = which == 0 ? r_in : r_out;
+            const int i = tid;
+            if (i + r <= sv) {
+                auto pred = [&](int s) {
+                    if (s + r >= sv) return true;
+                    return dsamp[s] <= dsamp[s + r] && (s + r) >= ju;
+                };
+                if (pred(i) && (i == 0 || !pred(i - 1))) { sh.win[which * 2] = i; sh.win[which * 2 + 1] = i + r - 1; }
+            }
+        }
+        __syncthreads();
+        int il = sh.win[0], iu = sh.win[1], il2 = sh.win[2], iu2 = sh.win[3];
+        if (il < 0 || il2 < 0) { give_up(7); return; }
+        il2 = il2 < il ? il2 : il;
+        iu2 = iu2 > iu ? iu2 : iu;
+        // both windows must straddle the centre (V-shape argument)
+        if (!(il2 <= il && il < ju && ju <= iu && iu <= iu2 && il2 < ju)) { give_up(8); return; }
+        // candidates reach one sample BEYOND the outer window on each side (or to the end of the
+        // value range), so that everything outside is proven to deviate at least d_out
+        const K L1 = samp[il], U1 = samp[iu];
+        const K L2 = il2 > 0 ? samp[il2 - 1] : K(0);
+        const K U2 = iu2 + 1 < sv ? samp[iu2 + 1] : kExcl - 1;
+        const K d_in = dsamp[il] > dsamp[iu] ? dsamp[il] : dsamp[iu];       // interior deviations <= this
+        const K d_lo2 = il2 > 0 ? dsamp[il2 - 1] : kExcl, d_up2 = iu2 + 1 < sv ? dsamp[iu2 + 1] : kExcl;
+        const K d_out = d_lo2 < d_up2 ? d_lo2 : d_up2;                      // exterior deviations >= this
+        __syncthreads();  // dsamp (= cand) is overwritten below
+        const K span_all = U2 - L2;
+        const K w_in = U1 > L1 ? U1 - L1 - 1 : K(0);
+        uint32_t inside = 0, mine = 0;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            K k4[4];
+            if (sizeof(K) == 4) {
+                const uint4 q = *reinterpret_cast<const uint4*>(keys + ((size_t)g * NT + tid) * 4);
+                k4[0] = q.x; k4[1] = q.y; k4[2] = q.z; k4[3] = q.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) k4[i] = keys[((size_t)g * NT + tid) * 4 + i];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool in_all = (K)(k4[i] - L2) <= span_all;
+                const bool interior = (K)(k4[i] - L1 - 1) < w_in;
+                inside += interior ? 1u : 0u;
+                mine += (in_all && !interior) ? 1u : 0u;
+            }
+        }
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        uint32_t base = 0;
+        const uint32_t wb = __reduce_add_sync(0xffffffffu, inside);
+        if (lane == 31) { base = atomicAdd(&sh.cursor, incl); atomicAdd(&sh.below, wb); }
+        base = __shfl_sync(0xffffffffu, base, 31);
+        uint32_t at = base + incl - mine;
+        __syncthreads();
+        const uint32_t M = sh.cursor, B = sh.below;
+        if (M > (uint32_t)kMonoCap || B > k1 || k2 >= B + M) { give_up(9); return; }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            K k4[4];
+            if (sizeof(K) == 4) {
+                const uint4 q = *reinterpret_cast<const uint4*>(keys + ((size_t)g * NT + tid) * 4);
+                k4[0] = q.x; k4[1] = q.y; k4[2] = q.z; k4[3] = q.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) k4[i] = keys[((size_t)g * NT + tid) * 4 + i];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool in_all = (K)(k4[i] - L2) <= span_all;
+                const bool interior = (K)(k4[i] - L1 - 1) < w_in;
+                if (in_all && !interior) cand[at++] = k4[i];
+            }
+        }
+        __syncthreads();
+        // exact deviation of every candidate, in place
+        for (uint32_t i = tid; i < M; i += NT) {
+            const T ps = proc_nofill<T>(raw_val<T>(cand[i]), pp, m, m2);
+            cand[i] = to_key<T>(fabs_(ps - c));
+        }
+        __syncthreads();
+        K r1k, r2k;
+        mono_resolve<K, NT>(cand, M, k1 - B, k2 - B, r1k, r2k, sh);
+        // the answers must lie inside what the windows prove
+        if (r1k < d_in || r2k > d_out) { give_up(11); return; }
+        d = median_of_pair<T>(from_key<T>(r1k), from_key<T>(r2k), nv);
+        const T ds = d * (T)p.sigma;
+        thr_hi = c + ds;
+        thr_lo = c - ds;
+
+        // ---- exact raw-domain thresholds: 32-ary search evaluating the chain itself (warp 0)
+        if (warp == 0) {
+            constexpr K kTop = kInfKey;  // first key that is not a finite value
+            // raw_hi = max{a finite : proc(a) <= thr_hi}
+            K res_hi, res_lo;
+            {
+                auto ok = [&](K k) { return proc_nofill<T>(raw_val<T>(k), pp, m, m2) <= thr_hi; };
+                if (!(thr_hi == thr_hi)) res_hi = kTop;            // NaN threshold: nothing above it
+                else if (!ok(K(0))) res_hi = kExcl;                // everything is above (marker)
+                else {
+                    K a = 0, b = kTop;                              // ok(a), !ok(b) (b == kTop: sentinel)
+                    if (ok(kTop - 1)) a = kTop - 1;
+                    while (b - a > 1 && a != kTop - 1) {
+                        const K step = (b - a + 32) / 33;
+                        K t = a + (K)(lane + 1) * step;
+                        const bool inr = t < b;
+                        const bool good = inr && ok(t);
+                        const uint32_t bal = __ballot_sync(0xffffffffu, good);
+                        const int n = __popc(bal);                  // monotone: a prefix of the lanes
+                        const K na = a + (K)n * step;
+                        const K nb = a + (K)(n + 1) * step;
+                        a = na;
+                        b = nb < b ? nb : b;
+                    }
+                    res_hi = a;
+                }
+            }
+            // raw_lo = min{a finite : proc(a) >= thr_lo}
+            {
+                auto ok = [&](K k) { return proc_nofill<T>(raw_val<T>(k), pp, m, m2) >= thr_lo; };
+                if (!(thr_lo == thr_lo)) res_lo = 0;               // NaN threshold: nothing below it
+                else if (ok(K(0))) res_lo = 0;
+                else if (!ok(kTop - 1)) res_lo = kTop;              // every finite sample is below
+                else {
+                    K a = 0, b = kTop - 1;                          // !ok(a), ok(b)
+                    while (b - a > 1) {
+                        const K step = (b - a + 32) / 33;
+                        K t = a + (K)(lane + 1) * step;
+                        const bool inr = t < b;
+                        const bool bad = inr && !ok(t);
+                        const uint32_t bal = __ballot_sync(0xffffffffu, bad);
+                        const int n = __popc(bal);                  // lanes still below the threshold
+                        const K na = a + (K)n * step;
+                        const K nb = a + (K)(n + 1) * step;
+                        a = na;
+                        b = nb < b ? nb : b;
+                    }
+                    res_lo = b;
+                }
+            }
+            if (lane == 0) { sh.res1 = res_lo; sh.res2 = res_hi; }
+        }
+        __syncthreads();
+        const K klo = sh.res1, khi = sh.res2;
+        // value form for phase 2: flagged iff raw < raw_lo or raw > raw_hi
+        raw_lo = raw_val<T>(klo);                                   // kTop -> +inf: every finite sample
+        raw_hi = (khi == kExcl) ? T(-1) : raw_val<T>(khi);          // kTop -> +inf: nothing
+        // ---- flagged samples, on the raw keys
+        const K khi_cmp = (khi == kExcl) ? K(0) : khi;              // "everything": key > -1
+        const bool all_hi = (khi == kExcl);
+        uint32_t nf = 0;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const K x = keys[((size_t)g * NT + tid) * 4 + i];
+                const bool f = (x != kExcl) && (all_hi || x > khi_cmp || x < klo);
+                nf += f ? 1u : 0u;
+            }
+        }
+        nf = __reduce_add_sync(0xffffffffu, nf);
+        if (tid == 0) sh.acc[3] = 0;
+        __syncthreads();
+        if (lane == 0 && nf) atomicAdd(&sh.acc[3], nf);
+        __syncthreads();
+        nflag = sh.acc[3];
+    } else if (p.flag_mode == RFI_FLAGS_CUSTOM) {
+        uint32_t nf = 0;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const size_t idx = origin + (size_t)(g * RS + warp) * p.times + lane * 4;
+            const uint32_t f4 = __ldg(reinterpret_cast<const uint32_t*>(flags + idx));
+            const uint32_t nz = (((f4 & 0x7f7f7f7fu) + 0x7f7f7f7fu) | f4) & 0x80808080u;
+            nf += __popc(nz);
+        }
+        nf = __reduce_add_sync(0xffffffffu, nf);
+        if (tid == 0) sh.acc[3] = 0;
+        __syncthreads();
+        if (lane == 0 && nf) atomicAdd(&sh.acc[3], nf);
+        __syncthreads();
+        nflag = sh.acc[3];
+    }
+
+    if (tid == 0) {
+        rfi_tile_stat_t st;
+        st.median_before = (real_branch && p.norm_before) ? (double)m : 0.0;
+        st.inf_fill = 0.0;
+        st.median_after = (real_branch && p.norm_after) ? (double)m2 : 0.0;
+        st.centre = (double)c; st.mad = (double)d;
+        st.thr_lo = (double)thr_lo; st.thr_hi = (double)thr_hi;
+        st.n_valid = (int)nv; st.n_inf = 0; st.n_flagged = (int)nflag;
+        st.route = (p.flag_mode == RFI_FLAGS_MAD) ? RFI_TILE_RAW_THRESHOLDS : 0;
+        st.raw_lo = (double)raw_lo; st.raw_hi = (double)raw_hi;
+        stats[tile] = st;
+    }
+}
+
+}  // namespace rfi

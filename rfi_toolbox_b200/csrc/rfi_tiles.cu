@@ -13,6 +13,7 @@
 // (restated in SURVEY.md Appendix A).  Statistics are rotation invariant for dims divisible
 // by P, so they are computed once per original tile and shared by the R rotated patches.
 #include "rfi_tiles.cuh"
+#include "rfi_stats_mono.cuh"
 
 namespace rfi {
 
@@ -34,7 +35,9 @@ namespace rfi {
 template <int DT, int NT>
 __global__ void __launch_bounds__(NT, (sizeof(typename In<DT>::T) == 4) ? 2 : 1)
 tile_stats_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __restrict__ flags,
-                  rfi_tile_stat_t* __restrict__ stats) {
+                  rfi_tile_stat_t* __restrict__ stats, int only_general) {
+    // second launch after tile_stats_mono_kernel: only the tiles it handed over
+    if (only_general && (stats[blockIdx.x].route & 0xff) != RFI_TILE_GENERAL) return;
     using T = typename In<DT>::T;
     using K = typename Scalar<T>::key_t;
     constexpr int E = kP * kP / NT;  // samples per thread
@@ -74,7 +77,7 @@ tile_stats_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __res
     if (threadIdx.x == 0) {
         st.median_before = st.inf_fill = st.median_after = 0.0;
         st.centre = st.mad = st.thr_lo = st.thr_hi = 0.0;
-        st.n_valid = 0; st.n_inf = 0; st.n_flagged = 0; st.reserved = 0;
+        st.n_valid = 0; st.n_inf = 0; st.n_flagged = 0; st.route = only_general ? (stats[blockIdx.x].route | 0) : RFI_TILE_GENERAL; st.raw_lo = st.raw_hi = 0.0;
     }
 
     // non-NaN samples (recounted before every general median: inf / inf can create a NaN)
@@ -247,7 +250,7 @@ flags_count_kernel(PlanDev p, const uint8_t* __restrict__ flags, rfi_tile_stat_t
         rfi_tile_stat_t st;
         st.median_before = st.inf_fill = st.median_after = 0.0;
         st.centre = st.mad = st.thr_lo = st.thr_hi = 0.0;
-        st.n_valid = kP * kP; st.n_inf = 0; st.n_flagged = (int)nf; st.reserved = 0;
+        st.n_valid = kP * kP; st.n_inf = 0; st.n_flagged = (int)nf; st.route = 0; st.raw_lo = st.raw_hi = 0.0;
         stats[tile] = st;
     }
 }
@@ -507,10 +510,15 @@ template <int DT, int NT>
 static int launch_stats(const PlanDev& d, long long tiles, const void* data, const uint8_t* flags,
                         rfi_tile_stat_t* stats, cudaStream_t st) {
     using K = typename Scalar<typename In<DT>::T>::key_t;
+    auto mono = tile_stats_mono_kernel<DT, kMonoNT>;
+    size_t msmem = (size_t)(kP * kP + kMonoCap + kMonoNT) * sizeof(K);
+    RFI_CUDA_TRY(cudaFuncSetAttribute(mono, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+    mono<<<(unsigned)tiles, kMonoNT, msmem, st>>>(d, data, flags, stats);
+    // tiles with negative / infinite / inf-filled samples, or whose sampled bracket missed
     auto kern = tile_stats_kernel<DT, NT>;
     size_t smem = (size_t)kP * kP * sizeof(K);
     RFI_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)tiles, NT, smem, st>>>(d, data, flags, stats);
+    kern<<<(unsigned)tiles, NT, smem, st>>>(d, data, flags, stats, 1);
     return RFI_OK;
 }
 

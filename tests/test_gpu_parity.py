@@ -150,7 +150,7 @@ def test_tile_statistics_exact(native_lib):
     st = np.frombuffer(raw.tobytes(), dtype=np.dtype([
         ("median_before", "f8"), ("inf_fill", "f8"), ("median_after", "f8"), ("centre", "f8"),
         ("mad", "f8"), ("thr_lo", "f8"), ("thr_hi", "f8"), ("n_valid", "i4"), ("n_inf", "i4"),
-        ("n_flagged", "i4"), ("reserved", "i4")]))
+        ("n_flagged", "i4"), ("route", "i4"), ("raw_lo", "f8"), ("raw_hi", "f8")]))
     tiles = np.concatenate([oracle.tile(w, 128) for bl in data for w in bl])
     for k, t in enumerate(tiles):
         m = np.nanmedian(t)
