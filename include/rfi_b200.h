@@ -180,6 +180,11 @@ int rfi_statistics(const void* data, int dtype, const uint8_t* flags, int64_t n,
  * after the call is what the reference leaves behind. */
 int rfi_legacy_permutation(uint32_t* mt_key, int32_t* mt_pos, int64_t n, int64_t* out);
 
+/* Self test (used by tests/): counts the inputs t in [1, 2] (all 2^23 + 1 float32 values) for
+ * which the range-restricted square root of the magnitude kernel differs from sqrt.rn.f32.
+ *   mismatches_dev  device uint64, ACCUMULATED into (caller zeroes); must end up 0 */
+int rfi_selftest_sqrt_unit(unsigned long long* mismatches_dev, void* stream);
+
 const char* rfi_last_error_string(void);
 int rfi_abi_version(void);
 

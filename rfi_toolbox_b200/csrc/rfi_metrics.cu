@@ -228,3 +228,20 @@ extern "C" int rfi_confusion_counts_segmented(const void* pred, int elem_pred, i
     return rfi::dispatch(pred, elem_pred, is_float_pred, truth, elem_true, is_float_true, n_seg * seg, n_seg,
                          seg, counts, (cudaStream_t)stream);
 }
+
+// ---- self-test hook (tests only): sqrt_rn_unit vs sqrt.rn.f32 over [1, 2] ---------------------
+#include "rfi_tiles.cuh"
+namespace rfi {
+__global__ void sqrt_unit_check_kernel(unsigned long long* mismatches) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // 0 .. 2^23
+    if (i > (1u << 23)) return;
+    const float t = __uint_as_float(0x3f800000u + i);
+    if (__float_as_uint(sqrt_rn_unit(t)) != __float_as_uint(__fsqrt_rn(t))) atomicAdd(mismatches, 1ull);
+}
+}  // namespace rfi
+extern "C" int rfi_selftest_sqrt_unit(unsigned long long* mismatches_dev, void* stream) {
+    using namespace rfi;
+    sqrt_unit_check_kernel<<<((1u << 23) + 256) / 256 + 1, 256, 0, (cudaStream_t)stream>>>(mismatches_dev);
+    RFI_CUDA_TRY(cudaGetLastError());
+    return RFI_OK;
+}

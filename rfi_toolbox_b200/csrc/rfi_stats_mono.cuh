@@ -98,7 +98,7 @@ RFI_DEVINL T raw_val(typename Scalar<T>::key_t k) { return Scalar<T>::from_bits(
 
 // processed sample WITHOUT the inf fill (the searches walk outside the tile's value range)
 template <typename T>
-RFI_DEVINL T proc_nofill(T a, const PlanDev& p, T m, T m2) {
+__device__ __noinline__ T proc_nofill(T a, const PlanDev& p, T m, T m2) {
     if (p.norm_before && m > T(0)) a = a / m;
     if (p.stretch != RFI_STRETCH_NONE) a = apply_stretch<T>(a, p.stretch);
     if (p.norm_after && m2 > T(0)) a = a / m2;
@@ -180,17 +180,19 @@ RFI_DEVINL void mono_resolve(const K* cand, uint32_t M, uint32_t q1, uint32_t q2
                 if ((K)(x - blo) <= bw) sh.small_a[atomicAdd(&sh.n_small_a, 1u)] = x;
             }
             __syncthreads();
-            if (warp == 0) {  // element with exactly (q - pre) smaller-or-earlier elements
+            {   // element with exactly (q - pre) smaller-or-earlier elements: 8 threads per element
                 const uint32_t n = sh.n_small_a, want = q - pre;
-                for (uint32_t i = lane; i < n; i += 32) {
-                    const K x = sh.small_a[i];
-                    uint32_t rank = 0;
-                    for (uint32_t j = 0; j < n; ++j) {
-                        const K y = sh.small_a[j];
-                        rank += (y < x || (y == x && j < i)) ? 1u : 0u;
-                    }
-                    if (rank == want) sh.res1 = x;
+                const uint32_t i = tid >> 3, sub = tid & 7;
+                const K x = i < n ? sh.small_a[i] : ~K(0);
+                uint32_t rank = 0;
+                for (uint32_t j = sub; j < n; j += 8) {
+                    const K y = sh.small_a[j];
+                    rank += (y < x || (y == x && j < i)) ? 1u : 0u;
                 }
+                rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+                rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+                rank += __shfl_xor_sync(0xffffffffu, rank, 4);
+                if (sub == 0 && i < n && rank == want) sh.res1 = x;
             }
             __syncthreads();
             answer = sh.res1;
@@ -259,28 +261,28 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
         if (tid == 0) stats[tile].route = RFI_TILE_GENERAL | (reason << 8);
     };
 
-    // ---- load: magnitude fused into the 128-bit loads, raw keys to shared memory
+    // ---- load: magnitude fused into the 128-bit loads, raw bit patterns to shared memory.
+    // Special values cost ONE instruction per sample here: the running unsigned max of the bit
+    // patterns is >= the +inf pattern iff the tile holds a NaN, an inf or a negative value
+    // (sign bit); only then does a second pass classify them.
     if (tid < 4) sh.acc[tid] = 0;
-    if (tid == 0) { sh.cursor = 0; sh.below = 0; }
+    if (tid == 0) { sh.cursor = 0; sh.below = 0; sh.kmin = kExcl; sh.kmax = 0; }
     __syncthreads();
-    uint32_t nvalid = 0, nodd = 0;
     // this thread's sample, element e_s = g * 4 + i of its 32 (row g * 16 + warp, column
     // 4 * lane + i): stratified so that every row AND every column of the tile gives 4 samples
     const int e_s = (((lane + warp * 3) & 7) << 2) | (((lane >> 3) + warp) & 3);
+    K bmax = 0, bmin = kExcl;
 #pragma unroll
     for (int g = 0; g < G; ++g) {
         const size_t idx = origin + (size_t)(g * RS + warp) * p.times + lane * 4;
         T q[4];
-        load4_mag<DT>(data, idx, q);
+        load4_mag_fast<DT>(data, idx, q);
         K k4[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const K b = Scalar<T>::bits(q[i]);
-            const bool nan = (b & ~kSignBit) > kInfKey;
-            // odd: negative (sign bit, -0.0 included) or +inf -> not a monotone tile
-            nodd += (!nan && ((b & kSignBit) != 0 || b == kInfKey)) ? 1u : 0u;
-            nvalid += nan ? 0u : 1u;
-            k4[i] = nan ? kExcl : b;
+            k4[i] = Scalar<T>::bits(q[i]);
+            bmax = k4[i] > bmax ? k4[i] : bmax;
+            bmin = k4[i] < bmin ? k4[i] : bmin;
         }
         if (sizeof(K) == 4) {
             *reinterpret_cast<uint4*>(keys + ((size_t)g * NT + tid) * 4) =
@@ -290,26 +292,99 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
             for (int i = 0; i < 4; ++i) keys[((size_t)g * NT + tid) * 4 + i] = k4[i];
         }
     }
-    samp[tid] = keys[((size_t)(e_s >> 2) * NT + tid) * 4 + (e_s & 3)];  // own store, no barrier needed
-    {
-        const uint32_t a = __reduce_add_sync(0xffffffffu, nvalid), b = __reduce_add_sync(0xffffffffu, nodd);
-        if (lane == 0) { atomicAdd(&sh.acc[0], a); if (b) atomicAdd(&sh.acc[1], b); }
+    bmax = warp_max(bmax);
+    bmin = warp_min(bmin);
+    if (lane == 0) {
+        if (sizeof(K) == 8) {
+            atomicMin(reinterpret_cast<unsigned long long*>(&sh.kmin), (unsigned long long)bmin);
+            atomicMax(reinterpret_cast<unsigned long long*>(&sh.kmax), (unsigned long long)bmax);
+        } else {
+            atomicMin(reinterpret_cast<unsigned int*>(&sh.kmin), (unsigned int)bmin);
+            atomicMax(reinterpret_cast<unsigned int*>(&sh.kmax), (unsigned int)bmax);
+        }
     }
     __syncthreads();
-    const uint32_t nv = sh.acc[0];
-    if (sh.acc[1] != 0 || nv < 64) { give_up(1); return; }
+    K tile_min = sh.kmin, tile_max = sh.kmax;  // raw extremes (valid samples)
+    uint32_t nv = kP * kP;
+    if (tile_max >= kInfKey) {
+        // rare: NaN (-> excluded key), +inf or a negative value (-> general kernel)
+        uint32_t nnan = 0, nodd = 0;
+        K vmax = 0, vmin = kExcl;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                K& x = keys[((size_t)g * NT + tid) * 4 + i];
+                const K b = x;
+                const bool nan = (b & ~kSignBit) > kInfKey;
+                nodd += (!nan && ((b & kSignBit) != 0 || b == kInfKey)) ? 1u : 0u;
+                nnan += nan ? 1u : 0u;
+                if (nan) x = kExcl;
+                else { vmax = b > vmax ? b : vmax; vmin = b < vmin ? b : vmin; }
+            }
+        }
+        __syncthreads();  // every thread has read the first-pass extremes
+        if (tid == 0) { sh.kmin = kExcl; sh.kmax = 0; }
+        __syncthreads();
+        nnan = __reduce_add_sync(0xffffffffu, nnan);
+        nodd = __reduce_add_sync(0xffffffffu, nodd);
+        vmax = warp_max(vmax);
+        vmin = warp_min(vmin);
+        if (lane == 0) {
+            if (nnan) atomicAdd(&sh.acc[0], nnan);
+            if (nodd) atomicAdd(&sh.acc[1], nodd);
+            if (sizeof(K) == 8) {
+                atomicMin(reinterpret_cast<unsigned long long*>(&sh.kmin), (unsigned long long)vmin);
+                atomicMax(reinterpret_cast<unsigned long long*>(&sh.kmax), (unsigned long long)vmax);
+            } else {
+                atomicMin(reinterpret_cast<unsigned int*>(&sh.kmin), (unsigned int)vmin);
+                atomicMax(reinterpret_cast<unsigned int*>(&sh.kmax), (unsigned int)vmax);
+            }
+        }
+        __syncthreads();
+        nv -= sh.acc[0];
+        tile_min = sh.kmin; tile_max = sh.kmax;
+        if (sh.acc[1] != 0) { give_up(1); return; }
+    }
+    if (nv < 64) { give_up(1); return; }
 
-    // ---- warp 0 sorts the sample
-    if (warp == 0) {
-        K v[16];
+    // ---- sort the 512-sample: every warp sorts its 32 samples with shuffles, then every thread
+    //      finds the global rank of its sample by binary searches in the other 15 sorted runs
+    //      (ties broken by run index, so the ranks are a permutation) and scatters it.
+    {
+        K x = keys[((size_t)(e_s >> 2) * NT + tid) * 4 + (e_s & 3)];  // own store: no barrier needed
 #pragma unroll
-        for (int r = 0; r < 16; ++r) v[r] = samp[r * 32 + lane];
-        warp_sort512<K>(v, lane);
-        uint32_t sv = 0;
+        for (int k = 2; k <= 32; k <<= 1) {
 #pragma unroll
-        for (int r = 0; r < 16; ++r) { samp[r * 32 + lane] = v[r]; sv += (v[r] != kExcl) ? 1u : 0u; }
-        sv = __reduce_add_sync(0xffffffffu, sv);
-        if (lane == 0) sh.acc[2] = sv;
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                const K o = shfl_xor_key<K>(x, j);
+                const bool keep_min = (((lane & j) == 0) == ((lane & k) == 0));
+                const K mn = x < o ? x : o, mx = x < o ? o : x;
+                x = keep_min ? mn : mx;
+            }
+        }
+        K* runs = cand;  // [16][32], free until the first compaction
+        runs[tid] = x;
+        const int nvalid_s = __syncthreads_count(x != kExcl);
+        uint32_t rank = lane;
+        auto count_in_run = [&](const K* run, auto incl_tag) {
+            constexpr bool incl = decltype(incl_tag)::value;  // earlier runs win ties
+            uint32_t pos = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const K y = run[pos + step - 1];
+                pos += (incl ? (y <= x) : (y < x)) ? step : 0;
+            }
+            const K y = run[31];
+            pos += (pos == 31 && (incl ? (y <= x) : (y < x))) ? 1u : 0u;
+            return pos;
+        };
+#pragma unroll 3
+        for (int r = 0; r < warp; ++r) rank += count_in_run(runs + r * 32, std::true_type{});
+#pragma unroll 3
+        for (int r = warp + 1; r < NT / 32; ++r) rank += count_in_run(runs + r * 32, std::false_type{});
+        samp[rank] = x;
+        if (tid == 0) sh.acc[2] = (uint32_t)nvalid_s;
     }
     __syncthreads();
     const int sv = (int)sh.acc[2];  // valid samples (sorted first)
@@ -395,35 +470,8 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
     const PlanDev pp = [&]() { PlanDev q = p; if (!real_branch) { q.norm_before = q.norm_after = 0; q.stretch = RFI_STRETCH_NONE; } return q; }();
     // the extreme samples must stay finite through the chain (else: inf fill -> general kernel)
     {
-        // min / max raw key over the tile -> finite after the stretch?
-        K lo = kExcl, hi = 0;
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const K x = keys[((size_t)g * NT + tid) * 4 + i];
-                lo = x < lo ? x : lo;
-                const K y = x == kExcl ? K(0) : x;
-                hi = y > hi ? y : hi;
-            }
-        }
-        lo = warp_min(lo);
-        hi = warp_max(hi);
-        if (tid == 0) { sh.kmin = kExcl; sh.kmax = 0; }
-        __syncthreads();
-        if (lane == 0) {
-            if (sizeof(K) == 8) {
-                atomicMin(reinterpret_cast<unsigned long long*>(&sh.kmin), (unsigned long long)lo);
-                atomicMax(reinterpret_cast<unsigned long long*>(&sh.kmax), (unsigned long long)hi);
-            } else {
-                atomicMin(reinterpret_cast<unsigned int*>(&sh.kmin), (unsigned int)lo);
-                atomicMax(reinterpret_cast<unsigned int*>(&sh.kmax), (unsigned int)hi);
-            }
-        }
-        __syncthreads();
-        const T pmin = proc_nofill<T>(raw_val<T>(sh.kmin), pp, m, m2);
-        const T pmax = proc_nofill<T>(raw_val<T>(sh.kmax), pp, m, m2);
-        __syncthreads();
+        const T pmin = proc_nofill<T>(raw_val<T>(tile_min), pp, m, m2);
+        const T pmax = proc_nofill<T>(raw_val<T>(tile_max), pp, m, m2);
         if (is_inf(pmin) || is_inf(pmax) || is_nan(pmin) || is_nan(pmax)) { give_up(5); return; }
     }
 
@@ -548,57 +596,57 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
         thr_hi = c + ds;
         thr_lo = c - ds;
 
-        // ---- exact raw-domain thresholds: 32-ary search evaluating the chain itself (warp 0)
-        if (warp == 0) {
+        // ---- exact raw-domain thresholds.  Warp 0: raw_hi = max{a : proc(a) <= thr_hi}; warp 1:
+        //      raw_lo = min{a : proc(a) >= thr_lo}.  The chain is inverted approximately, the 32
+        //      keys around the guess are evaluated with the chain itself (one ballot); if the
+        //      transition is not among them, a 32-ary search over the whole key range finds it.
+        if (warp < 2) {
             constexpr K kTop = kInfKey;  // first key that is not a finite value
-            // raw_hi = max{a finite : proc(a) <= thr_hi}
-            K res_hi, res_lo;
-            {
-                auto ok = [&](K k) { return proc_nofill<T>(raw_val<T>(k), pp, m, m2) <= thr_hi; };
-                if (!(thr_hi == thr_hi)) res_hi = kTop;            // NaN threshold: nothing above it
-                else if (!ok(K(0))) res_hi = kExcl;                // everything is above (marker)
-                else {
-                    K a = 0, b = kTop;                              // ok(a), !ok(b) (b == kTop: sentinel)
-                    if (ok(kTop - 1)) a = kTop - 1;
-                    while (b - a > 1 && a != kTop - 1) {
-                        const K step = (b - a + 32) / 33;
-                        K t = a + (K)(lane + 1) * step;
-                        const bool inr = t < b;
-                        const bool good = inr && ok(t);
-                        const uint32_t bal = __ballot_sync(0xffffffffu, good);
-                        const int n = __popc(bal);                  // monotone: a prefix of the lanes
-                        const K na = a + (K)n * step;
-                        const K nb = a + (K)(n + 1) * step;
-                        a = na;
-                        b = nb < b ? nb : b;
+            const bool want_hi = (warp == 0);
+            const T thr = want_hi ? thr_hi : thr_lo;
+            // predicate that is true on a PREFIX of the keys: hi: proc <= thr ; lo: proc < thr
+            auto pre = [&](K k) {
+                const T v = proc_nofill<T>(raw_val<T>(k), pp, m, m2);
+                return want_hi ? (v <= thr) : !(v >= thr);
+            };
+            K first_false;  // smallest key where the predicate fails (kTop if none below kTop)
+            if (!(thr == thr)) first_false = want_hi ? kTop : K(0);  // NaN: nothing above / below
+            else if (!pre(K(0))) first_false = 0;
+            else if (pre(kTop - 1)) first_false = kTop;
+            else {
+                K a = 0, b = kTop - 1;  // pre(a), !pre(b)
+                // approximate inverse of the chain
+                T g = thr;
+                if (pp.norm_after && m2 > T(0)) g = g * m2;
+                if (pp.stretch == RFI_STRETCH_SQRT) g = g * g;
+                else if (pp.stretch == RFI_STRETCH_LOG10) g = (T)exp10((double)g);
+                if (pp.norm_before && m > T(0)) g = g * m;
+                K gk = (g == g && g > T(0)) ? Scalar<T>::bits(g) : K(16);
+                gk = gk < K(16) ? K(16) : (gk > kTop - 17 ? kTop - 17 : gk);
+                {
+                    const K t = gk - 16 + (K)lane;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, pre(t));
+                    if ((bal & 1u) && !(bal >> 31)) {  // transition inside the window
+                        const int n = __popc(bal);
+                        a = gk - 16 + (K)(n - 1);
+                        b = a + 1;
                     }
-                    res_hi = a;
                 }
-            }
-            // raw_lo = min{a finite : proc(a) >= thr_lo}
-            {
-                auto ok = [&](K k) { return proc_nofill<T>(raw_val<T>(k), pp, m, m2) >= thr_lo; };
-                if (!(thr_lo == thr_lo)) res_lo = 0;               // NaN threshold: nothing below it
-                else if (ok(K(0))) res_lo = 0;
-                else if (!ok(kTop - 1)) res_lo = kTop;              // every finite sample is below
-                else {
-                    K a = 0, b = kTop - 1;                          // !ok(a), ok(b)
-                    while (b - a > 1) {
-                        const K step = (b - a + 32) / 33;
-                        K t = a + (K)(lane + 1) * step;
-                        const bool inr = t < b;
-                        const bool bad = inr && !ok(t);
-                        const uint32_t bal = __ballot_sync(0xffffffffu, bad);
-                        const int n = __popc(bal);                  // lanes still below the threshold
-                        const K na = a + (K)n * step;
-                        const K nb = a + (K)(n + 1) * step;
-                        a = na;
-                        b = nb < b ? nb : b;
-                    }
-                    res_lo = b;
+                while (b - a > 1) {
+                    const K step = (b - a + 32) / 33;
+                    const K t = a + (K)(lane + 1) * step;
+                    const bool good = (t < b) && pre(t);
+                    const int n = __popc(__ballot_sync(0xffffffffu, good));  // monotone: a prefix of the lanes
+                    const K na = a + (K)n * step, nb = a + (K)(n + 1) * step;
+                    a = na;
+                    b = nb < b ? nb : b;
                 }
+                first_false = b;
             }
-            if (lane == 0) { sh.res1 = res_lo; sh.res2 = res_hi; }
+            if (lane == 0) {
+                if (want_hi) sh.res2 = (first_false == 0) ? kExcl : first_false - 1;  // kExcl: everything is above
+                else sh.res1 = first_false;
+            }
         }
         __syncthreads();
         const K klo = sh.res1, khi = sh.res2;

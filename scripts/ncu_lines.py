@@ -47,7 +47,9 @@ for r in rows:
     n = int(r[iE]); by[k] += n; tot += n; s = int(r[iSm]); bys[k] += s; stot += s
 print(f"{blk['name'][:90]}\n total warp instr {tot}, samples {stot}, mapped lines {len(addr2line)}")
 srcs = {}
-for (f, l), n in by.most_common(top):
+order = sorted(by, key=lambda k: -bys[k]) if os.environ.get("BY_SAMPLES") else [k for k, _ in by.most_common()]
+for (f, l) in order[:top]:
+    n = by[(f, l)]
     text = ""
     for d in ("rfi_toolbox_b200/csrc", "include"):
         pth = os.path.join(d, f or "")

@@ -72,3 +72,13 @@ def test_statistics_and_ffi(native_lib, dtype):
     assert compute_ffi(data, np.ones_like(mask)) == oracle.compute_ffi(data, np.ones_like(mask))
     with pytest.raises(IndexError):
         compute_ffi(data, mask.astype(np.uint8))
+
+
+def test_sqrt_unit_range_is_exact(native_lib):
+    """cabs_fast's square root (no range test, argument in [1, 2]) equals sqrt.rn.f32 on every
+    one of the 2^23 + 1 possible arguments."""
+    import torch
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    rc = native_lib.rfi_selftest_sqrt_unit(bad.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    assert int(bad.item()) == 0
