@@ -251,6 +251,42 @@ RFI_DEVINL void block_nanminmax(T& lo, T& hi, BlockScratch<NT>& s, int& parity) 
     parity ^= 1;
 }
 
+// Four NaN-ignoring (min, max) pairs per thread at once; results to every thread.  `buf` is
+// NT / 32 * 8 values of shared scratch.  Warp shuffles, one store per warp, ONE barrier pair,
+// then a 16-lane shuffle tree over the per-warp partials.
+template <int NT, typename T>
+RFI_DEVINL void block_nanminmax4(T (&lo)[4], T (&hi)[4], T* buf) {
+    constexpr int W = NT / 32;
+    static_assert(W <= 32, "one partial per lane");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            lo[k] = Scalar<T>::fmin_nan(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = Scalar<T>::fmax_nan(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+    }
+    __syncthreads();  // buf may alias a buffer other warps still read
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { buf[warp * 8 + k] = lo[k]; buf[warp * 8 + 4 + k] = hi[k]; }
+    }
+    __syncthreads();
+    const int src = lane < W ? lane : 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { lo[k] = buf[src * 8 + k]; hi[k] = buf[src * 8 + 4 + k]; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            lo[k] = Scalar<T>::fmin_nan(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = Scalar<T>::fmax_nan(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+    }
+    __syncthreads();  // before buf is reused
+}
+
 // ----------------------------------------------------------------------------------------
 // Round counters: block-wide sum of one u32 per thread with ONE barrier and ~6 instructions
 // per thread: warp REDUX, one shared atomic per warp into a rotating counter, barrier, one

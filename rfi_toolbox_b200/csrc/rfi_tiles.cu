@@ -325,9 +325,20 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
     // ---- pass A: processed sample -> log amplitude tile, label tiles, min/max of L.
     // One row per warp per step; the next step's samples are prefetched into registers while
     // the current ones go through magnitude / normalise / stretch / log10 (the loop is NOT
-    // unrolled over steps: the body is ~400 instructions and must stay inside the I-cache).
+    // unrolled over steps: the body is long and must stay inside the I-cache).
+    //
+    // Fast route (float32, tile measured by the monotone kernel, stretch None / SQRT): the label
+    // is two compares of the exact magnitude with the raw-domain thresholds of phase 1 -- no
+    // division, no square root -- and the log amplitude, which only feeds the tolerance-class
+    // image channels, comes from reciprocal-multiply, sqrt.approx and lg2.approx (|dL| < 2e-7).
     T llo = Scalar<T>::nan(), lhi = Scalar<T>::nan();
-    {
+    const bool fast_route = std::is_same<T, float>::value && !kComplexBranch &&
+                            (st.route & RFI_TILE_RAW_THRESHOLDS) != 0 && p.stretch != RFI_STRETCH_LOG10;
+    auto pass_a = [&](auto fast_tag) {
+        constexpr bool kFast = decltype(fast_tag)::value;
+        [[maybe_unused]] const float raw_lo = (float)st.raw_lo, raw_hi = (float)st.raw_hi;
+        [[maybe_unused]] const float rm = (p.norm_before && med_before > T(0)) ? 1.0f / (float)med_before : 1.0f;
+        [[maybe_unused]] const float rm2 = (p.norm_after && med_after > T(0)) ? 1.0f / (float)med_after : 1.0f;
         RawSample<DT> cur[Q], nxt[Q];
 #pragma unroll
         for (int q = 0; q < Q; ++q)
@@ -350,12 +361,23 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
             for (int q = 0; q < Q; ++q) {
                 const int col = lane + 32 * q;
                 T a, ph;
-                raw_to_mag<DT, kComplexBranch>(cur[q], a, ph);
-                T x = a;
-                if (real_branch) x = process_sample<T>(a, p, med_before, inf_fill, med_after);
                 unsigned char f = fl[q];
-                if (p.flag_mode == RFI_FLAGS_MAD) f = ((x > thr_hi) || (x < thr_lo)) ? 1 : 0;
-                T L = log10_img(fabs_(x) + T(1e-10));
+                T L;
+                if constexpr (kFast) {
+                    raw_to_mag_fast<DT>(cur[q], a);
+                    ph = T(0);
+                    if (p.flag_mode == RFI_FLAGS_MAD) f = ((a > (T)raw_hi) || (a < (T)raw_lo)) ? 1 : 0;
+                    float y = (float)a * rm;
+                    if (p.stretch == RFI_STRETCH_SQRT) y = sqrt_fast(y);
+                    y = y * rm2;
+                    L = (T)(lg2_fast(y + 1e-10f) * 0.30102999566f);
+                } else {
+                    raw_to_mag<DT, kComplexBranch>(cur[q], a, ph);
+                    T x = a;
+                    if (real_branch) x = process_sample<T>(a, p, med_before, inf_fill, med_after);
+                    if (p.flag_mode == RFI_FLAGS_MAD) f = ((x > thr_hi) || (x < thr_lo)) ? 1 : 0;
+                    L = log10_img(fabs_(x) + T(1e-10));
+                }
                 Ls[row * LP + col] = L;
                 FbT[col * FP + row] = f;
                 // label rows of the untransposed rotations go out now: 32 lanes x 1 byte = one full sector
@@ -373,7 +395,9 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
 #pragma unroll
             for (int q = 0; q < Q; ++q) cur[q] = nxt[q];
         }
-    }
+    };
+    if (fast_route) pass_a(std::true_type{});
+    else pass_a(std::false_type{});
     __syncthreads();
 
     // ---- pass B: min/max of the squared gradient for each distinct rotation variant
@@ -390,24 +414,26 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
             const T bi = (i > 0) ? c - Ls[(i - 1) * LP + j] : T(0);
             const T bj = (j > 0) ? c - Ls[i * LP + j - 1] : T(0);
             const T bi2 = bi * bi, bj2 = bj * bj;
-            const T ss0 = bi2 + bj2;
+            const T ss0 = Scalar<T>::fma(bi, bi, bj2);
             s0lo = Scalar<T>::fmin_nan(s0lo, ss0); s0hi = Scalar<T>::fmax_nan(s0hi, ss0);
             if (R >= 2) {
                 const T fi = (i < kP - 1) ? c - Ls[(i + 1) * LP + j] : T(0);
-                const T ss1 = fi * fi + bj2;
+                const T ss1 = Scalar<T>::fma(fi, fi, bj2);
                 s1lo = Scalar<T>::fmin_nan(s1lo, ss1); s1hi = Scalar<T>::fmax_nan(s1hi, ss1);
             }
             if (R >= 4) {
                 const T fj = (j < kP - 1) ? c - Ls[i * LP + j + 1] : T(0);
-                const T ss3 = fj * fj + bi2;
+                const T ss3 = Scalar<T>::fma(fj, fj, bi2);
                 s3lo = Scalar<T>::fmin_nan(s3lo, ss3); s3hi = Scalar<T>::fmax_nan(s3hi, ss3);
             }
         }
     }
-    block_nanminmax<NT, T>(s0lo, s0hi, scr, parity);
-    if (R >= 2) block_nanminmax<NT, T>(s1lo, s1hi, scr, parity);
-    if (R >= 4) block_nanminmax<NT, T>(s3lo, s3hi, scr, parity);
-    if constexpr (!kComplexBranch) block_nanminmax<NT, T>(llo, lhi, scr, parity);
+    {   // all four NaN-ignoring min / max pairs in one block reduction
+        T lo4[4] = {s0lo, s1lo, s3lo, llo}, hi4[4] = {s0hi, s1hi, s3hi, lhi};
+        block_nanminmax4<NT, T>(lo4, hi4, reinterpret_cast<T*>(stage));
+        s0lo = lo4[0]; s1lo = lo4[1]; s3lo = lo4[2]; llo = lo4[3];
+        s0hi = hi4[0]; s1hi = hi4[1]; s3hi = hi4[2]; lhi = hi4[3];
+    }
 
     // sqrt is monotone: min/max of g = sqrt(min/max of g^2)
     const ChanScale<T> g0 = make_scale<T>(sqrt_fast(s0lo), sqrt_fast(s0hi));
@@ -433,6 +459,9 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
         constexpr int base_at = (rot == 0) ? 0 : (rot == 1) ? (kP - 1) * LP : (rot == 2) ? 0 : (kP - 1);
         constexpr int db = -scol;
         const int row0 = warp * STEPS;
+        // u = (v - lo) * inv, out = u / std - mean / std  ==  v * (inv / std) + (-lo * inv / std - mean / std)
+        const T ga = gs.inv * (T)is0, gb = Scalar<T>::fma(-gs.lo * gs.inv, (T)is0, (T)nb0);
+        [[maybe_unused]] const T la = ls.inv * (T)is1, lb = Scalar<T>::fma(-ls.lo * ls.inv, (T)is1, (T)nb1);
         T prev[Q];
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
@@ -450,8 +479,8 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
                 const T td = (orow > 0) ? c - prev[q] : T(0);
                 const T fd = (ocol > 0) ? c - Ls[at + db] : T(0);
                 prev[q] = c;
-                const T g = sqrt_fast(td * td + fd * fd);
-                const float u0 = (float)((g - gs.lo) * gs.inv);
+                const T g = sqrt_fast(Scalar<T>::fma(td, td, fd * fd));
+                const float o0 = (float)Scalar<T>::fma(g, ga, gb);  // ((g - lo) * inv) * (1/std) - mean/std, folded
                 float o1, o2;
                 if constexpr (kComplexBranch) {
                     T u = (c - T(-3.0)) * T(1.0 / 7.0);
@@ -459,11 +488,10 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
                     o1 = __fmaf_rn((float)u, is1, nb1);
                     o2 = Ph[at];
                 } else {
-                    const float u1 = (float)((c - ls.lo) * ls.inv);
-                    o1 = __fmaf_rn(u1, is1, nb1);
+                    o1 = (float)Scalar<T>::fma(c, la, lb);
                     o2 = nb2;
                 }
-                wstage[ocol * 3 + 0] = __fmaf_rn(u0, is0, nb0);
+                wstage[ocol * 3 + 0] = o0;
                 wstage[ocol * 3 + 1] = o1;
                 wstage[ocol * 3 + 2] = o2;
             }
