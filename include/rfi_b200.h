@@ -180,6 +180,19 @@ int rfi_statistics(const void* data, int dtype, const uint8_t* flags, int64_t n,
  * after the call is what the reference leaves behind. */
 int rfi_legacy_permutation(uint32_t* mt_key, int32_t* mt_pos, int64_t n, int64_t* out);
 
+/* Host helper (no CUDA): blank-patch removal, shuffle and truncation (preprocessor.py:746-763,
+ * :356-359) between the two phases.
+ *   n_flagged    host, per statistic group (rfi_plan_num_tiles() entries), `stride_bytes` apart
+ *                (pass the n_flagged field of the copied-back rfi_tile_stat_t array, stride 88)
+ *   shuffle      0 = inference mode: canonical order, nothing dropped, RNG untouched
+ *   mt_key/pos   as for rfi_legacy_permutation (advanced in place)
+ *   num_patches  <= 0: keep all
+ *   order        host int64[rfi_plan_num_patches()]: canonical index of output patch k, k < *n_out
+ *   dest         host int64[rfi_plan_num_patches()]: output slot of canonical patch q, -1 = dropped */
+int rfi_plan_slots(const rfi_plan_t* plan, const int32_t* n_flagged, int64_t stride_bytes, int shuffle,
+                   uint32_t* mt_key, int32_t* mt_pos, int64_t num_patches, int64_t* order,
+                   int64_t* dest, int64_t* n_out);
+
 /* Self test (used by tests/): counts the inputs t in [1, 2] (all 2^23 + 1 float32 values) for
  * which the range-restricted square root of the magnitude kernel differs from sqrt.rn.f32.
  *   mismatches_dev  device uint64, ACCUMULATED into (caller zeroes); must end up 0 */

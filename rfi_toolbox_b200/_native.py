@@ -60,6 +60,8 @@ SYMBOLS = {
     "rfi_statistics_workspace_bytes": (C.c_size_t, []),
     "rfi_statistics": (_I, [_VP, _I, _VP, _I64, _VP, _VP, _VP]),
     "rfi_legacy_permutation": (_I, [_VP, C.POINTER(C.c_int32), _I64, _VP]),
+    "rfi_plan_slots": (_I, [C.POINTER(RfiPlan), _VP, _I64, _I, _VP, C.POINTER(C.c_int32), _I64, _VP, _VP,
+                            C.POINTER(C.c_int64)]),
     "rfi_selftest_sqrt_unit": (_I, [_VP, _VP]),
     "rfi_last_error_string": (C.c_char_p, []),
     "rfi_abi_version": (_I, []),
@@ -93,14 +95,40 @@ def load():
     return lib
 
 
+def _global_mt19937():
+    """(key pointer, pos pointer) INTO the global legacy generator's MT19937 state -- the
+    native helpers then advance the very stream `np.random.permutation` would -- or None when
+    the global generator is not MT19937 / does not expose its state (the callers then go
+    through get_state / set_state)."""
+    import numpy as np
+    try:
+        bg = np.random.mtrand._rand._bit_generator
+        if type(bg).__name__ != "MT19937":
+            return None
+        addr = int(bg.ctypes.state_address)  # struct { uint32_t key[624]; int pos; }
+        return bg, addr, addr + 624 * 4
+    except Exception:
+        return None
+
+
 def legacy_permutation(n: int):
     """`np.random.permutation(n)` of the GLOBAL legacy generator (same values, same stream
     position afterwards), computed by the native helper.  Falls back to NumPy itself when the
     global generator is not MT19937."""
     import numpy as np
 
+    if n < 2:
+        return np.random.permutation(n)
+    direct = _global_mt19937()
+    if direct is not None:
+        bg, kaddr, paddr = direct
+        out = np.empty(n, dtype=np.int64)
+        with bg.lock:
+            rc = load().rfi_legacy_permutation(kaddr, C.cast(paddr, C.POINTER(C.c_int32)), n, out.ctypes.data)
+        check(rc, "rfi_legacy_permutation")
+        return out
     state = np.random.get_state()
-    if state[0] != "MT19937" or n < 2:
+    if state[0] != "MT19937":
         return np.random.permutation(n)
     key = np.array(state[1], dtype=np.uint32, copy=True)
     pos = C.c_int32(int(state[2]))
@@ -109,6 +137,39 @@ def legacy_permutation(n: int):
     check(rc, "rfi_legacy_permutation")
     np.random.set_state(("MT19937", key, int(pos.value), state[3], state[4]))
     return out
+
+
+def plan_slots(plan, n_flagged, shuffle, num_patches, order, dest):
+    """`rfi_plan_slots` on NumPy buffers, drawing from / advancing the GLOBAL legacy generator
+    exactly like `np.random.permutation(n_kept)`.  `n_flagged` int32 [groups] (any stride) or
+    None; `order`, `dest` int64 [n_patches] outputs.  Returns n_out."""
+    import numpy as np
+
+    lib = load()
+    n_out = C.c_int64(0)
+    fptr, stride = (None, 0) if n_flagged is None else (n_flagged.ctypes.data, n_flagged.strides[0])
+    direct = _global_mt19937() if shuffle else None
+    if direct is not None:
+        bg, kaddr, paddr = direct
+        with bg.lock:
+            rc = lib.rfi_plan_slots(C.byref(plan), fptr, stride, 1, kaddr, C.cast(paddr, C.POINTER(C.c_int32)),
+                                    int(num_patches) if num_patches else 0, order.ctypes.data, dest.ctypes.data,
+                                    C.byref(n_out))
+        check(rc, "rfi_plan_slots")
+        return int(n_out.value)
+    state = np.random.get_state() if shuffle else None
+    if shuffle and state[0] != "MT19937":
+        raise NativeError("the global NumPy generator is not MT19937; cannot reproduce the reference shuffle")
+    key = np.array(state[1], dtype=np.uint32, copy=True) if shuffle else None
+    pos = C.c_int32(int(state[2]) if shuffle else 0)
+    rc = lib.rfi_plan_slots(C.byref(plan), fptr, stride, int(bool(shuffle)),
+                            key.ctypes.data if shuffle else None, C.byref(pos),
+                            int(num_patches) if num_patches else 0, order.ctypes.data, dest.ctypes.data,
+                            C.byref(n_out))
+    check(rc, "rfi_plan_slots")
+    if shuffle:
+        np.random.set_state(("MT19937", key, int(pos.value), state[3], state[4]))
+    return int(n_out.value)
 
 
 def check(rc: int, what: str):

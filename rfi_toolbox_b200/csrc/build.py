@@ -16,7 +16,7 @@ HERE = Path(__file__).resolve().parent
 PKG = HERE.parent
 LIB = PKG / "_lib" / "librfi_b200.so"
 OBJ = HERE / "build"
-SOURCES = ["rfi_error.cu", "rfi_tiles.cu", "rfi_generic.cu", "rfi_metrics.cu", "rfi_stats.cu", "rfi_host.cu"]
+SOURCES = ["rfi_error.cu", "rfi_tiles.cu", "rfi_generic.cu", "rfi_metrics.cu", "rfi_stats.cu", "rfi_host.cpp"]
 HEADERS = sorted(HERE.glob("*.cuh")) + [PKG.parent / "include" / "rfi_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -51,12 +51,15 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     def compile_one(src: Path) -> Path:
         obj = OBJ / (src.stem + ".o")
         if force or _stale(obj, [src] + HEADERS + [Path(__file__)]):
-            cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
-            if verbose:
-                cmd.insert(1, "-Xptxas=-v")
+            if src.suffix == ".cpp":  # host-only helper: plain g++ (vectorises what nvcc's host pass does not)
+                cmd = [os.environ.get("CXX", "g++"), "-O3", "-std=c++17", "-fPIC", "-c", str(src), "-o", str(obj)]
+            else:
+                cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+                if verbose:
+                    cmd.insert(1, "-Xptxas=-v")
             r = subprocess.run(cmd, capture_output=True, text=True)
             if r.returncode != 0:
-                raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stdout}\n{r.stderr}")
+                raise RuntimeError(f"compilation failed for {src.name}:\n{r.stdout}\n{r.stderr}")
             if verbose:
                 sys.stderr.write(r.stderr)
         return obj

@@ -88,6 +88,26 @@ def _keep_in_canonical_order(keep_tile, n_rot):
     return np.concatenate(parts, axis=1).reshape(-1)
 
 
+_HOST_BUFFERS = {}
+
+
+def _host_buffers(device, n_groups, n_patches):
+    """Pinned staging buffers (flag counts down, destination slots up), grown on demand and
+    reused across calls: pinning memory costs more than the whole host phase."""
+    key = (device.index,)
+    hb = _HOST_BUFFERS.get(key)
+    if hb is None or hb["nflag"].numel() < n_groups or hb["dest"].numel() < n_patches:
+        g = max(n_groups, 2 * hb["nflag"].numel() if hb else 0)
+        n = max(n_patches, 2 * hb["dest"].numel() if hb else 0)
+        hb = {"nflag": torch.empty(g, dtype=torch.int32, pin_memory=True),
+              "dest": torch.empty(n, dtype=torch.int64, pin_memory=True),
+              "order": torch.empty(n, dtype=torch.int64),
+              "event": torch.cuda.Event(), "copied": torch.cuda.Event()}
+        hb["nflag_np"], hb["dest_np"], hb["order_np"] = hb["nflag"].numpy(), hb["dest"].numpy(), hb["order"].numpy()
+        _HOST_BUFFERS[key] = hb
+    return hb
+
+
 class Preprocessor:
     """Preprocess waterfall data into training patches (preprocessor.py:139-196)."""
 
@@ -231,27 +251,23 @@ class Preprocessor:
             self.last_tile_stats = stats
 
             # ---- host: blank-patch compaction + shuffle -> destination slot of every patch
-            if inference_mode:
-                order = np.arange(n0, dtype=np.int64)  # :345-353 keeps the canonical order
-            else:
-                nflag = stats[:n_tiles].view(torch.int32)[:, 16].cpu().numpy()  # n_flagged column
-                if padded:
-                    keep = nflag > 0  # groups ARE the patches, already in canonical order
-                else:
-                    keep = _keep_in_canonical_order((nflag > 0).reshape(B * npol, nh, nw), R)
-                if keep.any():  # :752-756
-                    kept = np.flatnonzero(keep)
-                else:
-                    logger.warning("No flagged patches found - keeping all patches")
-                    kept = np.arange(n0, dtype=np.int64)
-                perm = _native.legacy_permutation(len(kept))  # :760, the one RNG draw (global legacy stream)
-                order = kept[perm]
-            if num_patches and num_patches < len(order):  # :356-359
-                order = order[:num_patches]
-            n_out = len(order)
-            dest = np.full(max(n0, 1), -1, dtype=np.int64)
-            dest[order] = np.arange(n_out, dtype=np.int64)
-            dest_dev = torch.from_numpy(dest).to(device, non_blocking=True)
+            #      (one native call on pinned buffers; draws the ONE np.random.permutation of
+            #      preprocessor.py:760 from the global legacy stream)
+            hb = _host_buffers(device, max(n_tiles, 1), max(n0, 1))
+            hb["copied"].synchronize()  # the previous call's upload has left the pinned buffer
+            nflag = None
+            if not inference_mode:
+                hb["nflag"][:n_tiles].copy_(stats[:n_tiles].view(torch.int32)[:, 16], non_blocking=True)
+                hb["event"].record()
+                hb["event"].synchronize()
+                nflag = hb["nflag_np"][:n_tiles]
+            n_out = _native.plan_slots(plan, nflag, not inference_mode, num_patches, hb["order_np"], hb["dest_np"])
+            if not inference_mode and nflag is not None and not (nflag > 0).any():
+                logger.warning("No flagged patches found - keeping all patches")
+            order = hb["order_np"][:n_out].copy()
+            dest_dev = torch.empty(max(n0, 1), dtype=torch.int64, device=device)
+            dest_dev.copy_(hb["dest"][:max(n0, 1)], non_blocking=True)
+            hb["copied"].record()
 
             # ---- phase 2: every kept patch written once, at its final position
             images = torch.empty((n_out, P if not skip_patchify else C_, P if not skip_patchify else T_, 3),

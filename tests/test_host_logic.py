@@ -122,3 +122,51 @@ def test_legacy_permutation_matches_numpy(native_lib):
             b = _native.legacy_permutation(n); rb = np.random.random(5); gb = np.random.standard_normal(3)
             assert a.dtype == b.dtype and np.array_equal(a, b), (seed, n)
             assert np.array_equal(ra, rb) and np.array_equal(ga, gb), (seed, n)
+
+
+@pytest.mark.parametrize("shape,patch,rot", [((256, 384), 128, 4), ((256, 384), 128, 2), ((256, 384), 128, 1),
+                                             ((200, 300), 128, 4), ((100, 60), 512, 1), ((256, 256), 512, 4),
+                                             ((250, 330), 100, 4), ((512, 256), 256, 2)])
+def test_plan_slots_matches_numpy_pipeline(native_lib, shape, patch, rot):
+    """rfi_plan_slots == keep mask in canonical order -> np.random.permutation -> dest (the
+    host phase of create_dataset written with NumPy), including the RNG stream position."""
+    import ctypes as C
+    import numpy as np
+    from rfi_toolbox_b200 import _native
+    from rfi_toolbox_b200.preprocessing.preprocessor import _keep_in_canonical_order
+    C_, T_ = shape
+    W = 3
+    plan = _native.RfiPlan(dtype=0, magnitude=0, n_waterfalls=W, channels=C_, times=T_, patch=patch,
+                           rotations=rot, stretch=1, norm_before=1, norm_after=0, flag_mode=1, sigma=5.0)
+    n_groups = int(native_lib.rfi_plan_num_tiles(C.byref(plan)))
+    n0 = int(native_lib.rfi_plan_num_patches(C.byref(plan)))
+    skip = C_ <= patch and T_ <= patch
+    padded = not skip and (C_ % patch or T_ % patch)
+    nh, nw = (1, 1) if skip else (-(-C_ // patch), -(-T_ // patch))
+    rng = np.random.default_rng(3)
+    for frac, num_patches in [(0.7, None), (0.0, None), (1.0, 5), (0.3, 10_000)]:
+        stats = np.zeros((n_groups, 22), dtype=np.int32)
+        stats[:, 16] = (rng.random(n_groups) < frac) * rng.integers(1, 9, n_groups)
+        nflag = stats[:, 16]
+        keep = (nflag > 0) if padded else _keep_in_canonical_order((nflag > 0).reshape(W, nh, nw), rot)
+        assert keep.size == n0
+        np.random.seed(11)
+        kept = np.flatnonzero(keep) if keep.any() else np.arange(n0)
+        want = kept[np.random.permutation(len(kept))]
+        if num_patches and num_patches < len(want):
+            want = want[:num_patches]
+        after = np.random.random(4)
+        order, dest = np.empty(n0, dtype=np.int64), np.empty(n0, dtype=np.int64)
+        np.random.seed(11)
+        n_out = _native.plan_slots(plan, nflag, True, num_patches, order, dest)
+        assert np.array_equal(np.random.random(4), after)
+        assert n_out == len(want) and np.array_equal(order[:n_out], want)
+        ref = np.full(n0, -1, dtype=np.int64)
+        ref[want] = np.arange(len(want))
+        assert np.array_equal(dest, ref)
+    # inference mode: canonical order, RNG untouched
+    np.random.seed(5)
+    a = np.random.get_state()[2]
+    n_out = _native.plan_slots(plan, None, False, None, order, dest)
+    assert n_out == n0 and np.array_equal(order, np.arange(n0)) and np.array_equal(dest, np.arange(n0))
+    assert np.random.get_state()[2] == a
