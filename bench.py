@@ -272,8 +272,14 @@ def run_ours(args):
     write_ms = float(np.mean(kern_ms["write"]))
     stats_ms = float(np.mean(kern_ms["stats"]))
     achieved = alg_bytes / (write_ms * 1e-3) / 1e9
+    # DRAM bytes of one launch from the committed `ncu --set full` capture of this very workload
+    # (profiles/traffic.json, written by scripts/ncu_summary.py); null for any other workload
+    traffic = None
+    tj = ROOT / "profiles" / "traffic.json"
+    if tj.exists() and not args.baselines:
+        traffic = json.loads(tj.read_text()).get("write_patches_kernel", {}).get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "kernel": "write_patches_kernel", "achieved": achieved, "peak": peak,
-                "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": write_ms,
                 "stats_kernel_ms": stats_ms, "stats_kernel_gbs": npix * cube.element_size() / (stats_ms * 1e-3) / 1e9,
                 "step_ms_device": dev_ms / args.steps}
@@ -291,7 +297,9 @@ def run_ours(args):
                    "parallelism": f"baseline-sharded x{world}, NCCL all-reduce of TP/FP/FN" if world > 1 else "single GPU"},
         "e2e": {"value": e2e_value, "unit": "Gpixel/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "note": "pinned host cube copied H2D every step; dataset stays in HBM, metric dict read back"},
-        "gpu_launches": 3 * args.steps,
+        # per step: tile_stats_mono_kernel, tile_stats_kernel (fallback tiles), write_patches_kernel,
+        # confusion_kernel
+        "gpu_launches": 4 * args.steps,
         "roofline": roofline,
         "cpu_baseline": {"value": cpu_v, "unit": "Gpixel/s", "cores": 1, "kind": "port",
                          "sample": f"2 baselines x 4 pols x 1024x1024 ({cpu_npix} px) in {cpu_dt:.1f} s, one process"},

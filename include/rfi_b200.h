@@ -171,6 +171,13 @@ size_t rfi_statistics_workspace_bytes(void);
 int rfi_statistics(const void* data, int dtype, const uint8_t* flags, int64_t n,
                    rfi_stats_t* out, void* workspace, void* stream);
 
+/* Per-pair sweep (BASELINE config 4): the same statistics for every consecutive segment of `seg`
+ * samples (seg <= 16384, e.g. one 128 x 128 patch) in one launch, one CTA per segment.
+ *   out  device rfi_stats_t[n_seg][2]: [i][0] over all samples of segment i (statistics.py:73),
+ *        [i][1] over its unflagged samples (:74), n_flagged filled in [i][1] */
+int rfi_statistics_segmented(const void* data, int dtype, const uint8_t* flags, int64_t n_seg,
+                             int64_t seg, rfi_stats_t* out, void* stream);
+
 /* Host helper (no CUDA): np.random.permutation(n) of NumPy's legacy MT19937 generator --
  * replaces the shuffle of preprocessor.py:758-763 at ~3 ns per element instead of ~30.
  *   mt_key  host uint32[624], the generator key  (np.random.get_state()[1]), advanced in place

@@ -15,10 +15,13 @@ from .evaluation import (  # noqa: F401,E402
     compute_dice,
     compute_f1,
     compute_ffi,
+    compute_ffi_batch,
     compute_iou,
     compute_precision,
     compute_recall,
     compute_statistics,
+    compute_statistics_batch,
     evaluate_segmentation,
+    evaluate_segmentation_batch,
 )
 from .preprocessing import Preprocessor  # noqa: F401,E402

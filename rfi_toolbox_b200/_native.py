@@ -59,6 +59,7 @@ SYMBOLS = {
     "rfi_confusion_counts_segmented": (_I, [_VP, _I, _I, _VP, _I, _I, _I64, _I64, _VP, _VP]),
     "rfi_statistics_workspace_bytes": (C.c_size_t, []),
     "rfi_statistics": (_I, [_VP, _I, _VP, _I64, _VP, _VP, _VP]),
+    "rfi_statistics_segmented": (_I, [_VP, _I, _VP, _I64, _I64, _VP, _VP]),
     "rfi_legacy_permutation": (_I, [_VP, C.POINTER(C.c_int32), _I64, _VP]),
     "rfi_plan_slots": (_I, [C.POINTER(RfiPlan), _VP, _I64, _I, _VP, C.POINTER(C.c_int32), _I64, _VP, _VP,
                             C.POINTER(C.c_int64)]),

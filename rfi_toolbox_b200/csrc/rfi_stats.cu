@@ -264,6 +264,116 @@ static int run_stats(const void* data, const uint8_t* flags, long long n, StatsW
     return RFI_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Per-pair sweep (BASELINE config 4): statistics of every consecutive segment of `seg` samples
+// (one 128 x 128 patch pair per CTA), before and after flagging, in ONE launch.  The segment
+// lives in registers as order-preserving keys (32 per thread); medians / MADs by the
+// register-resident radix select of rfi_common.cuh; moments accumulate in float64.
+constexpr int kSegNT = 512, kSegE = 32;  // <= 16384 samples per segment
+
+template <typename T, int NT>
+RFI_DEVINL void seg_moments(const T (&x)[kSegE], const bool (&use)[kSegE], double* red, rfi_stats_t& o,
+                            T& mean_t, uint32_t& n_use, uint32_t& n_nan) {
+    // red: shared scratch of 4 doubles (zeroed by the caller before a barrier)
+    double s = 0.0;
+    uint32_t n = 0, nn = 0;
+#pragma unroll
+    for (int e = 0; e < kSegE; ++e) {
+        if (use[e]) { s += (double)x[e]; n += 1; nn += is_nan(x[e]) ? 1u : 0u; }
+    }
+    s = warp_sum_d(s);
+    n = __reduce_add_sync(0xffffffffu, n);
+    nn = __reduce_add_sync(0xffffffffu, nn);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&red[0], s);
+        atomicAdd(&red[1], (double)n);
+        atomicAdd(&red[2], (double)nn);
+    }
+    __syncthreads();
+    const double sum = red[0];
+    n_use = (uint32_t)red[1];
+    n_nan = (uint32_t)red[2];
+    mean_t = n_use ? (T)(sum / (double)n_use) : T(0);
+    double q = 0.0;
+#pragma unroll
+    for (int e = 0; e < kSegE; ++e) {
+        if (use[e]) { const T d = x[e] - mean_t; q += (double)(d * d); }
+    }
+    q = warp_sum_d(q);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&red[3], q);
+    __syncthreads();
+    const double sumsq = red[3];
+    o.count = (long long)n_use;
+    o.n_nan = (long long)n_nan;
+    if (n_use == 0) {
+        o.mean = o.std = o.median = o.mad = __longlong_as_double(0x7ff8000000000000LL);
+    } else {
+        o.mean = (double)mean_t;
+        o.std = (double)Scalar<T>::sqrt_rn((T)(sumsq / (double)n_use));
+    }
+    __syncthreads();
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kSegNT, 1)
+stats_segmented_kernel(const void* __restrict__ data, const uint8_t* __restrict__ flags, long long seg,
+                       rfi_stats_t* __restrict__ out) {
+    using T = typename SIn<DT>::T;
+    using K = typename Scalar<T>::key_t;
+    constexpr int NT = kSegNT, E = kSegE;
+    constexpr K kExcl = ~K(0);
+    __shared__ BlockScratch<NT> scr;
+    __shared__ RoundCounter rc;
+    __shared__ SelectScratch<K> sel;
+    __shared__ double red[4];
+    int parity = 0, round = 0;
+    round_init(rc);
+    const long long base = (long long)blockIdx.x * seg;
+    T x[E];
+    bool in_seg[E], clean[E];
+    uint32_t nflag = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const long long i = (long long)e * NT + threadIdx.x;
+        in_seg[e] = i < seg;
+        x[e] = in_seg[e] ? load_mag<DT>(data, base + i) : T(0);
+        const bool fl = in_seg[e] && flags && __ldg(flags + base + i) != 0;
+        nflag += fl ? 1u : 0u;
+        clean[e] = in_seg[e] && !fl;
+    }
+    for (int which = 0; which < 2; ++which) {  // 0: all samples, 1: unflagged samples
+        const bool (&use)[E] = which == 0 ? in_seg : clean;
+        rfi_stats_t o;
+        o.n_flagged = 0;
+        if (threadIdx.x < 4) red[threadIdx.x] = 0.0;
+        __syncthreads();
+        T mean_t;
+        uint32_t n_use, n_nan;
+        seg_moments<T, NT>(x, use, red, o, mean_t, n_use, n_nan);
+        if (n_use > 0) {
+            if (n_nan > 0) {  // np.median propagates NaN
+                o.median = o.mad = __longlong_as_double(0x7ff8000000000000LL);
+            } else {
+                K key[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) key[e] = use[e] ? to_key<T>(x[e]) : kExcl;
+                const T med = block_median<T, NT, E>(key, n_use, scr, parity, rc, round, sel);
+#pragma unroll
+                for (int e = 0; e < E; ++e) key[e] = use[e] ? to_key<T>(fabs_(x[e] - med)) : kExcl;
+                const T mad = block_median<T, NT, E>(key, n_use, scr, parity, rc, round, sel);
+                o.median = (double)med;
+                o.mad = (double)mad;
+            }
+        }
+        if (which == 1) {
+            const uint32_t nf = round_sum(nflag, rc, round);
+            o.n_flagged = (long long)nf;
+        }
+        if (threadIdx.x == 0) out[(long long)blockIdx.x * 2 + which] = o;
+        __syncthreads();
+    }
+}
+
 }  // namespace rfi
 
 extern "C" size_t rfi_statistics_workspace_bytes(void) { return sizeof(rfi::StatsWork); }
@@ -285,5 +395,29 @@ extern "C" int rfi_statistics(const void* data, int dtype, const uint8_t* flags,
     }
     if (rc) return rc;
     RFI_CUDA_TRY(cudaMemcpyAsync(out, &w->out, sizeof(rfi_stats_t), cudaMemcpyDeviceToDevice, st));
+    return RFI_OK;
+}
+
+extern "C" int rfi_statistics_segmented(const void* data, int dtype, const uint8_t* flags, int64_t n_seg,
+                                        int64_t seg, rfi_stats_t* out, void* stream) {
+    using namespace rfi;
+    if (n_seg < 0 || seg <= 0 || (n_seg > 0 && (!data || !out))) { set_error("bad arguments to rfi_statistics_segmented"); return RFI_E_INVALID; }
+    if (seg > (int64_t)kSegNT * kSegE) {
+        set_error("segment of %lld samples: the per-pair kernel holds at most %d (use rfi_statistics per segment)",
+                  (long long)seg, kSegNT * kSegE);
+        return RFI_E_UNSUPPORTED;
+    }
+    if (n_seg == 0) return RFI_OK;
+    if (n_seg > 0x7fffffffLL) { set_error("too many segments for one launch"); return RFI_E_UNSUPPORTED; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)n_seg;
+    switch (dtype) {
+        case RFI_F32:  stats_segmented_kernel<RFI_F32><<<grid, kSegNT, 0, st>>>(data, flags, seg, out); break;
+        case RFI_F64:  stats_segmented_kernel<RFI_F64><<<grid, kSegNT, 0, st>>>(data, flags, seg, out); break;
+        case RFI_C64:  stats_segmented_kernel<RFI_C64><<<grid, kSegNT, 0, st>>>(data, flags, seg, out); break;
+        case RFI_C128: stats_segmented_kernel<RFI_C128><<<grid, kSegNT, 0, st>>>(data, flags, seg, out); break;
+        default: set_error("bad dtype %d", dtype); return RFI_E_INVALID;
+    }
+    RFI_CUDA_TRY(cudaGetLastError());
     return RFI_OK;
 }

@@ -100,3 +100,79 @@ def compute_ffi(data, flags):
     ffi = (0.5 * mad_reduction + 0.5 * std_reduction) * (1.0 - 0.5 * penalty)
     return {"ffi": float(ffi), "mad_reduction": float(mad_reduction),
             "std_reduction": float(std_reduction), "flagged_fraction": float(penalty)}
+
+
+# ---------------------------------------------------------------------------------------------
+# per-pair sweeps (extension; BASELINE config 4): one launch for a stack of patch pairs
+_STATS_DTYPE = np.dtype([("mean", "f8"), ("median", "f8"), ("std", "f8"), ("mad", "f8"),
+                         ("count", "i8"), ("n_flagged", "i8"), ("n_nan", "i8")])
+
+
+def _run_batch(data, flags):
+    lib = _native.load()
+    device = _device_of(data, flags)
+    require_cuda(device)
+    d = as_device_tensor(data, device)
+    if d.dtype not in _DTYPE_CODE:
+        raise TypeError(f"unsupported data dtype {d.dtype} (float32/64, complex64/128)")
+    if d.ndim < 2:
+        raise ValueError("batched statistics need a leading pair axis: data.shape = (N, ...)")
+    n_seg = d.shape[0]
+    seg = d.numel() // n_seg if n_seg else 0
+    f = None
+    if flags is not None:
+        f = _flags_tensor(flags, device)
+        if tuple(f.shape) != tuple(d.shape):
+            raise IndexError("flags and data must have the same shape")
+    if n_seg == 0:
+        return np.zeros((0, 2), dtype=_STATS_DTYPE), seg
+    with torch.cuda.device(device):
+        out = torch.empty((n_seg, 2, _STATS_DTYPE.itemsize), dtype=torch.uint8, device=device)
+        rc = lib.rfi_statistics_segmented(d.data_ptr(), _DTYPE_CODE[d.dtype], f.data_ptr() if f is not None else None,
+                                          n_seg, seg, out.data_ptr(), current_stream_ptr(device))
+        _native.check(rc, "rfi_statistics_segmented")
+        host = out.cpu().numpy()
+    return host.view(_STATS_DTYPE).reshape(n_seg, 2), seg
+
+
+def compute_statistics_batch(data, flags=None):
+    """`compute_statistics(data[i], flags[i])` for every i in one launch (one CTA per pair,
+    pairs of at most 16384 samples).  Returns a dict of NumPy arrays of length N."""
+    st, seg = _run_batch(data, flags)
+    col = st[:, 1 if flags is not None else 0]
+    count = col["count"].astype(np.int64)
+    empty = count == 0
+    with np.errstate(invalid="ignore", divide="ignore"):
+        frac = (col["n_flagged"] / float(seg)) if flags is not None else np.zeros(len(col))
+    out = {k: np.where(empty, np.nan, col[k]) for k in ("mean", "median", "std", "mad")}
+    out["count"] = count
+    out["flagged_fraction"] = np.where(empty, 1.0, frac)
+    return out
+
+
+def compute_ffi_batch(data, flags, errors="raise"):
+    """`compute_ffi(data[i], flags[i])` for every i (statistics.py:59-97) in one launch.
+
+    Returns {'ffi','mad_reduction','std_reduction','flagged_fraction'} as float64 arrays whose
+    entries equal the reference's per-pair results.  A pair with constant data (MAD or std of
+    0 before flagging) makes the reference raise ZeroDivisionError; so does this function,
+    naming the first such pair, unless `errors="nan"` (those entries become NaN)."""
+    st, seg = _run_batch(data, flags)
+    before, after = st[:, 0], st[:, 1]
+    n = len(st)
+    # statistics.py:77-78 -- all flagged (count 0) or NaN in the unflagged data
+    guard = (after["count"] == 0) | np.isnan(after["mad"]) | np.isnan(after["std"])
+    zero = ~guard & ((before["mad"] == 0) | (before["std"] == 0))
+    if zero.any() and errors == "raise":
+        raise ZeroDivisionError(f"float division by zero (pair {int(np.flatnonzero(zero)[0])}: constant data)")
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mad_red = 1.0 - (after["mad"] / before["mad"])
+        std_red = 1.0 - (after["std"] / before["std"])
+        penalty = after["n_flagged"] / float(seg) if seg else np.zeros(n)
+        ffi = (0.5 * mad_red + 0.5 * std_red) * (1.0 - 0.5 * penalty)
+    bad = zero
+    res = {"ffi": np.where(guard, 0.0, np.where(bad, np.nan, ffi)),
+           "mad_reduction": np.where(guard, 0.0, np.where(bad, np.nan, mad_red)),
+           "std_reduction": np.where(guard, 0.0, np.where(bad, np.nan, std_red)),
+           "flagged_fraction": np.where(guard, 1.0, penalty)}
+    return res

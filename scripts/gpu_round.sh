@@ -9,11 +9,11 @@ python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; e
 cat gpurun_out/${tag}_bench.json
 python scripts/hostprof.py > gpurun_out/${tag}_hostprof.log 2>&1
 if [ -z "$NO_NCU" ]; then
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
-    python bench.py --steps 2 --warmup 3 > gpurun_out/${tag}_ncu_list.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${tag}_launches.csv \
+    -k regex:"tile_stats|write_patches|confusion|flags_count" python bench.py --steps 2 --warmup 3 > gpurun_out/${tag}_ncu_list.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:write_patches -s 3 -c 1 -f -o gpurun_out/${tag}_write \
     python bench.py --steps 1 --warmup 3 > gpurun_out/${tag}_ncu_write.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:tile_stats -s 3 -c 1 -f -o gpurun_out/${tag}_stats \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:tile_stats_mono -s 3 -c 1 -f -o gpurun_out/${tag}_stats \
     python bench.py --steps 1 --warmup 3 > gpurun_out/${tag}_ncu_stats.log 2>&1
 fi
 ls -la gpurun_out | tail -12

@@ -33,6 +33,7 @@ def raw(rep):
 
 def main():
     dest, reps = sys.argv[1], sys.argv[2:]
+    traffic = {}
     lines = ["# ncu summaries (`ncu --set full --clock-control none`, one launch per kernel, cold-ish cache)", ""]
     for rep in reps:
         hdr, units, launches = raw(rep)
@@ -57,12 +58,20 @@ def main():
                 wr = float(d["dram__bytes_write.sum"]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[u["dram__bytes_write.sum"]]
                 t = float(d["gpu__time_duration.sum"]) * {"ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1}[u["gpu__time_duration.sum"]]
                 lines.append("")
+                kname = d.get("Kernel Name", "?").split("<")[0].replace("void ", "").strip()
+                traffic[kname] = {"dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
+                                  "duration_ms_under_ncu": t * 1e3, "report": rep.split("/")[-1]}
                 lines.append(f"DRAM traffic {rd + wr:.4g} B (read {rd:.4g}, write {wr:.4g}) in {t * 1e3:.3f} ms = "
                              f"{(rd + wr) / t / 1e9:.0f} GB/s under ncu")
             except Exception:
                 pass
             lines.append("")
     open(dest, "w").write("\n".join(lines) + "\n")
+    if traffic:
+        import json
+        import os
+        tj = os.path.join(os.path.dirname(dest), "traffic.json")
+        json.dump(traffic, open(tj, "w"), indent=1)
     print("\n".join(lines))
 
 

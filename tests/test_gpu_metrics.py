@@ -82,3 +82,63 @@ def test_sqrt_unit_range_is_exact(native_lib):
     rc = native_lib.rfi_selftest_sqrt_unit(bad.data_ptr(), torch.cuda.current_stream().cuda_stream)
     assert rc == 0
     assert int(bad.item()) == 0
+
+
+def _pairs(n, dtype, seed=0, shape=(128, 128)):
+    rng = np.random.default_rng(seed)
+    truth = rng.random((n,) + shape) < 0.10
+    data = (rng.normal(0, 1, (n,) + shape) + 1j * rng.normal(0, 1, (n,) + shape)) * np.where(truth, 100.0, 1.0)
+    if np.dtype(dtype).kind != "c":
+        data = np.abs(data)
+    pred = truth ^ (rng.random(truth.shape) < 0.02)
+    return data.astype(dtype), truth, pred
+
+
+@pytest.mark.parametrize("dtype", [np.complex64, np.float32, np.complex128, np.float64])
+def test_ffi_sweep_matches_per_pair_oracle(native_lib, dtype):
+    """BASELINE config 4 (scaled down): compute_ffi / compute_statistics over a stack of
+    128 x 128 pairs in one launch == the reference called pair by pair.  Medians and MADs are
+    exact order statistics (bit-exact); means / stds within 1e-6 relative."""
+    import oracle
+    from rfi_toolbox_b200 import compute_ffi_batch, compute_statistics_batch
+    n = 24
+    data, truth, pred = _pairs(n, dtype, seed=2)
+    pred[3] = True                      # all flagged -> the reference's guard branch
+    data[5, 7, 9] = np.nan              # NaN in the data
+    pred[5, 7, 9] = False               # ... left unflagged -> guard branch too
+    data[6, 1, 1] = np.nan
+    pred[6, 1, 1] = True                # NaN flagged away: only `before` is NaN
+    got = compute_ffi_batch(data, pred)
+    st_b = compute_statistics_batch(data)
+    st_a = compute_statistics_batch(data, pred)
+    for i in range(n):
+        want = oracle.compute_ffi(data[i], pred[i])
+        for k, v in want.items():
+            assert got[k][i] == pytest.approx(v, rel=1e-6, abs=1e-9, nan_ok=True), (i, k)
+        for st, fl in ((st_b, None), (st_a, pred[i])):
+            ws = oracle.compute_statistics(data[i], fl)
+            for k in ("median", "mad"):
+                a, b = st[k][i], ws[k]
+                assert (np.isnan(a) and np.isnan(b)) or np.dtype(dtype).type(0).real.dtype.type(a) == b, (i, k, a, b)
+            for k in ("mean", "std", "flagged_fraction"):
+                assert st[k][i] == pytest.approx(ws[k], rel=1e-6, nan_ok=True), (i, k)
+            assert int(st["count"][i]) == ws["count"]
+
+
+def test_ffi_sweep_ragged_segment_and_errors(native_lib):
+    import oracle
+    from rfi_toolbox_b200 import compute_ffi_batch
+    data, truth, pred = _pairs(5, np.complex64, seed=4, shape=(50, 37))   # segment not a multiple of 512
+    got = compute_ffi_batch(data, pred)
+    for i in range(5):
+        want = oracle.compute_ffi(data[i], pred[i])
+        for k, v in want.items():
+            assert got[k][i] == pytest.approx(v, rel=1e-6, abs=1e-9)
+    const = np.ones((2, 16, 16), dtype=np.float32)
+    with pytest.raises(ZeroDivisionError):
+        compute_ffi_batch(const, np.zeros_like(const, dtype=bool))
+    assert np.isnan(compute_ffi_batch(const, np.zeros_like(const, dtype=bool), errors="nan")["ffi"]).all()
+    with pytest.raises(IndexError):
+        compute_ffi_batch(const, np.zeros_like(const, dtype=np.uint8))
+    with pytest.raises(NotImplementedError):
+        compute_ffi_batch(np.ones((1, 256, 256), dtype=np.float32), np.zeros((1, 256, 256), dtype=bool))
