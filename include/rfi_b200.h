@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RFI_B200_ABI_VERSION 3
+#define RFI_B200_ABI_VERSION 4
 
 /* status codes */
 #define RFI_OK 0
@@ -160,6 +160,7 @@ typedef struct rfi_stats {
     int64_t count;     /* unflagged samples                               (statistics.py:54) */
     int64_t n_flagged; /* non-zero flag bytes                             (statistics.py:34) */
     int64_t n_nan;     /* NaNs among the unflagged samples; if > 0 median and mad are NaN */
+    double max;        /* np.max of the unflagged magnitudes (NaN if any is NaN)   (statistics.py:161) */
 } rfi_stats_t;
 
 size_t rfi_statistics_workspace_bytes(void);

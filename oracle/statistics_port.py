@@ -48,3 +48,41 @@ def compute_ffi(data, flags):
     ffi = (0.5 * mad_red + 0.5 * std_red) * (1.0 - 0.5 * pen)
     return {"ffi": float(ffi), "mad_reduction": float(mad_red),
             "std_reduction": float(std_red), "flagged_fraction": float(pen)}
+
+
+def compute_calcquality(data, flags, reference_data=None):
+    """statistics.py:100-193."""
+    data = np.asarray(data)
+    if np.iscomplexobj(data):
+        data = np.abs(data)
+    if reference_data is not None:
+        reference_data = np.asarray(reference_data)
+        if np.iscomplexobj(reference_data):
+            reference_data = np.abs(reference_data)
+        ref_stats = compute_statistics(reference_data, None)
+        ref_data = reference_data.ravel()
+    else:
+        ref_stats = compute_statistics(data, None)
+        ref_data = data.ravel()
+    flag_stats = compute_statistics(data, flags)
+    rmean, rstd = ref_stats["mean"], ref_stats["std"]
+    fmean, fstd = flag_stats["mean"], flag_stats["std"]
+    pflag = flag_stats["flagged_fraction"] * 100
+    if np.isnan(fmean) or np.isnan(fstd) or rstd < 1e-10:
+        return {"calcquality": np.inf, "sensitivity": np.inf, "mean_shift": np.inf, "std_shift": np.inf,
+                "overflagging_penalty": np.inf, "flagged_pct": float(pflag), "components": {}}
+    rmax = np.max(ref_data)
+    maxdev = (rmax - rmean) / rstd
+    fdiff = fmean - rmean
+    sdiff = fstd - rstd
+    a = abs(abs(maxdev) - 3)
+    b = abs(fdiff) / rstd - 1
+    c = abs(sdiff) / rstd
+    d = max(0, (pflag - 70) / 10)
+    calcquality = np.sqrt(a**2 + b**2 + c**2 + d**2)
+    return {
+        "calcquality": float(calcquality), "sensitivity": float(a), "mean_shift": float(b),
+        "std_shift": float(c), "overflagging_penalty": float(d), "flagged_pct": float(pflag),
+        "components": {"rmean": float(rmean), "rstd": float(rstd), "fmean": float(fmean), "fstd": float(fstd),
+                       "rmax": float(rmax), "maxdev": float(maxdev), "fdiff": float(fdiff), "sdiff": float(sdiff)},
+    }

@@ -15,7 +15,7 @@ RFI_F32, RFI_F64, RFI_C64, RFI_C128 = 0, 1, 2, 3
 RFI_STRETCH_NONE, RFI_STRETCH_SQRT, RFI_STRETCH_LOG10 = 0, 1, 2
 RFI_FLAGS_CUSTOM, RFI_FLAGS_MAD, RFI_FLAGS_INFERENCE = 0, 1, 2
 RFI_E_INVALID, RFI_E_UNSUPPORTED, RFI_E_CUDA = -1, -2, -3
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class RfiPlan(C.Structure):
@@ -40,7 +40,7 @@ class RfiTileStat(C.Structure):
 class RfiStats(C.Structure):
     _fields_ = [
         ("mean", C.c_double), ("median", C.c_double), ("std", C.c_double), ("mad", C.c_double),
-        ("count", C.c_int64), ("n_flagged", C.c_int64), ("n_nan", C.c_int64),
+        ("count", C.c_int64), ("n_flagged", C.c_int64), ("n_nan", C.c_int64), ("max", C.c_double),
     ]
 
 

@@ -20,6 +20,7 @@ struct StatsWork {
     // moments
     unsigned long long n_clean, n_flagged, n_nan;
     double sum, sumsq;
+    unsigned long long maxkey;  // ordered key (of the double-widened value) of the largest sample; NaN = all ones
     double mean_t;  // mean rounded to T
     // select state
     unsigned long long prefix, k1, k2, n_sel;
@@ -63,7 +64,7 @@ template <int DT>
 __global__ void __launch_bounds__(kStatThreads)
 moments1_kernel(const void* __restrict__ data, const uint8_t* __restrict__ flags, long long n, StatsWork* w) {
     using T = typename SIn<DT>::T;
-    unsigned long long nc = 0, nf = 0, nn = 0;
+    unsigned long long nc = 0, nf = 0, nn = 0, mk = 0;
     double s = 0.0;
     for (long long i = (long long)blockIdx.x * kStatThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kStatThreads) {
         const bool fl = flags ? (__ldg(flags + i) != 0) : false;
@@ -72,10 +73,14 @@ moments1_kernel(const void* __restrict__ data, const uint8_t* __restrict__ flags
             T x = load_mag<DT>(data, i);
             nc += 1; nn += is_nan(x) ? 1 : 0;
             s += (double)x;
+            const unsigned long long k = to_key<double>((double)x);
+            mk = k > mk ? k : mk;
         }
     }
     nc = warp_sum_u(nc); nf = warp_sum_u(nf); nn = warp_sum_u(nn); s = warp_sum_d(s);
+    mk = warp_max(mk);
     if ((threadIdx.x & 31) == 0) {
+        if (mk) atomicMax(&w->maxkey, mk);
         if (nc) atomicAdd(&w->n_clean, nc);
         if (nf) atomicAdd(&w->n_flagged, nf);
         if (nn) atomicAdd(&w->n_nan, nn);
@@ -219,9 +224,10 @@ __global__ void stats_finish_kernel(StatsWork* w) {
     o.n_flagged = (long long)w->n_flagged;
     o.n_nan = (long long)w->n_nan;
     if (w->n_clean == 0) {
-        o.mean = o.std = o.median = o.mad = __longlong_as_double(0x7ff8000000000000LL);
+        o.mean = o.std = o.median = o.mad = o.max = __longlong_as_double(0x7ff8000000000000LL);
         return;
     }
+    o.max = from_key<double>(w->maxkey);
     o.mean = w->mean_t;
     const T var = (T)(w->sumsq / (double)w->n_clean);
     o.std = (double)Scalar<T>::sqrt_rn(var);
@@ -274,13 +280,20 @@ constexpr int kSegNT = 512, kSegE = 32;  // <= 16384 samples per segment
 template <typename T, int NT>
 RFI_DEVINL void seg_moments(const T (&x)[kSegE], const bool (&use)[kSegE], double* red, rfi_stats_t& o,
                             T& mean_t, uint32_t& n_use, uint32_t& n_nan) {
-    // red: shared scratch of 4 doubles (zeroed by the caller before a barrier)
+    // red: shared scratch of 5 doubles (zeroed by the caller before a barrier)
     double s = 0.0;
     uint32_t n = 0, nn = 0;
+    unsigned long long mk = 0;
 #pragma unroll
     for (int e = 0; e < kSegE; ++e) {
-        if (use[e]) { s += (double)x[e]; n += 1; nn += is_nan(x[e]) ? 1u : 0u; }
+        if (use[e]) {
+            s += (double)x[e]; n += 1; nn += is_nan(x[e]) ? 1u : 0u;
+            const unsigned long long k = to_key<double>((double)x[e]);
+            mk = k > mk ? k : mk;
+        }
     }
+    mk = warp_max(mk);
+    if ((threadIdx.x & 31) == 0 && mk) atomicMax(reinterpret_cast<unsigned long long*>(&red[4]), mk);
     s = warp_sum_d(s);
     n = __reduce_add_sync(0xffffffffu, n);
     nn = __reduce_add_sync(0xffffffffu, nn);
@@ -306,8 +319,9 @@ RFI_DEVINL void seg_moments(const T (&x)[kSegE], const bool (&use)[kSegE], doubl
     o.count = (long long)n_use;
     o.n_nan = (long long)n_nan;
     if (n_use == 0) {
-        o.mean = o.std = o.median = o.mad = __longlong_as_double(0x7ff8000000000000LL);
+        o.mean = o.std = o.median = o.mad = o.max = __longlong_as_double(0x7ff8000000000000LL);
     } else {
+        o.max = from_key<double>(*reinterpret_cast<unsigned long long*>(&red[4]));
         o.mean = (double)mean_t;
         o.std = (double)Scalar<T>::sqrt_rn((T)(sumsq / (double)n_use));
     }
@@ -325,7 +339,7 @@ stats_segmented_kernel(const void* __restrict__ data, const uint8_t* __restrict_
     __shared__ BlockScratch<NT> scr;
     __shared__ RoundCounter rc;
     __shared__ SelectScratch<K> sel;
-    __shared__ double red[4];
+    __shared__ double red[5];  // sum, count, NaNs, squared deviations, max key (bits)
     int parity = 0, round = 0;
     round_init(rc);
     const long long base = (long long)blockIdx.x * seg;
@@ -345,7 +359,7 @@ stats_segmented_kernel(const void* __restrict__ data, const uint8_t* __restrict_
         const bool (&use)[E] = which == 0 ? in_seg : clean;
         rfi_stats_t o;
         o.n_flagged = 0;
-        if (threadIdx.x < 4) red[threadIdx.x] = 0.0;
+        if (threadIdx.x < 5) red[threadIdx.x] = 0.0;
         __syncthreads();
         T mean_t;
         uint32_t n_use, n_nan;

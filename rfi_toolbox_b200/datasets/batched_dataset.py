@@ -67,3 +67,90 @@ class TorchDataset:
     def __repr__(self):
         return (f"TorchDataset(samples={len(self)}, image_shape={tuple(self.images.shape[1:])}, "
                 f"size={self._size_gb():.2f}GB)")
+
+
+class BatchWriter:
+    """Mirror of rfi_toolbox/datasets/batched_dataset.py:79-184: accumulates `TorchDataset`s and
+    writes `batch_###.pt` files ({"images", "labels"} CPU tensors, `samples_per_batch` samples
+    each) plus `metadata.json` -- the sink after the hot path.
+
+    B200 differences: datasets normally arrive resident in HBM.  `add_batch` starts an
+    asynchronous device->pinned-host copy on a side stream and returns at once, so the next
+    `create_dataset` overlaps the download; the copy is awaited only when a file is written.
+    File contents and names are the reference's.  `metadata.json` records the actual patch
+    shape (the reference hard-codes 1024 x 1024, :172-173)."""
+
+    def __init__(self, output_dir, samples_per_batch=100):
+        self.output_dir = Path(output_dir)
+        self.output_dir.mkdir(parents=True, exist_ok=True)
+        self.samples_per_batch = samples_per_batch
+        self.accumulated_images = []
+        self.accumulated_labels = []
+        self._pending = []  # events of in-flight downloads
+        self.batch_file_idx = 0
+        self.total_samples = 0
+        self._shape = None
+        self._stream = None
+
+    def _to_host(self, t):
+        if not t.is_cuda:
+            return t
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=t.device)
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        self._stream.wait_stream(torch.cuda.current_stream(t.device))
+        with torch.cuda.stream(self._stream):
+            host.copy_(t, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._stream)
+        t.record_stream(self._stream)
+        self._pending.append(ev)
+        return host
+
+    def add_batch(self, dataset):
+        self._shape = tuple(dataset.images.shape[1:])
+        self.accumulated_images.append(self._to_host(dataset.images))
+        self.accumulated_labels.append(self._to_host(dataset.labels))
+        if sum(len(img) for img in self.accumulated_images) >= self.samples_per_batch:
+            self._flush()
+
+    def _flush(self):
+        if not self.accumulated_images:
+            return
+        for ev in self._pending:
+            ev.synchronize()
+        self._pending = []
+        images = torch.cat(self.accumulated_images)
+        labels = torch.cat(self.accumulated_labels)
+        self.accumulated_images, self.accumulated_labels = [], []
+        for start in range(0, len(images), self.samples_per_batch):
+            end = min(start + self.samples_per_batch, len(images))
+            img, lab = images[start:end], labels[start:end]
+            batch_file = self.output_dir / f"batch_{self.batch_file_idx:03d}.pt"
+            torch.save({"images": img, "labels": lab}, batch_file)
+            size_gb = (img.element_size() * img.numel() + lab.element_size() * lab.numel()) / 1e9
+            print(f"    Wrote {batch_file.name}: {len(img)} patches ({size_gb:.2f} GB)")
+            self.total_samples += len(img)
+            self.batch_file_idx += 1
+
+    def finalize(self):
+        import json
+
+        if self.accumulated_images:
+            self._flush()
+        shape = list(self._shape) if self._shape else [1024, 1024, 3]
+        metadata = {
+            "num_samples": self.total_samples,
+            "samples_per_batch": self.samples_per_batch,
+            "num_batches": self.batch_file_idx,
+            "image_shape": shape,
+            "mask_shape": shape[:2],
+            "dtype": "float32",
+        }
+        metadata_path = self.output_dir / "metadata.json"
+        with open(metadata_path, "w") as f:
+            json.dump(metadata, f, indent=2)
+        print("\nBatch writing complete:")
+        print(f"  Total samples: {self.total_samples}")
+        print(f"  Batch files: {self.batch_file_idx}")
+        print(f"  Metadata: {metadata_path}")

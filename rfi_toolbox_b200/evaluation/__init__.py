@@ -10,15 +10,17 @@ from .metrics import (
     evaluate_segmentation_batch,
 )
 from .statistics import (
+    compute_calcquality,
     compute_ffi,
     compute_ffi_batch,
     compute_mad,
     compute_statistics,
     compute_statistics_batch,
+    print_statistics_comparison,
 )
 
 __all__ = [
     "compute_iou", "compute_precision", "compute_recall", "compute_f1", "compute_dice",
     "evaluate_segmentation", "evaluate_segmentation_batch", "confusion_counts",
-    "compute_statistics", "compute_ffi", "compute_mad", "compute_statistics_batch", "compute_ffi_batch",
+    "compute_statistics", "compute_ffi", "compute_mad", "compute_statistics_batch", "compute_ffi_batch", "compute_calcquality", "print_statistics_comparison",
 ]

@@ -102,10 +102,70 @@ def compute_ffi(data, flags):
             "std_reduction": float(std_reduction), "flagged_fraction": float(penalty)}
 
 
+def compute_calcquality(data, flags, reference_data=None):
+    """statistics.py:100-193 (lower is better): sensitivity, mean shift, std shift and
+    over-flagging penalty from the statistics before / after flagging; the reductions
+    (moments, max) run on the GPU, the formulas are the reference's Python-float ones."""
+    if reference_data is not None:
+        ref_st, _ = _run(reference_data, None)
+        ref_stats = compute_statistics(reference_data, flags=None)
+    else:
+        ref_st, _ = _run(data, None)
+        ref_stats = compute_statistics(data, flags=None)
+    flag_stats = compute_statistics(data, flags=flags)
+    rmean, rstd = ref_stats["mean"], ref_stats["std"]
+    fmean, fstd = flag_stats["mean"], flag_stats["std"]
+    pflag = flag_stats["flagged_fraction"] * 100
+    if np.isnan(fmean) or np.isnan(fstd) or rstd < 1e-10:
+        return {"calcquality": np.inf, "sensitivity": np.inf, "mean_shift": np.inf, "std_shift": np.inf,
+                "overflagging_penalty": np.inf, "flagged_pct": float(pflag), "components": {}}
+    rmax = ref_st.max
+    maxdev = (rmax - rmean) / rstd
+    fdiff = fmean - rmean
+    sdiff = fstd - rstd
+    a = abs(abs(maxdev) - 3)
+    b = abs(fdiff) / rstd - 1
+    c = abs(sdiff) / rstd
+    d = max(0, (pflag - 70) / 10)
+    calcquality = np.sqrt(a**2 + b**2 + c**2 + d**2)
+    return {
+        "calcquality": float(calcquality), "sensitivity": float(a), "mean_shift": float(b),
+        "std_shift": float(c), "overflagging_penalty": float(d), "flagged_pct": float(pflag),
+        "components": {"rmean": float(rmean), "rstd": float(rstd), "fmean": float(fmean), "fstd": float(fstd),
+                       "rmax": float(rmax), "maxdev": float(maxdev), "fdiff": float(fdiff), "sdiff": float(sdiff)},
+    }
+
+
+def print_statistics_comparison(data, flags):
+    """statistics.py:196-229 -- same text, same number formats."""
+    b = compute_statistics(data, flags=None)
+    a = compute_statistics(data, flags=flags)
+    f = compute_ffi(data, flags)
+    print("\n" + "=" * 60)
+    print("Statistics Comparison (Before/After Flagging)")
+    print("=" * 60)
+    print("\nBefore Flagging:")
+    print(f"  Mean:   {b['mean']:.4e}")
+    print(f"  Median: {b['median']:.4e}")
+    print(f"  Std:    {b['std']:.4e}")
+    print(f"  MAD:    {b['mad']:.4e}")
+    print(f"  Count:  {b['count']}")
+    print(f"\nAfter Flagging ({a['flagged_fraction']*100:.2f}% flagged):")
+    print(f"  Mean:   {a['mean']:.4e}")
+    print(f"  Median: {a['median']:.4e}")
+    print(f"  Std:    {a['std']:.4e}")
+    print(f"  MAD:    {a['mad']:.4e}")
+    print(f"  Count:  {a['count']}")
+    print("\nFlagging Fidelity Index (FFI):")
+    print(f"  FFI:            {f['ffi']:.4f}")
+    print(f"  MAD Reduction:  {f['mad_reduction']:.4f}")
+    print(f"  STD Reduction:  {f['std_reduction']:.4f}")
+
+
 # ---------------------------------------------------------------------------------------------
 # per-pair sweeps (extension; BASELINE config 4): one launch for a stack of patch pairs
 _STATS_DTYPE = np.dtype([("mean", "f8"), ("median", "f8"), ("std", "f8"), ("mad", "f8"),
-                         ("count", "i8"), ("n_flagged", "i8"), ("n_nan", "i8")])
+                         ("count", "i8"), ("n_flagged", "i8"), ("n_nan", "i8"), ("max", "f8")])
 
 
 def _run_batch(data, flags):

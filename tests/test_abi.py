@@ -27,7 +27,7 @@ def test_every_declared_symbol_is_exported_and_bound(native_lib):
 def test_struct_layout_and_pure_host_calls(native_lib):
     from rfi_toolbox_b200 import _native
     assert native_lib.rfi_abi_version() == _native.ABI_VERSION
-    assert C.sizeof(_native.RfiTileStat) == 88 and C.sizeof(_native.RfiStats) == 56 and C.sizeof(_native.RfiPlan) == 64
+    assert C.sizeof(_native.RfiTileStat) == 88 and C.sizeof(_native.RfiStats) == 64 and C.sizeof(_native.RfiPlan) == 64
     plan = _native.RfiPlan(dtype=0, magnitude=0, n_waterfalls=8, channels=1024, times=2048, patch=128,
                            rotations=4, stretch=1, norm_before=1, norm_after=0, flag_mode=1, sigma=5.0)
     assert native_lib.rfi_plan_num_tiles(C.byref(plan)) == 8 * 8 * 16

@@ -142,3 +142,28 @@ def test_ffi_sweep_ragged_segment_and_errors(native_lib):
         compute_ffi_batch(const, np.zeros_like(const, dtype=np.uint8))
     with pytest.raises(NotImplementedError):
         compute_ffi_batch(np.ones((1, 256, 256), dtype=np.float32), np.zeros((1, 256, 256), dtype=bool))
+
+
+@pytest.mark.parametrize("dtype", [np.complex64, np.float32, np.float64])
+def test_calcquality_and_print_comparison(native_lib, dtype, capsys):
+    """statistics.py:100-229 (the "next" row of SURVEY section 8f)."""
+    import oracle
+    from rfi_toolbox_b200.evaluation import compute_calcquality, print_statistics_comparison
+    data, mask = make_cube(dtype=dtype, seed=71)
+    noisy = mask ^ (np.random.default_rng(5).random(mask.shape) < 0.01)
+    for kwargs in ({}, {"reference_data": data * dtype(0.5)}):
+        got, want = compute_calcquality(data, noisy, **kwargs), oracle.compute_calcquality(data, noisy, **kwargs)
+        assert set(got) == set(want)
+        for k, v in want.items():
+            if k == "components":
+                for kk, vv in v.items():
+                    assert got[k][kk] == pytest.approx(vv, rel=2e-6, abs=1e-9), kk
+            else:
+                assert got[k] == pytest.approx(v, rel=1e-5, abs=1e-6), k
+    allf = compute_calcquality(data, np.ones_like(mask))
+    assert allf["calcquality"] == np.inf and allf["components"] == {} and allf["flagged_pct"] == 100.0
+    print_statistics_comparison(data, noisy)
+    out = capsys.readouterr().out
+    assert "Statistics Comparison (Before/After Flagging)" in out and "Flagging Fidelity Index (FFI):" in out
+    st = oracle.compute_statistics(data, noisy)
+    assert f"  Count:  {st['count']}" in out and f"({st['flagged_fraction']*100:.2f}% flagged)" in out

@@ -170,3 +170,26 @@ def test_plan_slots_matches_numpy_pipeline(native_lib, shape, patch, rot):
     n_out = _native.plan_slots(plan, None, False, None, order, dest)
     assert n_out == n0 and np.array_equal(order, np.arange(n0)) and np.array_equal(dest, np.arange(n0))
     assert np.random.get_state()[2] == a
+
+
+def test_batch_writer_files_match_reference_format(tmp_path):
+    """BatchWriter (batched_dataset.py:79-184): chunking into batch_###.pt + metadata.json."""
+    import json
+    import torch
+    from rfi_toolbox_b200.datasets import BatchWriter, TorchDataset
+    w = BatchWriter(tmp_path / "out", samples_per_batch=5)
+    total = 0
+    for n in (3, 4, 6):
+        imgs = torch.arange(total, total + n, dtype=torch.float32)[:, None, None, None].expand(n, 8, 8, 3).contiguous()
+        w.add_batch(TorchDataset(imgs, torch.ones((n, 8, 8), dtype=torch.uint8), {}))
+        total += n
+    w.finalize()
+    files = sorted((tmp_path / "out").glob("batch_*.pt"))
+    assert [f.name for f in files] == ["batch_000.pt", "batch_001.pt", "batch_002.pt", "batch_003.pt"]
+    sizes = [len(torch.load(f)["images"]) for f in files]
+    assert sizes == [5, 2, 5, 1]  # the reference flushes everything accumulated, in chunks of 5
+    first = torch.cat([torch.load(f)["images"][:, 0, 0, 0] for f in files])
+    assert torch.equal(first, torch.arange(13, dtype=torch.float32))
+    meta = json.loads((tmp_path / "out" / "metadata.json").read_text())
+    assert meta["num_samples"] == 13 and meta["num_batches"] == 4 and meta["samples_per_batch"] == 5
+    assert meta["image_shape"] == [8, 8, 3] and meta["mask_shape"] == [8, 8]

@@ -86,6 +86,12 @@ def test_metrics_and_statistics(ref):
         assert ref["compute_statistics"](data, mask) == oracle.compute_statistics(data, mask)
         assert ref["compute_statistics"](data) == oracle.compute_statistics(data)
         assert ref["compute_ffi"](data, np.ones_like(mask)) == oracle.compute_ffi(data, np.ones_like(mask))
+        from rfi_toolbox.evaluation.statistics import compute_calcquality
+        noisy = mask ^ (rng.random(mask.shape) < 0.01)
+        assert compute_calcquality(data, noisy) == oracle.compute_calcquality(data, noisy)
+        assert compute_calcquality(data, noisy, reference_data=data * 0.5) == \
+            oracle.compute_calcquality(data, noisy, reference_data=data * 0.5)
+        assert compute_calcquality(data, np.ones_like(mask)) == oracle.compute_calcquality(data, np.ones_like(mask))
 
 
 def test_patchify_and_tile_agree(ref):
