@@ -99,57 +99,57 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 50 ms from before the warm-up;
-    `window()` keeps the samples whose host timestamp falls inside the timed region (or,
-    when the region is shorter than the sampling period, the samples taken under load)."""
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons sampled through NVML every 5 ms from a host thread
+    (nvidia-smi's own loop cannot go below ~50 ms, longer than a short timed region);
+    `window()` keeps the samples whose host timestamp falls inside the timed region."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self._stop, self._thr, self._h = index, [], False, None, None
+        self.max_mhz = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
-                 "--format=csv,noheader,nounits", "-lms", "50"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            self._h = None
+            return
+        self._thr = threading.Thread(target=self._loop, daemon=True)
+        self._thr.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+    def _loop(self):
+        nv = self._nv
+        while not self._stop:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0
+                rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                self.rows.append((time.perf_counter(), sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
+        self._stop = True
+        if self._thr:
+            self._thr.join(timeout=1.0)
 
     def window(self, t0, t1):
-        def num(x):
-            try:
-                return float(x)
-            except ValueError:
-                return None
-        rows = [r for t, r in self.rows if len(r) >= 9 and t0 <= t <= t1 + 0.06]
+        rows = [r for r in self.rows if t0 <= r[0] <= t1]
         scope = "timed region"
         if not rows:
-            rows = [r for t, r in self.rows if len(r) >= 9 and (num(r[3]) or 0) > 250.0]
+            rows = [r for r in self.rows if r[2] > 250.0]
             scope = "under load (warm-up + timed region; region shorter than the sampling period)"
-        sm = [num(r[1]) for r in rows if num(r[1]) is not None]
-        mx = [num(r[2]) for r in rows if num(r[2]) is not None]
-        pw = [num(r[3]) for r in rows if num(r[3]) is not None]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            for n, v in zip(names, r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm),
-                "scope": scope}
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        reasons = sorted({n for r in rows for bit, n in names.items() if r[3] & bit})
+        sm = [r[1] for r in rows]
+        pw = [r[2] for r in rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(sm), "scope": scope}
 
 
 # ------------------------------------------------------------------------------------- GPU side
@@ -217,7 +217,6 @@ def run_ours(args):
     barrier()
     t1 = time.perf_counter()
     wall = t1 - t0
-    time.sleep(0.06)
     sampler.stop()
     clocks = sampler.window(t0, t1)
     dev_ms = e0.elapsed_time(e1)
@@ -297,9 +296,8 @@ def run_ours(args):
                    "parallelism": f"baseline-sharded x{world}, NCCL all-reduce of TP/FP/FN" if world > 1 else "single GPU"},
         "e2e": {"value": e2e_value, "unit": "Gpixel/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "note": "pinned host cube copied H2D every step; dataset stays in HBM, metric dict read back"},
-        # per step: tile_stats_mono_kernel, tile_stats_kernel (fallback tiles), write_patches_kernel,
-        # confusion_kernel
-        "gpu_launches": 4 * args.steps,
+        # per step: tile_stats_mono_kernel, write_patches_kernel, confusion_kernel
+        "gpu_launches": 3 * args.steps,
         "roofline": roofline,
         "cpu_baseline": {"value": cpu_v, "unit": "Gpixel/s", "cores": 1, "kind": "port",
                          "sample": f"2 baselines x 4 pols x 1024x1024 ({cpu_npix} px) in {cpu_dt:.1f} s, one process"},
@@ -314,7 +312,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--baselines", type=int, default=0, help="override the 45 baselines per GPU (debug)")

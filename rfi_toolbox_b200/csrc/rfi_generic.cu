@@ -227,14 +227,14 @@ gsel_count_kernel(GGeom g, const void* __restrict__ data, const rfi_tile_stat_t*
     const GWindow win = group_window(g, grp);
     const K prefix = (K)s.prefix;
     const int shift = s.shift;
-    const long long n = (long long)g.Pr * g.Pc;
+    const uint32_t n = (uint32_t)g.Pr * (uint32_t)g.Pc;
     unsigned int c[16];
 #pragma unroll
     for (int t = 0; t < 16; ++t) c[t] = 0;
     for (int k = 0; k < kGE; ++k) {
-        const long long e = (long long)chunk * kGChunk + (long long)k * kGT + threadIdx.x;
+        const uint32_t e = (uint32_t)chunk * kGChunk + (uint32_t)k * kGT + threadIdx.x;  // < 2^31 (make_geom)
         if (e >= n) break;
-        const long long yy = e / g.Pc, xx = e % g.Pc;
+        const uint32_t yy = e / (uint32_t)g.Pc, xx = e - yy * (uint32_t)g.Pc;
         T a, ph;
         load_src<DT, false>(data, g, win.w, win.r0 + yy, win.c0 + xx, a, ph);
         const K key = stage_key<T, STAGE>(a, g, ctx);
@@ -297,9 +297,9 @@ gsel_next_kernel(GGeom g, const void* __restrict__ data, const rfi_tile_stat_t* 
     unsigned int cle = 0;
     K nxt = ~K(0);
     for (int k = 0; k < kGE; ++k) {
-        const long long e = (long long)chunk * kGChunk + (long long)k * kGT + threadIdx.x;
+        const uint32_t e = (uint32_t)chunk * kGChunk + (uint32_t)k * kGT + threadIdx.x;  // < 2^31 (make_geom)
         if (e >= n) break;
-        const long long yy = e / g.Pc, xx = e % g.Pc;
+        const uint32_t yy = e / (uint32_t)g.Pc, xx = e - yy * (uint32_t)g.Pc;
         T a, ph;
         load_src<DT, false>(data, g, win.w, win.r0 + yy, win.c0 + xx, a, ph);
         const K key = stage_key<T, STAGE>(a, g, ctx);
@@ -357,9 +357,9 @@ ginf_count_kernel(GGeom g, const void* __restrict__ data, rfi_tile_stat_t* __res
     const long long n = (long long)g.Pr * g.Pc;
     unsigned int ninf = 0, nfin = 0;
     for (int k = 0; k < kGE; ++k) {
-        const long long e = (long long)chunk * kGChunk + (long long)k * kGT + threadIdx.x;
+        const uint32_t e = (uint32_t)chunk * kGChunk + (uint32_t)k * kGT + threadIdx.x;  // < 2^31 (make_geom)
         if (e >= n) break;
-        const long long yy = e / g.Pc, xx = e % g.Pc;
+        const uint32_t yy = e / (uint32_t)g.Pc, xx = e - yy * (uint32_t)g.Pc;
         T a, ph;
         load_src<DT, false>(data, g, win.w, win.r0 + yy, win.c0 + xx, a, ph);
         if (ctx.divide) a = a / ctx.m;
@@ -388,9 +388,10 @@ gflag_count_kernel(GGeom g, const void* __restrict__ data, const uint8_t* __rest
     const long long n = (long long)g.Pr * g.Pc;
     unsigned int nf = 0;
     for (int k = 0; k < kGE; ++k) {
-        const long long e = (long long)chunk * kGChunk + (long long)k * kGT + threadIdx.x;
+        const uint32_t e = (uint32_t)chunk * kGChunk + (uint32_t)k * kGT + threadIdx.x;
         if (e >= n) break;
-        const long long row = win.r0 + e / g.Pc, col = win.c0 + e % g.Pc;
+        const uint32_t yy = e / (uint32_t)g.Pc;
+        const long long row = win.r0 + yy, col = win.c0 + (e - yy * (uint32_t)g.Pc);
         if (g.flag_mode == RFI_FLAGS_MAD) {
             T a, ph;
             load_src<DT, false>(data, g, win.w, row, col, a, ph);
@@ -476,9 +477,9 @@ grange_kernel(GGeom g, const void* __restrict__ data, const rfi_tile_stat_t* __r
     const long long n = (long long)p.rows * p.cols;
     K llo = ~K(0), lhi = 0, glo = ~K(0), ghi = 0;
     for (int k = 0; k < kGE; ++k) {
-        const long long e = (long long)chunk * kGChunk + (long long)k * kGT + threadIdx.x;
+        const uint32_t e = (uint32_t)chunk * kGChunk + (uint32_t)k * kGT + threadIdx.x;
         if (e >= n) break;
-        const int y = (int)(e / p.cols), x = (int)(e % p.cols);
+        const int y = (int)(e / (uint32_t)p.cols), x = (int)(e - (uint32_t)y * (uint32_t)p.cols);
         const T c = eval_L<DT>(data, g, p, ctx, y, x);
         const T td = (y > 0) ? c - eval_L<DT>(data, g, p, ctx, y - 1, x) : T(0);
         const T fd = (x > 0) ? c - eval_L<DT>(data, g, p, ctx, y, x - 1) : T(0);
@@ -523,9 +524,9 @@ gwrite_kernel(GGeom g, const void* __restrict__ data, const uint8_t* __restrict_
     float* out_img = images + (size_t)slot * n * 3;
     uint8_t* out_lab = labels + (size_t)slot * n;
     for (int k = 0; k < kGE; ++k) {
-        const long long e = (long long)chunk * kGChunk + (long long)k * kGT + threadIdx.x;
+        const uint32_t e = (uint32_t)chunk * kGChunk + (uint32_t)k * kGT + threadIdx.x;
         if (e >= n) break;
-        const int y = (int)(e / p.cols), x = (int)(e % p.cols);
+        const int y = (int)(e / (uint32_t)p.cols), x = (int)(e - (uint32_t)y * (uint32_t)p.cols);
         T xp, c, ph;
         eval_pixel<DT, kComplexBranch>(data, g, p, ctx, y, x, xp, c, ph);
         const T td = (y > 0) ? c - eval_L<DT>(data, g, p, ctx, y - 1, x) : T(0);
@@ -591,6 +592,7 @@ static int make_geom(const rfi_plan_t* plan, GGeom& g) {
     g.n_patches = g.n_waterfalls * g.R * g.per;
     g.n_groups = g.padded ? g.n_patches : g.n_waterfalls * g.per;
     const long long n = (long long)g.Pr * g.Pc;
+    if (n > 0x40000000LL) { set_error("patch of %lld samples is too large", n); return RFI_E_UNSUPPORTED; }
     g.chunks = (int)((n + kGChunk - 1) / kGChunk);
     g.stretch = plan->stretch; g.norm_before = plan->norm_before; g.norm_after = plan->norm_after;
     g.flag_mode = plan->flag_mode; g.sigma = plan->sigma;

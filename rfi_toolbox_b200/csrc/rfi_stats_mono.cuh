@@ -19,7 +19,8 @@
 // keys inside it; the exact rank inside that list is resolved by a 512-bucket linear
 // histogram + one <= 64 element ranking.  All brackets are validated (the answer must fall
 // strictly inside what was proven), otherwise the tile is handed to the general kernel
-// (tile_stats_kernel, RFI_TILE_GENERAL) -- results are exact either way.
+// (tile_stats_general, RFI_TILE_GENERAL), which then runs in the same CTA -- results are exact
+// either way.
 //
 // Cost: ~45 k warp instructions per tile instead of ~150 k for the 32-round register
 // bisection; keys live in shared memory (64 KB per float32 tile, 2 CTAs / SM).
@@ -227,6 +228,12 @@ RFI_DEVINL void mono_resolve(const K* cand, uint32_t M, uint32_t q1, uint32_t q2
     __syncthreads();
 }
 
+// general algorithm (rfi_tiles.cu): any tile, register-resident radix select
+template <int DT, int NT>
+__device__ void tile_stats_general(const PlanDev& p, const void* __restrict__ data,
+                                   const uint8_t* __restrict__ flags, rfi_tile_stat_t* __restrict__ stats,
+                                   int route_bits);
+
 template <int DT, int NT>
 __global__ void __launch_bounds__(NT, (sizeof(typename In<DT>::T) == 4) ? 2 : 1)
 tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __restrict__ flags,
@@ -258,7 +265,8 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
     // (the reason is kept in the upper bits of `route` until the general kernel overwrites it;
     //  scripts/diag_stats.py reads it)
     auto give_up = [&](int reason) {
-        if (tid == 0) stats[tile].route = RFI_TILE_GENERAL | (reason << 8);
+        __syncthreads();  // shared memory is handed over
+        tile_stats_general<DT, NT>(p, data, flags, stats, RFI_TILE_GENERAL | (reason << 8));
     };
 
     // ---- load: magnitude fused into the 128-bit loads, raw bit patterns to shared memory.

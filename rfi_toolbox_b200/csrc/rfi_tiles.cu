@@ -33,11 +33,9 @@ namespace rfi {
 // The shortcut is dropped (general selects) as soon as a tile has a negative, infinite or
 // inf-filled sample.
 template <int DT, int NT>
-__global__ void __launch_bounds__(NT, (sizeof(typename In<DT>::T) == 4) ? 2 : 1)
-tile_stats_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __restrict__ flags,
-                  rfi_tile_stat_t* __restrict__ stats, int only_general) {
-    // second launch after tile_stats_mono_kernel: only the tiles it handed over
-    if (only_general && (stats[blockIdx.x].route & 0xff) != RFI_TILE_GENERAL) return;
+__device__ __noinline__ void tile_stats_general(const PlanDev& p, const void* __restrict__ data,
+                                                const uint8_t* __restrict__ flags,
+                                                rfi_tile_stat_t* __restrict__ stats, int route_bits) {
     using T = typename In<DT>::T;
     using K = typename Scalar<T>::key_t;
     constexpr int E = kP * kP / NT;  // samples per thread
@@ -77,7 +75,7 @@ tile_stats_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __res
     if (threadIdx.x == 0) {
         st.median_before = st.inf_fill = st.median_after = 0.0;
         st.centre = st.mad = st.thr_lo = st.thr_hi = 0.0;
-        st.n_valid = 0; st.n_inf = 0; st.n_flagged = 0; st.route = only_general ? (stats[blockIdx.x].route | 0) : RFI_TILE_GENERAL; st.raw_lo = st.raw_hi = 0.0;
+        st.n_valid = 0; st.n_inf = 0; st.n_flagged = 0; st.route = route_bits; st.raw_lo = st.raw_hi = 0.0;
     }
 
     // non-NaN samples (recounted before every general median: inf / inf can create a NaN)
@@ -219,6 +217,15 @@ tile_stats_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __res
         if (threadIdx.x == 0) st.n_flagged = (int)nf;
     }
     if (threadIdx.x == 0) stats[tile] = st;
+}
+
+// the general algorithm as a kernel of its own (tests; tiles of the float64 paths reach it
+// through tile_stats_mono_kernel like every other tile)
+template <int DT, int NT>
+__global__ void __launch_bounds__(NT, (sizeof(typename In<DT>::T) == 4) ? 2 : 1)
+tile_stats_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __restrict__ flags,
+                  rfi_tile_stat_t* __restrict__ stats) {
+    tile_stats_general<DT, NT>(p, data, flags, stats, RFI_TILE_GENERAL);
 }
 
 // custom flags / inference with nothing to measure on the data: flags only.
@@ -541,12 +548,10 @@ static int launch_stats(const PlanDev& d, long long tiles, const void* data, con
     auto mono = tile_stats_mono_kernel<DT, kMonoNT>;
     size_t msmem = (size_t)(kP * kP + kMonoCap + kMonoNT) * sizeof(K);
     RFI_CUDA_TRY(cudaFuncSetAttribute(mono, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+    // tiles with negative / infinite / inf-filled samples, or whose sampled bracket missed, run
+    // the general algorithm inside the same CTA (no second launch, no tail)
     mono<<<(unsigned)tiles, kMonoNT, msmem, st>>>(d, data, flags, stats);
-    // tiles with negative / infinite / inf-filled samples, or whose sampled bracket missed
-    auto kern = tile_stats_kernel<DT, NT>;
-    size_t smem = (size_t)kP * kP * sizeof(K);
-    RFI_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)tiles, NT, smem, st>>>(d, data, flags, stats, 1);
+    static_assert(NT == kMonoNT, "the general path runs inside the monotone kernel's CTA");
     return RFI_OK;
 }
 
