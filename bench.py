@@ -33,14 +33,21 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 WORKLOAD = dict(n_bl=45, n_pol=4, channels=1024, times=1024, patch=128, stretch="SQRT", sigma=5, rot=4)
+# other BASELINE.json configs, runnable for the record (`--workload c3`): per-GPU shard of the
+# VLA-scale cube (351 baselines over 8 GPUs = 44 per GPU), LOG10 stretch
+WORKLOADS = {
+    "c2": dict(WORKLOAD, name="configs[1]"),
+    "c3": dict(n_bl=44, n_pol=4, channels=4096, times=2048, patch=128, stretch="LOG10", sigma=5, rot=4, name="configs[2] (one of 8 baseline shards)"),
+}
 METRIC = "waterfall Gpixel/s (create_dataset+metrics)"
+ACTIVE = WORKLOAD  # set from --workload in main(); inherited by the forked CPU-baseline workers
 
 
 # ------------------------------------------------------------------------------------- CPU side
 def _cpu_cube(n_bl, seed):
     from tests.cubes import make_cube
-    return make_cube(n_bl=n_bl, n_pol=WORKLOAD["n_pol"], channels=WORKLOAD["channels"],
-                     times=WORKLOAD["times"], seed=seed, dtype=np.complex64)
+    return make_cube(n_bl=n_bl, n_pol=ACTIVE["n_pol"], channels=ACTIVE["channels"],
+                     times=ACTIVE["times"], seed=seed, dtype=np.complex64)
 
 
 def _cpu_step(args):
@@ -48,8 +55,8 @@ def _cpu_step(args):
     import oracle
     cube, truth_seed = args
     np.random.seed(truth_seed)
-    ds = oracle.create_dataset(np.abs(cube), None, patch_size=WORKLOAD["patch"], stretch=WORKLOAD["stretch"],
-                               flag_sigma=WORKLOAD["sigma"], use_custom_flags=False, num_workers=0)
+    ds = oracle.create_dataset(np.abs(cube), None, patch_size=ACTIVE["patch"], stretch=ACTIVE["stretch"],
+                               flag_sigma=ACTIVE["sigma"], use_custom_flags=False, num_workers=0)
     truth = ds.labels ^ (np.random.default_rng(truth_seed).random(ds.labels.shape) < 0.01)
     oracle.evaluate_segmentation(ds.labels, truth)
     return cube.size
@@ -82,12 +89,15 @@ def run_reference(args):
         times.append(dt)
     total = sum(times)
     value = npix * len(times) / total / 1e9
-    sample = f"{procs} processes x 1 baseline x 4 pols x 1024x1024 per step (one Preprocessor per process)"
+    sample = (f"{procs} processes x 1 baseline x 4 pols x {ACTIVE['channels']}x{ACTIVE['times']} per step "
+              "(one Preprocessor per process)")
     line = {
         "metric": METRIC, "value": value, "unit": "Gpixel/s", "impl": "reference", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1] 45bl x 4pol x 1024ch x 1024t complex64, SQRT, MAD sigma=5, R=4, P=128",
+        "config": {"workload": f"{ACTIVE.get('name', 'configs[1]')} {ACTIVE['n_bl']}bl x {ACTIVE['n_pol']}pol x "
+                               f"{ACTIVE['channels']}ch x {ACTIVE['times']}t complex64, {ACTIVE['stretch']}, "
+                               f"MAD sigma={ACTIVE['sigma']}, R={ACTIVE['rot']}, P={ACTIVE['patch']}",
                    "sample": sample},
         "cpu_baseline": {"value": value, "unit": "Gpixel/s", "cores": procs, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Gpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -169,7 +179,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     group = True if world > 1 else None
 
-    w = dict(WORKLOAD)
+    w = dict(WORKLOADS[args.workload])
     if args.baselines:
         w["n_bl"] = args.baselines
     cube, mask = device_cube(w["n_bl"], w["n_pol"], w["channels"], w["times"], seed=1234 + rank, device=dev)
@@ -275,7 +285,7 @@ def run_ours(args):
     # (profiles/traffic.json, written by scripts/ncu_summary.py); null for any other workload
     traffic = None
     tj = ROOT / "profiles" / "traffic.json"
-    if tj.exists() and not args.baselines:
+    if tj.exists() and not args.baselines and args.workload == "c2":
         traffic = json.loads(tj.read_text()).get("write_patches_kernel", {}).get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "kernel": "write_patches_kernel", "achieved": achieved, "peak": peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -283,16 +293,18 @@ def run_ours(args):
                 "stats_kernel_ms": stats_ms, "stats_kernel_gbs": npix * cube.element_size() / (stats_ms * 1e-3) / 1e9,
                 "step_ms_device": dev_ms / args.steps}
 
-    cpu_v, cpu_npix, cpu_dt = cpu_baseline(2, 1)
+    cpu_bl = 2 if w["channels"] * w["times"] <= 1 << 20 else 1
+    cpu_v, cpu_npix, cpu_dt = cpu_baseline(cpu_bl, 1)
     line = {
         "metric": METRIC, "value": value, "unit": "Gpixel/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"configs[1] {w['n_bl']}bl x {w['n_pol']}pol x {w['channels']}ch x {w['times']}t "
+        "config": {"workload": f"{w['name']} {w['n_bl']}bl x {w['n_pol']}pol x {w['channels']}ch x {w['times']}t "
                                f"complex64 per GPU, magnitude fused, {w['stretch']}, MAD sigma={w['sigma']}, "
                                f"R={w['rot']}, P={w['patch']}",
                    "pixels_per_step_per_gpu": npix, "patches_kept": n_kept,
-                   "l2": "input cube 1.5 GB and 9.8 GB of output per step exceed the 126 MB L2; no flush needed",
+                   "l2": f"input cube {cube.numel() * 8 / 1e9:.1f} GB and {n_kept * w['patch'] ** 2 * 13 / 1e9:.1f} GB of output "
+                         "per step exceed the 126 MB L2; no flush needed",
                    "parallelism": f"baseline-sharded x{world}, NCCL all-reduce of TP/FP/FN" if world > 1 else "single GPU"},
         "e2e": {"value": e2e_value, "unit": "Gpixel/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "note": "pinned host cube copied H2D every step; dataset stays in HBM, metric dict read back"},
@@ -300,7 +312,7 @@ def run_ours(args):
         "gpu_launches": 3 * args.steps,
         "roofline": roofline,
         "cpu_baseline": {"value": cpu_v, "unit": "Gpixel/s", "cores": 1, "kind": "port",
-                         "sample": f"2 baselines x 4 pols x 1024x1024 ({cpu_npix} px) in {cpu_dt:.1f} s, one process"},
+                         "sample": f"{cpu_bl} baselines x 4 pols x {w['channels']}x{w['times']} ({cpu_npix} px) in {cpu_dt:.1f} s, one process"},
         "clocks": clocks, "wall_s": wall, "metrics_last_step": {k_: float(v) for k_, v in m.items()},
     }
     print(json.dumps(line))
@@ -316,7 +328,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--baselines", type=int, default=0, help="override the 45 baselines per GPU (debug)")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = the bench workload (default)")
     args = ap.parse_args()
+    global ACTIVE
+    ACTIVE = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -705,7 +705,7 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
         st.centre = (double)c; st.mad = (double)d;
         st.thr_lo = (double)thr_lo; st.thr_hi = (double)thr_hi;
         st.n_valid = (int)nv; st.n_inf = 0; st.n_flagged = (int)nflag;
-        st.route = (p.flag_mode == RFI_FLAGS_MAD) ? RFI_TILE_RAW_THRESHOLDS : 0;
+        st.route = RFI_TILE_RAW_THRESHOLDS;  // monotone tile: raw thresholds valid (0 / +inf when labels are not MAD flags)
         st.raw_lo = (double)raw_lo; st.raw_hi = (double)raw_hi;
         stats[tile] = st;
     }

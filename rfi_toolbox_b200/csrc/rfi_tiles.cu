@@ -334,13 +334,13 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
     // the current ones go through magnitude / normalise / stretch / log10 (the loop is NOT
     // unrolled over steps: the body is long and must stay inside the I-cache).
     //
-    // Fast route (float32, tile measured by the monotone kernel, stretch None / SQRT): the label
+    // Fast route (float32, tile measured by the monotone kernel): the label
     // is two compares of the exact magnitude with the raw-domain thresholds of phase 1 -- no
     // division, no square root -- and the log amplitude, which only feeds the tolerance-class
     // image channels, comes from reciprocal-multiply, sqrt.approx and lg2.approx (|dL| < 2e-7).
     T llo = Scalar<T>::nan(), lhi = Scalar<T>::nan();
     const bool fast_route = std::is_same<T, float>::value && !kComplexBranch &&
-                            (st.route & RFI_TILE_RAW_THRESHOLDS) != 0 && p.stretch != RFI_STRETCH_LOG10;
+                            (st.route & RFI_TILE_RAW_THRESHOLDS) != 0;
     auto pass_a = [&](auto fast_tag) {
         constexpr bool kFast = decltype(fast_tag)::value;
         [[maybe_unused]] const float raw_lo = (float)st.raw_lo, raw_hi = (float)st.raw_hi;
@@ -374,8 +374,16 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
                     raw_to_mag_fast<DT>(cur[q], a);
                     ph = T(0);
                     if (p.flag_mode == RFI_FLAGS_MAD) f = ((a > (T)raw_hi) || (a < (T)raw_lo)) ? 1 : 0;
-                    float y = (float)a * rm;
-                    if (p.stretch == RFI_STRETCH_SQRT) y = sqrt_fast(y);
+                    float y;
+                    if (p.stretch == RFI_STRETCH_LOG10) {
+                        // log10 cancels near y = 1: the quotient must be the exactly rounded one and
+                        // the logarithm relatively accurate (log10f, 2 ulp); only the outer log is approximate
+                        y = (p.norm_before && med_before > T(0)) ? (float)a / (float)med_before : (float)a;
+                        y = fabsf(log10f(y));
+                    } else {
+                        y = (float)a * rm;
+                        if (p.stretch == RFI_STRETCH_SQRT) y = sqrt_fast(y);
+                    }
                     y = y * rm2;
                     L = (T)(lg2_fast(y + 1e-10f) * 0.30102999566f);
                 } else {
