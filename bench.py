@@ -38,6 +38,10 @@ WORKLOAD = dict(n_bl=45, n_pol=4, channels=1024, times=1024, patch=128, stretch=
 WORKLOADS = {
     "c2": dict(WORKLOAD, name="configs[1]"),
     "c3": dict(n_bl=44, n_pol=4, channels=4096, times=2048, patch=128, stretch="LOG10", sigma=5, rot=4, name="configs[2] (one of 8 baseline shards)"),
+    # long-track cube, P = 256 (big-tile path): the per-GPU shard (44 baselines, 153 GB of output) is
+    # streamed through create_dataset in baseline chunks; one step = one 8-baseline chunk
+    "c5": dict(n_bl=8, n_pol=4, channels=1024, times=16384, patch=256, stretch=None, sigma=3, rot=4,
+               name="configs[4] (8-baseline chunk of one of 8 baseline shards)"),
 }
 METRIC = "waterfall Gpixel/s (create_dataset+metrics)"
 ACTIVE = WORKLOAD  # set from --workload in main(); inherited by the forked CPU-baseline workers
@@ -277,7 +281,8 @@ def run_ours(args):
         peaks = json.loads(pk.read_text())
     peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
     k = n_kept / (n_tiles * w["rot"])
-    alg_bytes = npix * (cube.element_size() + w["rot"] * k * 13.0)
+    # the big-tile writer (P > 128) reads the float32 magnitude scratch of phase 1, not the complex cube
+    alg_bytes = npix * ((cube.element_size() if w["patch"] == 128 else 4) + w["rot"] * k * 13.0)
     write_ms = float(np.mean(kern_ms["write"]))
     stats_ms = float(np.mean(kern_ms["stats"]))
     achieved = alg_bytes / (write_ms * 1e-3) / 1e9
@@ -287,7 +292,8 @@ def run_ours(args):
     tj = ROOT / "profiles" / "traffic.json"
     if tj.exists() and not args.baselines and args.workload == "c2":
         traffic = json.loads(tj.read_text()).get("write_patches_kernel", {}).get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "write_patches_kernel", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "write_patches_kernel" if w["patch"] == 128 else "big_write_kernel",
+                "achieved": achieved, "peak": peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": write_ms,
                 "stats_kernel_ms": stats_ms, "stats_kernel_gbs": npix * cube.element_size() / (stats_ms * 1e-3) / 1e9,

@@ -43,7 +43,13 @@ struct GGeom {
     int chunks;              // CTAs per group / per patch
     int stretch, norm_before, norm_after, flag_mode, real_branch;
     double sigma;
+    // statistics over a SUBSET of the groups (the big-tile path's fallback, rfi_bigtile.cu):
+    // `list` holds n_active group indices; NULL = all n_groups groups
+    const int* list;
+    long long n_active;
 };
+
+RFI_DEVINL long long active_group(const GGeom& g, long long i) { return g.list ? (long long)g.list[i] : i; }
 
 // select state of one group (workspace)
 struct GSel {
@@ -218,7 +224,7 @@ gsel_count_kernel(GGeom g, const void* __restrict__ data, const rfi_tile_stat_t*
                   GSel* __restrict__ sel) {
     using T = typename In<DT>::T;
     using K = typename Scalar<T>::key_t;
-    const long long grp = blockIdx.x / g.chunks;
+    const long long grp = active_group(g, blockIdx.x / g.chunks);
     const int chunk = blockIdx.x % g.chunks;
     const rfi_tile_stat_t st = stats[grp];
     const GSel s = sel[grp];
@@ -255,8 +261,9 @@ gsel_count_kernel(GGeom g, const void* __restrict__ data, const rfi_tile_stat_t*
 }
 
 __global__ void gsel_begin_kernel(GGeom g, GSel* __restrict__ sel, int key_bits) {
-    const long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (grp >= g.n_groups) return;
+    const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= g.n_active) return;
+    const long long grp = active_group(g, gi);
     GSel& s = sel[grp];
     s.prefix = 0; s.nxt = ~0ull; s.cle = 0; s.n = 0; s.k1 = s.k2 = 0;
     s.shift = key_bits - 4;
@@ -264,8 +271,9 @@ __global__ void gsel_begin_kernel(GGeom g, GSel* __restrict__ sel, int key_bits)
 }
 
 __global__ void gsel_decide_kernel(GGeom g, GSel* __restrict__ sel, int first) {
-    const long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (grp >= g.n_groups) return;
+    const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= g.n_active) return;
+    const long long grp = active_group(g, gi);
     GSel& s = sel[grp];
     if (first) {
         s.n = s.cnt[15];
@@ -285,7 +293,7 @@ gsel_next_kernel(GGeom g, const void* __restrict__ data, const rfi_tile_stat_t* 
                  GSel* __restrict__ sel) {
     using T = typename In<DT>::T;
     using K = typename Scalar<T>::key_t;
-    const long long grp = blockIdx.x / g.chunks;
+    const long long grp = active_group(g, blockIdx.x / g.chunks);
     const int chunk = blockIdx.x % g.chunks;
     const rfi_tile_stat_t st = stats[grp];
     const GSel s = sel[grp];
@@ -318,8 +326,9 @@ gsel_next_kernel(GGeom g, const void* __restrict__ data, const rfi_tile_stat_t* 
 template <typename T, int STAGE>
 __global__ void gsel_finish_kernel(GGeom g, rfi_tile_stat_t* __restrict__ stats, GSel* __restrict__ sel) {
     using K = typename Scalar<T>::key_t;
-    const long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (grp >= g.n_groups) return;
+    const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= g.n_active) return;
+    const long long grp = active_group(g, gi);
     rfi_tile_stat_t& st = stats[grp];
     GSel& s = sel[grp];
     if (!stage_active(STAGE, st, s)) return;
@@ -350,7 +359,7 @@ __global__ void __launch_bounds__(kGT)
 ginf_count_kernel(GGeom g, const void* __restrict__ data, rfi_tile_stat_t* __restrict__ stats,
                   GSel* __restrict__ sel) {
     using T = typename In<DT>::T;
-    const long long grp = blockIdx.x / g.chunks;
+    const long long grp = active_group(g, blockIdx.x / g.chunks);
     const int chunk = blockIdx.x % g.chunks;
     const GCtx<T> ctx = load_ctx<T>(g, stats[grp], sel[grp]);
     const GWindow win = group_window(g, grp);
@@ -381,7 +390,7 @@ __global__ void __launch_bounds__(kGT)
 gflag_count_kernel(GGeom g, const void* __restrict__ data, const uint8_t* __restrict__ flags,
                    rfi_tile_stat_t* __restrict__ stats, const GSel* __restrict__ sel) {
     using T = typename In<DT>::T;
-    const long long grp = blockIdx.x / g.chunks;
+    const long long grp = active_group(g, blockIdx.x / g.chunks);
     const int chunk = blockIdx.x % g.chunks;
     const GCtx<T> ctx = load_ctx<T>(g, stats[grp], sel[grp]);
     const GWindow win = group_window(g, grp);
@@ -406,12 +415,14 @@ gflag_count_kernel(GGeom g, const void* __restrict__ data, const uint8_t* __rest
 }
 
 __global__ void gstats_init_kernel(GGeom g, rfi_tile_stat_t* __restrict__ stats, GSel* __restrict__ sel) {
-    const long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (grp >= g.n_groups) return;
+    const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= g.n_active) return;
+    const long long grp = active_group(g, gi);
     rfi_tile_stat_t st;
     st.median_before = st.inf_fill = st.median_after = 0.0;
     st.centre = st.mad = st.thr_lo = st.thr_hi = 0.0;
-    st.n_valid = g.Pr * g.Pc; st.n_inf = 0; st.n_flagged = 0; st.route = 0; st.raw_lo = st.raw_hi = 0.0;
+    st.n_valid = g.Pr * g.Pc; st.n_inf = 0; st.n_flagged = 0; st.raw_lo = st.raw_hi = 0.0;
+    st.route = g.list ? RFI_TILE_GENERAL : 0;
     stats[grp] = st;
     GSel s;
     s.prefix = 0; s.nxt = ~0ull; s.cle = s.n = s.k1 = s.k2 = 0; s.shift = 0; s.pad = 0;
@@ -597,6 +608,7 @@ static int make_geom(const rfi_plan_t* plan, GGeom& g) {
     g.stretch = plan->stretch; g.norm_before = plan->norm_before; g.norm_after = plan->norm_after;
     g.flag_mode = plan->flag_mode; g.sigma = plan->sigma;
     g.real_branch = (plan->dtype < RFI_C64 || plan->magnitude) ? 1 : 0;
+    g.list = nullptr; g.n_active = g.n_groups;
     if (!g.real_branch) { g.stretch = RFI_STRETCH_NONE; g.norm_before = g.norm_after = 0; }
     if ((long long)g.chunks * (g.n_patches > g.n_groups ? g.n_patches : g.n_groups) > 0x7fffffffLL) {
         set_error("cube too large for one launch of the generic path"); return RFI_E_UNSUPPORTED; }
@@ -632,8 +644,8 @@ template <int DT, int STAGE>
 static void run_select(const GGeom& g, const void* data, rfi_tile_stat_t* stats, GSel* sel, cudaStream_t st) {
     using T = typename In<DT>::T;
     constexpr int kBits = sizeof(T) * 8;
-    const unsigned gthreads = 128, ggrid = (unsigned)((g.n_groups + gthreads - 1) / gthreads);
-    const unsigned grid = (unsigned)(g.n_groups * g.chunks);
+    const unsigned gthreads = 128, ggrid = (unsigned)((g.n_active + gthreads - 1) / gthreads);
+    const unsigned grid = (unsigned)(g.n_active * g.chunks);
     gsel_begin_kernel<<<ggrid, gthreads, 0, st>>>(g, sel, kBits);
     for (int p = 0; p < kBits / 4; ++p) {
         gsel_count_kernel<DT, STAGE><<<grid, kGT, 0, st>>>(g, data, stats, sel);
@@ -646,8 +658,8 @@ static void run_select(const GGeom& g, const void* data, rfi_tile_stat_t* stats,
 template <int DT>
 static int run_generic_stats(const GGeom& g, const void* data, const uint8_t* flags,
                              rfi_tile_stat_t* stats, GSel* sel, cudaStream_t st) {
-    const unsigned gthreads = 128, ggrid = (unsigned)((g.n_groups + gthreads - 1) / gthreads);
-    const unsigned grid = (unsigned)(g.n_groups * g.chunks);
+    const unsigned gthreads = 128, ggrid = (unsigned)((g.n_active + gthreads - 1) / gthreads);
+    const unsigned grid = (unsigned)(g.n_active * g.chunks);
     gstats_init_kernel<<<ggrid, gthreads, 0, st>>>(g, stats, sel);
     if (g.real_branch) {
         if (g.norm_before) run_select<DT, GS_RAW>(g, data, stats, sel, st);
@@ -679,6 +691,24 @@ int generic_tile_stats(const rfi_plan_t* plan, const void* data, const uint8_t* 
     if (!workspace) { set_error("this geometry runs on the generic path and needs a workspace of "
                                 "rfi_plan_workspace_bytes() bytes"); return RFI_E_INVALID; }
     if (g.flag_mode == RFI_FLAGS_CUSTOM && !flags) { set_error("custom flag mode needs flags"); return RFI_E_INVALID; }
+    GSel* sel = ws_sel(workspace);
+    switch (plan->dtype) {
+        case RFI_F32: return run_generic_stats<RFI_F32>(g, data, flags, stats, sel, st);
+        case RFI_F64: return run_generic_stats<RFI_F64>(g, data, flags, stats, sel, st);
+        case RFI_C64: return run_generic_stats<RFI_C64>(g, data, flags, stats, sel, st);
+        default:      return run_generic_stats<RFI_C128>(g, data, flags, stats, sel, st);
+    }
+}
+
+int generic_tile_stats_subset(const rfi_plan_t* plan, const void* data, const uint8_t* flags,
+                              rfi_tile_stat_t* stats, void* workspace, const int* list, int n_list,
+                              cudaStream_t st) {
+    GGeom g;
+    int rc = make_geom(plan, g);
+    if (rc) return rc;
+    if (n_list <= 0) return RFI_OK;
+    if (g.padded || g.skip) { set_error("internal: group subsets need an unpadded geometry"); return RFI_E_INVALID; }
+    g.list = list; g.n_active = n_list;
     GSel* sel = ws_sel(workspace);
     switch (plan->dtype) {
         case RFI_F32: return run_generic_stats<RFI_F32>(g, data, flags, stats, sel, st);

@@ -593,6 +593,7 @@ extern "C" int64_t rfi_plan_num_patches(const rfi_plan_t* plan) {
 }
 extern "C" size_t rfi_plan_workspace_bytes(const rfi_plan_t* plan) {
     if (!plan || plan->patch <= 0 || plan_is_fast(plan)) return 0;
+    if (plan_is_big(plan)) return big_workspace_bytes(plan);
     return generic_workspace_bytes(plan);
 }
 
@@ -600,6 +601,7 @@ extern "C" int rfi_tile_stats(const rfi_plan_t* plan, const void* data, const ui
                               rfi_tile_stat_t* stats, void* workspace, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (plan && plan->patch > 0 && !plan_is_fast(plan)) {
+        if (plan_is_big(plan)) return big_tile_stats(plan, data, flags, stats, workspace, st);
         return generic_tile_stats(plan, data, flags, stats, workspace, st);
     }
     PlanDev d;
@@ -633,8 +635,10 @@ extern "C" int rfi_write_patches(const rfi_plan_t* plan, const void* data, const
                                  float* images, uint8_t* labels, void* workspace, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const long long* dest = reinterpret_cast<const long long*>(dest_slot);
-    if (plan && plan->patch > 0 && !plan_is_fast(plan))
+    if (plan && plan->patch > 0 && !plan_is_fast(plan)) {
+        if (plan_is_big(plan)) return big_write_patches(plan, data, flags, stats, dest, images, labels, workspace, st);
         return generic_write_patches(plan, data, flags, stats, dest, images, labels, workspace, st);
+    }
     PlanDev d;
     int rc = make_plan(plan, d);
     if (rc) return rc;

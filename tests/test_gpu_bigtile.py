@@ -1,0 +1,101 @@
+"""GPU parity of the BIG-TILE create_dataset path (csrc/rfi_bigtile.cu): P = 256 / 512 / 1024 with
+dims that are multiples of P, float32 arithmetic, real branch -- BASELINE config 5's geometry.
+The oracle is the CPU restatement of the reference; bars as in tests/test_gpu_parity.py
+(labels, patch order, statistics bit-exact; images within 1e-6 relative + 2e-5)."""
+import numpy as np
+import pytest
+import torch
+
+from tests.cubes import make_cube
+from tests.test_gpu_parity import _compare, _run_gpu, _run_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _routes(pre):
+    from rfi_toolbox_b200 import _native
+    raw = pre.last_tile_stats.cpu().numpy()
+    st = np.frombuffer(raw.tobytes(), dtype=np.dtype([
+        ("median_before", "f8"), ("inf_fill", "f8"), ("median_after", "f8"), ("centre", "f8"), ("mad", "f8"),
+        ("thr_lo", "f8"), ("thr_hi", "f8"), ("n_valid", "i4"), ("n_inf", "i4"), ("n_flagged", "i4"),
+        ("route", "i4"), ("raw_lo", "f8"), ("raw_hi", "f8")]))
+    assert st.itemsize == _native.TILE_STAT_BYTES
+    return st
+
+
+CASES = [
+    dict(stretch="SQRT", flag_sigma=5, use_custom_flags=False),
+    dict(stretch=None, flag_sigma=3, use_custom_flags=False),                     # config 5's call
+    dict(stretch="SQRT", flag_sigma=3.5, use_custom_flags=False, augmentation_rotations=2),
+    dict(stretch=None, flag_sigma=5, use_custom_flags=False, enable_augmentation=False),
+    dict(stretch="SQRT", flag_sigma=4, use_custom_flags=False, normalize_after_stretch=True),
+    dict(stretch=None, flag_sigma=5, use_custom_flags=False, normalize_before_stretch=False, num_patches=5),
+]
+
+
+@pytest.mark.parametrize("kw", CASES)
+@pytest.mark.parametrize("dtype", [np.float32, np.complex64])
+def test_p256_mad_flags_bit_exact(native_lib, kw, dtype):
+    data, _ = make_cube(n_bl=2, n_pol=2, channels=512, times=768, dtype=dtype, seed=71)
+    mag = dtype == np.complex64
+    pre, ds = _run_gpu(data, None, magnitude=mag, patch_size=256, **kw)
+    ods, inter = _run_oracle(data, None, magnitude=mag, patch_size=256, **kw)
+    _compare(ds, ods, inter, pre)
+    st = _routes(pre)
+    # the sampled brackets settle (nearly) every group: these cubes have no special values
+    assert (st["route"] & 1).mean() > 0.9
+
+
+@pytest.mark.parametrize("patch,shape", [(512, (1024, 1536)), (1024, (1024, 2048))])
+def test_p512_p1024(native_lib, patch, shape):
+    data, _ = make_cube(n_bl=1, n_pol=2, channels=shape[0], times=shape[1], dtype=np.float32, seed=73)
+    kw = dict(patch_size=patch, stretch="SQRT", flag_sigma=5, use_custom_flags=False)
+    pre, ds = _run_gpu(data, None, **kw)
+    ods, inter = _run_oracle(data, None, **kw)
+    _compare(ds, ods, inter, pre)
+    assert (_routes(pre)["route"] & 1).all()
+
+
+def test_p256_special_values_fall_back(native_lib):
+    """NaN / +inf / exact zero samples: those groups are measured by the generic select
+    (route GENERAL), the others keep the raw thresholds; results identical either way."""
+    data, _ = make_cube(n_bl=2, n_pol=2, channels=512, times=768, dtype=np.float32, seed=75, special=True)
+    kw = dict(patch_size=256, stretch="SQRT", flag_sigma=5, use_custom_flags=False)
+    pre, ds = _run_gpu(data, None, **kw)
+    ods, inter = _run_oracle(data, None, **kw)
+    _compare(ds, ods, inter, pre)
+    st = _routes(pre)
+    assert (st["route"] & 2).sum() >= 2 and (st["route"] & 1).sum() >= 1
+
+
+def test_p256_log10_zero_rows(native_lib):
+    """LOG10: the exact-zero bandpass edge rows give -inf -> MAD fill -> generic select for the
+    groups of the first / last tile row; float32 flags sit downstream of a non-reproducible log10."""
+    data, _ = make_cube(n_bl=1, n_pol=2, channels=1024, times=512, dtype=np.float32, seed=77)
+    kw = dict(patch_size=256, stretch="LOG10", flag_sigma=5, use_custom_flags=False)
+    pre, ds = _run_gpu(data, None, **kw)
+    ods, inter = _run_oracle(data, None, **kw)
+    _compare(ds, ods, inter, pre, exact_labels=False, max_label_mismatch=1e-4)
+    st = _routes(pre)
+    assert (st["route"] & 2).any() and (st["route"] & 1).any()
+
+
+@pytest.mark.parametrize("norm", [True, False])
+@pytest.mark.parametrize("rot", [1, 4])
+def test_p256_custom_flags(native_lib, norm, rot):
+    """custom flags: with normalisation (median only, no MAD pass) and without (no statistic)."""
+    data, mask = make_cube(n_bl=2, n_pol=2, channels=512, times=512, dtype=np.float32, seed=79)
+    kw = dict(patch_size=256, stretch="SQRT" if norm else None, use_custom_flags=True,
+              normalize_before_stretch=norm, augmentation_rotations=rot)
+    pre, ds = _run_gpu(data, mask, **kw)
+    ods, inter = _run_oracle(data, mask, **kw)
+    _compare(ds, ods, inter, pre)
+
+
+def test_p256_inference_mode(native_lib):
+    data, _ = make_cube(n_bl=1, n_pol=2, channels=512, times=512, dtype=np.complex64, seed=81)
+    kw = dict(patch_size=256, stretch="SQRT", inference_mode=True)
+    pre, ds = _run_gpu(data, None, magnitude=True, **kw)
+    ods, inter = _run_oracle(data, None, magnitude=True, **kw)
+    _compare(ds, ods, inter, pre)
+    assert int(ds.labels.sum()) == 0
