@@ -26,6 +26,9 @@
 //
 // Every bracket is validated exactly as in the P = 128 kernel, so results are exact either way.
 // Reference semantics: preprocessor.py:22-42, 413-446, 562-783.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include <vector>
 
 #include "rfi_tiles.cuh"
@@ -148,30 +151,50 @@ big_load_kernel(BigGeom g, const void* __restrict__ data, float* __restrict__ ma
 }
 
 // ------------------------------------------------------------------------------------------
-// group: sort the sample, median bracket
-__global__ void __launch_bounds__(1024)
+// group: sort the sample, median bracket.  Four warps each sort 512 keys in registers (bitonic
+// network over 16 keys per lane, shuffles across lanes -- no shared-memory traffic, no block
+// barriers), then every key finds its final rank by binary searches in the other three runs
+// (ties broken by run index, so the ranks are a permutation).
+__global__ void __launch_bounds__(128)
 big_sample_kernel(BigGeom g, BigGroup* __restrict__ groups, uint32_t* __restrict__ samples,
                   int* __restrict__ fail_list, int* __restrict__ fail_count) {
-    __shared__ uint32_t s[kBigS];
-    const int tid = threadIdx.x;
+    constexpr int kRun = 512, kRuns = kBigS / kRun;
+    static_assert(kRuns == 4, "one run per warp");
+    __shared__ uint32_t runs[kBigS], s[kBigS];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long grp = blockIdx.x;
     uint32_t* gs = samples + (size_t)grp * kBigS;
-    s[tid] = gs[tid];
-    s[tid + 1024] = gs[tid + 1024];
+    uint32_t v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = gs[warp * kRun + r * 32 + lane];
+    warp_sort512<uint32_t>(v, lane);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) runs[warp * kRun + r * 32 + lane] = v[r];
+    __syncthreads();
 #pragma unroll 1
-    for (int k = 2; k <= kBigS; k <<= 1) {
-#pragma unroll 1
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            __syncthreads();
-            const int idx = 2 * j * (tid / j) + (tid % j), partner = idx + j;
-            const bool up = (idx & k) == 0;
-            const uint32_t a = s[idx], b = s[partner];
-            if ((a > b) == up) { s[idx] = b; s[partner] = a; }
+    for (int r = 0; r < 16; ++r) {
+        uint32_t rank = r * 32 + lane;
+        const uint32_t x = runs[warp * kRun + rank];  // = v[r], without indexing the register array
+#pragma unroll
+        for (int o = 0; o < kRuns; ++o) {
+            if (o == warp) continue;  // warp-uniform
+            const uint32_t* run = runs + o * kRun;
+            const bool incl = o < warp;  // earlier runs win ties
+            uint32_t pos = 0;
+#pragma unroll
+            for (int step = kRun / 2; step > 0; step >>= 1) {
+                const uint32_t y = run[pos + step - 1];
+                pos += (incl ? (y <= x) : (y < x)) ? step : 0;
+            }
+            const uint32_t y = run[kRun - 1];
+            pos += (pos == kRun - 1 && (incl ? (y <= x) : (y < x))) ? 1u : 0u;
+            rank += pos;
         }
+        s[rank] = x;
     }
     __syncthreads();
-    gs[tid] = s[tid];
-    gs[tid + 1024] = s[tid + 1024];
+#pragma unroll
+    for (int k = 0; k < kBigS / 128; ++k) gs[tid + k * 128] = s[tid + k * 128];
     if (tid == 0) {
         BigGroup& G = groups[grp];
         if (G.kmax >= 0x7f800000u) {   // NaN, inf or a negative sample
@@ -190,7 +213,7 @@ big_sample_kernel(BigGeom g, BigGroup* __restrict__ groups, uint32_t* __restrict
 // ------------------------------------------------------------------------------------------
 // sub-tile pass over the raw keys: count + compact.  MODE 0: median bracket; MODE 1: MAD rings.
 template <int MODE>
-__global__ void __launch_bounds__(kBigNT, 2)
+__global__ void __launch_bounds__(kBigNT, 3)
 big_pass_kernel(BigGeom g, const float* __restrict__ src, BigGroup* __restrict__ groups,
                 uint32_t* __restrict__ cand_all) {
     constexpr int G8 = kP * kP / kBigNT / 4, RS = kBigNT / 32, W = kBigNT / 32;
@@ -201,25 +224,28 @@ big_pass_kernel(BigGeom g, const float* __restrict__ src, BigGroup* __restrict__
     uint32_t a0, span0, a1 = 0, span1 = 0;   // mine: (k - a0) <= span0 [and not (k - a1) < span1]; count: below a0 / inside (a1, span1)
     if (MODE == 0) { a0 = G->lo; span0 = G->hi - G->lo; }
     else { a0 = G->L2; span0 = G->U2 - G->L2; a1 = G->L1 + 1; span1 = G->U1 > G->L1 ? G->U1 - G->L1 - 1 : 0u; }
-    uint32_t k[G8 * 4];
-#pragma unroll
-    for (int g8 = 0; g8 < G8; ++g8) {
-        const size_t idx = t.origin + (size_t)(g8 * RS + warp) * g.p.times + lane * 4;
-        const float4 q = __ldg(reinterpret_cast<const float4*>(src + idx));
-        k[g8 * 4 + 0] = __float_as_uint(q.x); k[g8 * 4 + 1] = __float_as_uint(q.y);
-        k[g8 * 4 + 2] = __float_as_uint(q.z); k[g8 * 4 + 3] = __float_as_uint(q.w);
-    }
+    auto is_mine = [&](uint32_t k) {
+        if (MODE == 0) return (uint32_t)(k - a0) <= span0;
+        return ((uint32_t)(k - a0) <= span0) && !((uint32_t)(k - a1) < span1);
+    };
+    auto is_counted = [&](uint32_t k) {
+        if (MODE == 0) return k < a0;
+        return (uint32_t)(k - a1) < span1;
+    };
+    // sweep 1: counts only.  The keys are not kept in registers (three CTAs per SM hide the
+    // round trip of the group's cursor atomic); sweep 2 reads them again from L1 / L2.
     uint32_t cnt = 0, mine = 0;
+    const float* row0 = src + t.origin + (size_t)warp * g.p.times + lane * 4;
+    const size_t pitch = (size_t)RS * g.p.times;
+    {
+        float4 q[G8];
 #pragma unroll
-    for (int e = 0; e < G8 * 4; ++e) {
-        if (MODE == 0) {
-            cnt += (k[e] < a0) ? 1u : 0u;
-            mine += ((uint32_t)(k[e] - a0) <= span0) ? 1u : 0u;
-        } else {
-            const bool in_all = (uint32_t)(k[e] - a0) <= span0;
-            const bool interior = (uint32_t)(k[e] - a1) < span1;
-            cnt += interior ? 1u : 0u;
-            mine += (in_all && !interior) ? 1u : 0u;
+        for (int g8 = 0; g8 < G8; ++g8) q[g8] = __ldg(reinterpret_cast<const float4*>(row0 + g8 * pitch));
+#pragma unroll
+        for (int g8 = 0; g8 < G8; ++g8) {
+            const uint32_t k4[4] = {__float_as_uint(q[g8].x), __float_as_uint(q[g8].y), __float_as_uint(q[g8].z), __float_as_uint(q[g8].w)};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { cnt += is_counted(k4[i]) ? 1u : 0u; mine += is_mine(k4[i]) ? 1u : 0u; }
         }
     }
     uint32_t incl = mine;
@@ -242,13 +268,15 @@ big_pass_kernel(BigGeom g, const float* __restrict__ src, BigGroup* __restrict__
     }
     __syncthreads();
     if (base_s + total_s > g.cap) return;  // overflow: the group kernel sees cursor > cap and gives up
+    if (mine == 0) return;
     uint32_t* cand = cand_all + (size_t)t.grp * g.cap + base_s + wtot[warp] + (incl - mine);
+#pragma unroll 2
+    for (int g8 = 0; g8 < G8; ++g8) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(row0 + g8 * pitch));
+        const uint32_t k4[4] = {__float_as_uint(q.x), __float_as_uint(q.y), __float_as_uint(q.z), __float_as_uint(q.w)};
 #pragma unroll
-    for (int e = 0; e < G8 * 4; ++e) {
-        bool is;
-        if (MODE == 0) is = (uint32_t)(k[e] - a0) <= span0;
-        else is = ((uint32_t)(k[e] - a0) <= span0) && !((uint32_t)(k[e] - a1) < span1);
-        if (is) *cand++ = k[e];
+        for (int i = 0; i < 4; ++i)
+            if (is_mine(k4[i])) *cand++ = k4[i];
     }
 }
 
@@ -268,7 +296,7 @@ RFI_DEVINL void big_write_stat(rfi_tile_stat_t* out, const PlanDev& p, float m, 
     *out = st;
 }
 
-__global__ void __launch_bounds__(kBigNT)
+__global__ void __launch_bounds__(kBigNT, 3)
 big_median_kernel(BigGeom g, BigGroup* __restrict__ groups, const uint32_t* __restrict__ samples,
                   uint32_t* __restrict__ cand_all, rfi_tile_stat_t* __restrict__ stats,
                   int* __restrict__ fail_list, int* __restrict__ fail_count) {
@@ -358,7 +386,7 @@ big_median_kernel(BigGeom g, BigGroup* __restrict__ groups, const uint32_t* __re
 
 // ------------------------------------------------------------------------------------------
 // group: MAD from the candidate rings, thresholds, exact raw-domain thresholds
-__global__ void __launch_bounds__(kBigNT)
+__global__ void __launch_bounds__(kBigNT, 3)
 big_mad_kernel(BigGeom g, BigGroup* __restrict__ groups, uint32_t* __restrict__ cand_all,
                rfi_tile_stat_t* __restrict__ stats, int* __restrict__ fail_list, int* __restrict__ fail_count) {
     using T = float;
@@ -548,31 +576,14 @@ RFI_DEVINL void big_pass_a(const BigGeom& g, const BigTile& t, const BigMath& bm
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// sub-tile: flag count + min / max of L and of the squared-gradient variants -> group accumulators
-__global__ void __launch_bounds__(kBigNT, 2)
-big_range_kernel(BigGeom g, const float* __restrict__ src, const uint8_t* __restrict__ flags,
-                 rfi_tile_stat_t* __restrict__ stats, BigGroup* __restrict__ groups,
-                 const int* __restrict__ list, int count_flags) {
+// Pass B of a sub-tile: NaN-ignoring min / max of the squared gradient of the three distinct
+// rotation variants ([0] backward/backward, [1] forward rows, [2] forward columns) and of L ([3]),
+// per thread; differences reach into the halo where the neighbouring sub-tile is in the group.
+RFI_DEVINL void big_pass_b(const BigTile& t, int R, const float* Ls, const float* halo,
+                           float (&lo4)[4], float (&hi4)[4]) {
     constexpr int RS = kBigNT / 32, STEPS = kP / RS, Q = kP / 32, LP = kBigLP;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* Ls = reinterpret_cast<float*>(smem_raw);   // [kP][LP]
-    float* halo = Ls + (size_t)kP * LP;               // [4][kP]
-    float* red = halo + 4 * kP;                       // [NT / 32 * 8]
-    const long long blk = list ? (long long)list[blockIdx.x / g.n2] * g.n2 + (blockIdx.x % g.n2) : (long long)blockIdx.x;
-    const BigTile t = big_tile(g, blk);
-    if (!list && groups[t.grp].fail) return;          // measured later, after the fallback
-    const PlanDev& p = g.p;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const rfi_tile_stat_t st = stats[t.grp];
-    const BigMath bm = big_math(p, st);
-    uint32_t nf = 0;
-    if (bm.fast) big_pass_a<true, false>(g, t, bm, src, flags, Ls, halo, nullptr, nullptr, nullptr, nf);
-    else big_pass_a<false, false>(g, t, bm, src, flags, Ls, halo, nullptr, nullptr, nullptr, nf);
-    __syncthreads();
     const float* hT = halo, *hB = halo + kP, *hL = halo + 2 * kP, *hR = halo + 3 * kP;
-    const int R = p.rotations;
-    float lo4[4], hi4[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) lo4[k] = hi4[k] = Scalar<float>::nan();
 #pragma unroll 1
@@ -600,6 +611,32 @@ big_range_kernel(BigGeom g, const float* __restrict__ src, const uint8_t* __rest
             lo4[3] = fminf(lo4[3], c); hi4[3] = fmaxf(hi4[3], c);
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// sub-tile: flag count + min / max of L and of the squared-gradient variants -> group accumulators
+__global__ void __launch_bounds__(kBigNT, 2)
+big_range_kernel(BigGeom g, const float* __restrict__ src, const uint8_t* __restrict__ flags,
+                 rfi_tile_stat_t* __restrict__ stats, BigGroup* __restrict__ groups,
+                 const int* __restrict__ list, int count_flags) {
+    constexpr int LP = kBigLP;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* Ls = reinterpret_cast<float*>(smem_raw);   // [kP][LP]
+    float* halo = Ls + (size_t)kP * LP;               // [4][kP]
+    float* red = halo + 4 * kP;                       // [NT / 32 * 8]
+    const long long blk = list ? (long long)list[blockIdx.x / g.n2] * g.n2 + (blockIdx.x % g.n2) : (long long)blockIdx.x;
+    const BigTile t = big_tile(g, blk);
+    if (!list && groups[t.grp].fail) return;          // measured later, after the fallback
+    const PlanDev& p = g.p;
+    const int lane = threadIdx.x & 31;
+    const rfi_tile_stat_t st = stats[t.grp];
+    const BigMath bm = big_math(p, st);
+    uint32_t nf = 0;
+    if (bm.fast) big_pass_a<true, false>(g, t, bm, src, flags, Ls, halo, nullptr, nullptr, nullptr, nf);
+    else big_pass_a<false, false>(g, t, bm, src, flags, Ls, halo, nullptr, nullptr, nullptr, nf);
+    __syncthreads();
+    float lo4[4], hi4[4];
+    big_pass_b(t, p.rotations, Ls, halo, lo4, hi4);
     block_nanminmax4<kBigNT, float>(lo4, hi4, red);
     if (count_flags) nf = __reduce_add_sync(0xffffffffu, nf);
     if (count_flags && lane == 0 && nf) atomicAdd(reinterpret_cast<unsigned int*>(&stats[t.grp].n_flagged), nf);
@@ -615,6 +652,45 @@ big_range_kernel(BigGeom g, const float* __restrict__ src, const uint8_t* __rest
     }
 }
 
+// sub-tile: flagged samples only (the cluster writer finds the ranges itself): two compares on
+// the raw magnitude, or the caller's flag bytes.  Groups measured by the generic select were
+// counted there.
+__global__ void __launch_bounds__(kBigNT)
+big_count_kernel(BigGeom g, const float* __restrict__ src, const uint8_t* __restrict__ flags,
+                 rfi_tile_stat_t* __restrict__ stats, const BigGroup* __restrict__ groups) {
+    constexpr int G8 = kP * kP / kBigNT / 4, RS = kBigNT / 32;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const BigTile t = big_tile(g, blockIdx.x);
+    if (groups[t.grp].fail) return;
+    uint32_t nf = 0;
+    if (g.p.flag_mode == RFI_FLAGS_MAD) {
+        const float raw_lo = (float)stats[t.grp].raw_lo, raw_hi = (float)stats[t.grp].raw_hi;
+#pragma unroll
+        for (int g8 = 0; g8 < G8; ++g8) {
+            const size_t idx = t.origin + (size_t)(g8 * RS + warp) * g.p.times + lane * 4;
+            const float4 q = __ldg(reinterpret_cast<const float4*>(src + idx));
+            nf += ((q.x > raw_hi) || (q.x < raw_lo)) ? 1u : 0u;
+            nf += ((q.y > raw_hi) || (q.y < raw_lo)) ? 1u : 0u;
+            nf += ((q.z > raw_hi) || (q.z < raw_lo)) ? 1u : 0u;
+            nf += ((q.w > raw_hi) || (q.w < raw_lo)) ? 1u : 0u;
+        }
+    } else if (g.p.flag_mode == RFI_FLAGS_CUSTOM) {
+#pragma unroll
+        for (int g8 = 0; g8 < G8; ++g8) {
+            const size_t idx = t.origin + (size_t)(g8 * RS + warp) * g.p.times + lane * 4;
+            const uint32_t f4 = __ldg(reinterpret_cast<const uint32_t*>(flags + idx));
+            nf += __popc((((f4 & 0x7f7f7f7fu) + 0x7f7f7f7fu) | f4) & 0x80808080u);
+        }
+    }
+    __shared__ uint32_t tot;
+    if (tid == 0) tot = 0;
+    __syncthreads();
+    nf = __reduce_add_sync(0xffffffffu, nf);
+    if (lane == 0 && nf) atomicAdd(&tot, nf);
+    __syncthreads();
+    if (tid == 0 && tot) atomicAdd(reinterpret_cast<unsigned int*>(&stats[t.grp].n_flagged), tot);
+}
+
 RFI_DEVINL ChanScale<float> big_scale(uint32_t kmin, uint32_t kmax, bool take_sqrt) {
     float lo = (kmin == ~0u) ? Scalar<float>::nan() : from_key<float>(kmin);
     float hi = (kmax == 0u) ? Scalar<float>::nan() : from_key<float>(kmax);
@@ -624,6 +700,12 @@ RFI_DEVINL ChanScale<float> big_scale(uint32_t kmin, uint32_t kmax, bool take_sq
 
 // ------------------------------------------------------------------------------------------
 // phase 2: one CTA per sub-tile, every kept rotation written into its block of the output patch
+//
+// kCluster: the n2 CTAs of a group form one thread-block cluster; each finds the min / max of its
+// own sub-tile after pass A and the group's ranges are combined through distributed shared memory
+// (one cluster barrier pair), so no separate range launch reads the magnitudes again.  Otherwise
+// the ranges come from big_range_kernel's accumulators.
+template <bool kCluster>
 __global__ void __launch_bounds__(kBigNT, 2)
 big_write_kernel(BigGeom g, const float* __restrict__ src, const uint8_t* __restrict__ flags,
                  const rfi_tile_stat_t* __restrict__ stats, const BigGroup* __restrict__ groups,
@@ -665,11 +747,38 @@ big_write_kernel(BigGeom g, const float* __restrict__ src, const uint8_t* __rest
     else big_pass_a<false, true>(g, t, bm, src, flags, Ls, halo, FbT, lab_at(slot0, 0), lab_at(slot1, 1), nf_unused);
     __syncthreads();
 
-    const uint32_t* rng = groups[t.grp].rng;
-    const ChanScale<float> ls = big_scale(rng[0], rng[1], false);
-    const ChanScale<float> g0 = big_scale(rng[2], rng[3], true);
-    const ChanScale<float> g1 = big_scale(rng[4], rng[5], true);
-    const ChanScale<float> g3 = big_scale(rng[6], rng[7], true);
+    ChanScale<float> ls, g0, g1, g3;
+    if constexpr (kCluster) {
+        namespace cg = cooperative_groups;
+        cg::cluster_group cluster = cg::this_cluster();
+        __shared__ float xch[8];   // this CTA's (lo, hi) x 4, read by every CTA of the cluster
+        float lo4[4], hi4[4];
+        big_pass_b(t, R, Ls, halo, lo4, hi4);
+        block_nanminmax4<NT, float>(lo4, hi4, stage);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { xch[k] = lo4[k]; xch[4 + k] = hi4[k]; }
+        }
+        cluster.sync();
+        const unsigned nc = cluster.num_blocks();
+        for (unsigned r = 0; r < nc; ++r) {
+            if (r == cluster.block_rank()) continue;
+            const float* peer = cluster.map_shared_rank(xch, r);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { lo4[k] = fminf(lo4[k], peer[k]); hi4[k] = fmaxf(hi4[k], peer[4 + k]); }
+        }
+        cluster.sync();            // no CTA leaves (or reuses xch) while a peer still reads it
+        g0 = make_scale<float>(sqrt_fast(lo4[0]), sqrt_fast(hi4[0]));
+        g1 = make_scale<float>(sqrt_fast(lo4[1]), sqrt_fast(hi4[1]));
+        g3 = make_scale<float>(sqrt_fast(lo4[2]), sqrt_fast(hi4[2]));
+        ls = make_scale<float>(lo4[3], hi4[3]);
+    } else {
+        const uint32_t* rng = groups[t.grp].rng;
+        ls = big_scale(rng[0], rng[1], false);
+        g0 = big_scale(rng[2], rng[3], true);
+        g1 = big_scale(rng[4], rng[5], true);
+        g3 = big_scale(rng[6], rng[7], true);
+    }
 
     const float mean0 = 0.485f, mean1 = 0.456f, mean2 = 0.406f;
     const float std0 = 0.229f, std1 = 0.224f, std2 = 0.225f;
@@ -807,6 +916,13 @@ size_t big_workspace_bytes(const rfi_plan_t* plan) {
     return big_ws(plan, g, nullptr).bytes;
 }
 
+// P = 256: the four sub-tile CTAs of a group run as one cluster (RFI_BIG_NO_CLUSTER=1 keeps the
+// range launch instead -- for A/B timing)
+static bool big_use_cluster(const BigGeom& g) {
+    static const bool off = getenv("RFI_BIG_NO_CLUSTER") != nullptr;
+    return g.n2 == 4 && !off;
+}
+
 static size_t big_range_smem() { return ((size_t)kP * kBigLP + 4 * kP + kBigNT / 32 * 8) * sizeof(float); }
 static size_t big_write_smem() {
     return ((size_t)kP * kBigLP + 4 * kP) * sizeof(float) + (size_t)kP * kBigFP + (size_t)(kBigNT / 32) * 3 * kP * sizeof(float);
@@ -825,13 +941,14 @@ int big_tile_stats(const rfi_plan_t* plan, const void* data, const uint8_t* flag
     const bool need_median = g.p.norm_before || g.p.norm_after || g.p.flag_mode == RFI_FLAGS_MAD;
     const float* src = cplx ? w.mag : static_cast<const float*>(data);
     const unsigned subs = (unsigned)(g.n_groups * g.n2), groups = (unsigned)g.n_groups;
+    const bool cluster = big_use_cluster(g);
 
     big_init_kernel<<<(groups + 255) / 256, 256, 0, st>>>(g, w.groups, w.fail_count);
     if (cplx) big_load_kernel<RFI_C64><<<subs, kBigNT, 0, st>>>(g, data, w.mag, w.groups, w.samples, need_median ? 1 : 0);
     else if (need_median) big_load_kernel<RFI_F32><<<subs, kBigNT, 0, st>>>(g, data, w.mag, w.groups, w.samples, 1);
     int n_fail = 0;
     if (need_median) {
-        big_sample_kernel<<<groups, 1024, 0, st>>>(g, w.groups, w.samples, w.fail_list, w.fail_count);
+        big_sample_kernel<<<groups, 128, 0, st>>>(g, w.groups, w.samples, w.fail_list, w.fail_count);
         big_pass_kernel<0><<<subs, kBigNT, 0, st>>>(g, src, w.groups, w.cand);
         big_median_kernel<<<groups, kBigNT, 0, st>>>(g, w.groups, w.samples, w.cand, stats, w.fail_list, w.fail_count);
         if (g.p.flag_mode == RFI_FLAGS_MAD) {
@@ -861,13 +978,16 @@ int big_tile_stats(const rfi_plan_t* plan, const void* data, const uint8_t* flag
         }
         int rc = generic_tile_stats_subset(plan, data, flags, stats, w.generic, w.fail_list, n_fail, st);
         if (rc) return rc;
-        big_rearm_kernel<<<(n_fail + 255) / 256, 256, 0, st>>>(w.groups, w.fail_list, n_fail);
-        // ranges of the listed groups (their flag counts come from the generic path)
-        big_range_kernel<<<(unsigned)n_fail * g.n2, kBigNT, big_range_smem(), st>>>(g, src, flags, stats, w.groups, w.fail_list, 0);
+        if (!cluster) {
+            big_rearm_kernel<<<(n_fail + 255) / 256, 256, 0, st>>>(w.groups, w.fail_list, n_fail);
+            // ranges of the listed groups (their flag counts come from the generic path)
+            big_range_kernel<<<(unsigned)n_fail * g.n2, kBigNT, big_range_smem(), st>>>(g, src, flags, stats, w.groups, w.fail_list, 0);
+        }
     }
     if (need_median) {
         const int count = g.p.flag_mode != RFI_FLAGS_INFERENCE ? 1 : 0;
-        big_range_kernel<<<subs, kBigNT, big_range_smem(), st>>>(g, src, flags, stats, w.groups, nullptr, count);
+        if (!cluster) big_range_kernel<<<subs, kBigNT, big_range_smem(), st>>>(g, src, flags, stats, w.groups, nullptr, count);
+        else if (count) big_count_kernel<<<subs, kBigNT, 0, st>>>(g, src, flags, stats, w.groups);
     }
     RFI_CUDA_TRY(cudaGetLastError());
     return RFI_OK;
@@ -884,9 +1004,23 @@ int big_write_patches(const rfi_plan_t* plan, const void* data, const uint8_t* f
     if (g.p.flag_mode == RFI_FLAGS_CUSTOM && !flags) { set_error("custom flag mode needs flags"); return RFI_E_INVALID; }
     const BigWs w = big_ws(plan, g, workspace);
     const float* src = plan->dtype == RFI_C64 ? w.mag : static_cast<const float*>(data);
-    RFI_CUDA_TRY(cudaFuncSetAttribute(big_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_write_smem()));
-    big_write_kernel<<<(unsigned)(g.n_groups * g.n2), kBigNT, big_write_smem(), st>>>(
-        g, src, flags, stats, w.groups, dest_slot, images, labels);
+    const unsigned subs = (unsigned)(g.n_groups * g.n2);
+    if (big_use_cluster(g)) {
+        auto kern = big_write_kernel<true>;
+        RFI_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_write_smem()));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(subs); cfg.blockDim = dim3(kBigNT); cfg.dynamicSmemBytes = big_write_smem(); cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)g.n2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        const BigGroup* groups = w.groups;
+        RFI_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, g, src, flags, stats, groups, dest_slot, images, labels));
+    } else {
+        auto kern = big_write_kernel<false>;
+        RFI_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_write_smem()));
+        kern<<<subs, kBigNT, big_write_smem(), st>>>(g, src, flags, stats, w.groups, dest_slot, images, labels);
+    }
     RFI_CUDA_TRY(cudaGetLastError());
     return RFI_OK;
 }
