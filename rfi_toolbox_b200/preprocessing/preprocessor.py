@@ -26,7 +26,7 @@ import torch
 
 from .. import _native
 from ..datasets.batched_dataset import TorchDataset
-from ..utils.device import as_device_tensor, current_stream_ptr, require_cuda
+from ..utils.device import as_device_tensor, as_host_tensor, copy_stream, current_stream_ptr, require_cuda
 
 logger = logging.getLogger(__name__)
 
@@ -111,6 +111,9 @@ def _host_buffers(device, n_groups, n_patches):
 class Preprocessor:
     """Preprocess waterfall data into training patches (preprocessor.py:139-196)."""
 
+    #: host (pinned) input is uploaded in this many baseline chunks, overlapped with phase 1
+    upload_chunks = 8
+
     #: when True, CUDA events bracket the two kernels of every call (read by bench.py):
     #: `self.events = {"stats": (start, stop), "write": (start, stop)}` on the current stream.
     profile = False
@@ -167,7 +170,10 @@ class Preprocessor:
         if stretch and stretch not in ("SQRT", "LOG10"):
             raise ValueError(f"Invalid stretch '{stretch}'. Use 'SQRT' or 'LOG10'")
 
-        data = as_device_tensor(self.data, device, pin=self._pin)
+        # host input: uploaded below in baseline chunks on a side stream, each chunk's statistics
+        # kernel starting as soon as its chunk has landed (fast path); else one plain H2D copy
+        host = as_host_tensor(self.data, pin=self._pin)
+        data = host if host is not None else as_device_tensor(self.data, device, pin=self._pin)
         if data.dtype not in _DTYPE_CODE:
             raise TypeError(f"unsupported data dtype {data.dtype}: float32/64 or complex64/128")
         B, npol, C_, T_ = data.shape
@@ -244,8 +250,36 @@ class Preprocessor:
                 ev[0].record()
             work = torch.empty(ws_bytes, dtype=torch.uint8, device=device) if ws_bytes else None
             wptr = work.data_ptr() if work is not None else None
-            rc = lib.rfi_tile_stats(C.byref(plan), data.data_ptr(), fptr, stats.data_ptr(), wptr, stream)
-            _native.check(rc, "rfi_tile_stats")
+            pipelined = (host is not None and host.is_pinned() and ws_bytes == 0 and not skip_patchify
+                         and B > 1 and n_tiles > 0)
+            if host is not None and not pipelined:
+                data = host.to(device, non_blocking=True)
+            if pipelined:
+                # waterfalls are independent in phase 1: chunk c's kernel only waits for chunk c's copy
+                data = torch.empty(host.shape, dtype=host.dtype, device=device)
+                main, side = torch.cuda.current_stream(device), copy_stream(device)
+                side.wait_stream(main)  # the fresh buffer may still be in use by work queued on `main`
+                bounds = np.linspace(0, B, min(B, self.upload_chunks) + 1).astype(np.int64)
+                per_bl_tiles = n_tiles // B
+                for b0, b1 in zip(bounds[:-1], bounds[1:]):
+                    b0, b1 = int(b0), int(b1)
+                    with torch.cuda.stream(side):
+                        data[b0:b1].copy_(host[b0:b1], non_blocking=True)
+                        landed = torch.cuda.Event()
+                        landed.record(side)
+                    main.wait_event(landed)
+                    sub = _native.RfiPlan.from_buffer_copy(plan)
+                    sub.n_waterfalls = (b1 - b0) * npol
+                    off = b0 * npol * C_ * T_
+                    rc = lib.rfi_tile_stats(C.byref(sub), data.data_ptr() + off * data.element_size(),
+                                            fptr + off if fptr is not None else None,
+                                            stats.data_ptr() + b0 * per_bl_tiles * _native.TILE_STAT_BYTES,
+                                            None, stream)
+                    _native.check(rc, "rfi_tile_stats")
+                data.record_stream(side)
+            else:
+                rc = lib.rfi_tile_stats(C.byref(plan), data.data_ptr(), fptr, stats.data_ptr(), wptr, stream)
+                _native.check(rc, "rfi_tile_stats")
             if ev:
                 ev[1].record()
             self.last_tile_stats = stats
@@ -262,9 +296,6 @@ class Preprocessor:
                 hb["event"].synchronize()
                 nflag = hb["nflag_np"][:n_tiles]
             n_out = _native.plan_slots(plan, nflag, not inference_mode, num_patches, hb["order_np"], hb["dest_np"])
-            if not inference_mode and nflag is not None and not (nflag > 0).any():
-                logger.warning("No flagged patches found - keeping all patches")
-            order = hb["order_np"][:n_out].copy()
             dest_dev = torch.empty(max(n0, 1), dtype=torch.int64, device=device)
             dest_dev.copy_(hb["dest"][:max(n0, 1)], non_blocking=True)
             hb["copied"].record()
@@ -281,6 +312,10 @@ class Preprocessor:
             if ev:
                 ev[3].record()
                 self.events = {"stats": (ev[0], ev[1]), "write": (ev[2], ev[3])}
+            # host bookkeeping after the launch: the GPU idles between the phases, not here
+            if not inference_mode and nflag is not None and not (nflag > 0).any():
+                logger.warning("No flagged patches found - keeping all patches")
+            order = hb["order_np"][:n_out].copy()
 
         self.order = order  # canonical index of every output patch (not in the reference)
         self.patch_flags = labels

@@ -42,3 +42,33 @@ def as_device_tensor(x, device: torch.device, pin: bool = False) -> torch.Tensor
             t = t.pin_memory()
         t = t.to(device, non_blocking=True)
     return t.contiguous()
+
+
+def as_host_tensor(x, pin: bool = False):
+    """Host array / CPU tensor -> contiguous CPU tensor (pinned when it already is, or when `pin`);
+    None for anything already on a device.  Used by the chunked, overlapped upload."""
+    if isinstance(x, torch.Tensor):
+        if x.device.type != "cpu":
+            return None
+        t = x.detach().contiguous()
+    else:
+        a = np.asarray(x)
+        if not a.flags.c_contiguous:
+            a = np.ascontiguousarray(a)
+        if not a.flags.writeable:
+            a = a.copy()
+        t = torch.from_numpy(a)
+    if pin and not t.is_pinned():
+        t = t.pin_memory()
+    return t
+
+
+_COPY_STREAMS = {}
+
+
+def copy_stream(device: torch.device) -> torch.cuda.Stream:
+    """One side stream per device for host->device uploads that overlap with kernels."""
+    s = _COPY_STREAMS.get(device.index)
+    if s is None:
+        s = _COPY_STREAMS[device.index] = torch.cuda.Stream(device=device)
+    return s

@@ -195,3 +195,29 @@ def test_golden_fixture(native_lib, name):
         assert ffi[k] == pytest.approx(v, rel=1e-6, abs=1e-9, nan_ok=True)
     for k, v in c["stats"].items():
         assert float(st[k]) == pytest.approx(v, rel=1e-6, nan_ok=True)
+
+
+@pytest.mark.parametrize("chunks", [1, 3, 8])
+def test_pinned_host_input_chunked_upload(native_lib, chunks):
+    """Host (pinned) input is uploaded in baseline chunks on a side stream, each chunk's statistics
+    kernel waiting only for its own copy; results must not depend on the chunking."""
+    from rfi_toolbox_b200 import Preprocessor
+    data, mask = make_cube(n_bl=5, n_pol=2, dtype=np.complex64, seed=17)
+    kw = dict(stretch="SQRT", flag_sigma=5, use_custom_flags=False)
+    ods, inter = _run_oracle(data, None, magnitude=True, **kw)
+    for src in (torch.from_numpy(data).pin_memory(), data):
+        np.random.seed(11)
+        pre = Preprocessor(src, None, magnitude=True, pin=True)
+        pre.upload_chunks = chunks
+        ds = pre.create_dataset(**kw)
+        torch.cuda.synchronize()
+        _compare(ds, ods, inter, pre)
+    # custom flags travel with their chunk
+    kw = dict(stretch=None, use_custom_flags=True, normalize_before_stretch=False)
+    ods, inter = _run_oracle(data, mask, **kw)
+    np.random.seed(11)
+    pre = Preprocessor(torch.from_numpy(data).pin_memory(), mask, pin=True)
+    pre.upload_chunks = chunks
+    ds = pre.create_dataset(**kw)
+    torch.cuda.synchronize()
+    _compare(ds, ods, inter, pre)
