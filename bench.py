@@ -186,7 +186,9 @@ def run_ours(args):
     w = dict(WORKLOADS[args.workload])
     if args.baselines:
         w["n_bl"] = args.baselines
-    cube, mask = device_cube(w["n_bl"], w["n_pol"], w["channels"], w["times"], seed=1234 + rank, device=dev)
+    # Philox seed 1234, one subsequence per baseline of the sharded cube
+    cube, mask = device_cube(w["n_bl"], w["n_pol"], w["channels"], w["times"], seed=1234, device=dev,
+                             first_baseline=rank * w["n_bl"])
     npix = cube.numel()
     kw = dict(patch_size=w["patch"], stretch=w["stretch"], flag_sigma=w["sigma"], use_custom_flags=False,
               augmentation_rotations=w["rot"])
@@ -290,8 +292,9 @@ def run_ours(args):
     # (profiles/traffic.json, written by scripts/ncu_summary.py); null for any other workload
     traffic = None
     tj = ROOT / "profiles" / "traffic.json"
-    if tj.exists() and not args.baselines and args.workload == "c2":
-        traffic = json.loads(tj.read_text()).get("write_patches_kernel", {}).get("dram_bytes_per_launch")
+    if tj.exists() and not args.baselines and args.workload in ("c2", "c5"):
+        kname = "write_patches_kernel" if args.workload == "c2" else "big_write_kernel"
+        traffic = json.loads(tj.read_text()).get(kname, {}).get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "kernel": "write_patches_kernel" if w["patch"] == 128 else "big_write_kernel",
                 "achieved": achieved, "peak": peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -9,7 +9,9 @@
  *
  * Conventions
  *   - plain C: device pointers, sizes, a cudaStream_t passed as void*; no torch types;
- *   - no allocation inside (one exception: none), no host synchronisation, re-entrant per stream;
+ *   - no allocation inside, re-entrant per stream; no host synchronisation, with one exception:
+ *     rfi_tile_stats for P = 256 / 512 / 1024 reads one int back (how many groups need the
+ *     generic select) before it returns;
  *   - every call returns 0 on success or a negative RFI_E_* code; rfi_last_error_string()
  *     gives the text for the calling thread's last failure;
  *   - all device buffers are owned by the caller.
@@ -24,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RFI_B200_ABI_VERSION 4
+#define RFI_B200_ABI_VERSION 5
 
 /* status codes */
 #define RFI_OK 0
@@ -200,6 +202,38 @@ int rfi_legacy_permutation(uint32_t* mt_key, int32_t* mt_pos, int64_t n, int64_t
 int rfi_plan_slots(const rfi_plan_t* plan, const int32_t* n_flagged, int64_t stride_bytes, int shuffle,
                    uint32_t* mt_key, int32_t* mt_pos, int64_t num_patches, int64_t* order,
                    int64_t* dest, int64_t* n_out);
+
+/* Device-side synthetic visibilities -- the step BEFORE the hot path: replaces the per-pixel work of
+ * SyntheticDataGenerator._generate_single_sample / _generate_bandpass
+ * (data_generation/synthetic_generator.py:520-656, 657-673).  Distribution parity only (the
+ * reference's host MT19937 stream cannot be reproduced on a device): every pixel owns a
+ * Philox4x32-10 counter (key = seed; counter = pixel, first_baseline + b, stream), so the cube is a
+ * pure function of (seed, baseline index, shape) however the baselines are sharded over GPUs.
+ * The RFI events of a baseline (drawn on the host as the reference's _add_* do, :675-815) arrive in
+ * separable form -- all of them are rows x times rectangles or sweeps. */
+typedef struct rfi_synth {
+    int64_t channels, times;
+    int32_t n_pol;           /* pol 0 full RFI, pol 1 pol_corr x RFI, pols >= 2 noise only (:616-636) */
+    int32_t enable_bandpass; /* polynomial roll-off over 10 % of the channels at each edge (:657-673) */
+    int32_t bandpass_order;
+    int32_t n_bands;         /* narrow bands with a time profile per baseline (<= 64) */
+    int32_t n_sweeps;        /* frequency sweeps per baseline */
+    float noise_level;       /* clean amplitude ~ N(noise_level, 0.1 noise_level) (:549) */
+    float pol_corr;
+    uint64_t seed;
+} rfi_synth_t;
+
+/*   row_amp   device float32 [n_baselines][C]          summed amplitude of the full-row events
+ *   col_amp   device float32 [n_baselines][T]          summed amplitude of the full-column events
+ *   band_rows device int32   [n_baselines][n_bands][2] row range [r0, r1) of band k
+ *   band_amp  device float32 [n_baselines][n_bands][T] amplitude of band k at time t (0 = off)
+ *   sweep     device float32 [n_baselines][n_sweeps][6] start row, end row, width, order (1|2), amplitude, 0
+ *   cube      device complex64 [n_baselines][n_pol][C][T], written
+ *   mask      device uint8     same shape, written (exact RFI locations, pols 0 and 1) */
+int rfi_synth_waterfalls(const rfi_synth_t* sp, int64_t n_baselines, int64_t first_baseline,
+                         const float* row_amp, const float* col_amp, const int32_t* band_rows,
+                         const float* band_amp, const float* sweep, void* cube, uint8_t* mask,
+                         void* stream);
 
 /* Self test (used by tests/): counts the inputs t in [1, 2] (all 2^23 + 1 float32 values) for
  * which the range-restricted square root of the magnitude kernel differs from sqrt.rn.f32.

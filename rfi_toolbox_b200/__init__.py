@@ -9,7 +9,7 @@ No CPU fallback, no Triton, no multi-backend dispatch.
 
 __version__ = "0.1.0"
 
-from . import datasets, evaluation, preprocessing  # noqa: F401,E402
+from . import data_generation, datasets, evaluation, preprocessing  # noqa: F401,E402
 from .datasets import TorchDataset  # noqa: F401,E402
 from .evaluation import (  # noqa: F401,E402
     compute_dice,
@@ -24,4 +24,5 @@ from .evaluation import (  # noqa: F401,E402
     evaluate_segmentation,
     evaluate_segmentation_batch,
 )
-from .preprocessing import Preprocessor  # noqa: F401,E402
+from .data_generation import SyntheticDataGenerator  # noqa: F401,E402
+from .preprocessing import Preprocessor, iter_dataset_chunks  # noqa: F401,E402

@@ -15,7 +15,7 @@ RFI_F32, RFI_F64, RFI_C64, RFI_C128 = 0, 1, 2, 3
 RFI_STRETCH_NONE, RFI_STRETCH_SQRT, RFI_STRETCH_LOG10 = 0, 1, 2
 RFI_FLAGS_CUSTOM, RFI_FLAGS_MAD, RFI_FLAGS_INFERENCE = 0, 1, 2
 RFI_E_INVALID, RFI_E_UNSUPPORTED, RFI_E_CUDA = -1, -2, -3
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class RfiPlan(C.Structure):
@@ -44,6 +44,14 @@ class RfiStats(C.Structure):
     ]
 
 
+class RfiSynth(C.Structure):
+    _fields_ = [
+        ("channels", C.c_int64), ("times", C.c_int64), ("n_pol", C.c_int32), ("enable_bandpass", C.c_int32),
+        ("bandpass_order", C.c_int32), ("n_bands", C.c_int32), ("n_sweeps", C.c_int32),
+        ("noise_level", C.c_float), ("pol_corr", C.c_float), ("seed", C.c_uint64),
+    ]
+
+
 TILE_STAT_BYTES = C.sizeof(RfiTileStat)
 assert TILE_STAT_BYTES == 88
 
@@ -63,6 +71,7 @@ SYMBOLS = {
     "rfi_legacy_permutation": (_I, [_VP, C.POINTER(C.c_int32), _I64, _VP]),
     "rfi_plan_slots": (_I, [C.POINTER(RfiPlan), _VP, _I64, _I, _VP, C.POINTER(C.c_int32), _I64, _VP, _VP,
                             C.POINTER(C.c_int64)]),
+    "rfi_synth_waterfalls": (_I, [C.POINTER(RfiSynth), _I64, _I64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "rfi_selftest_sqrt_unit": (_I, [_VP, _VP]),
     "rfi_last_error_string": (C.c_char_p, []),
     "rfi_abi_version": (_I, []),

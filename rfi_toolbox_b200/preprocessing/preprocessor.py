@@ -332,3 +332,29 @@ class Preprocessor:
         self.dataset = TorchDataset(images, labels, metadata)
         logger.info("Dataset ready: %d samples", len(self.dataset))
         return self.dataset
+
+
+def iter_dataset_chunks(data, flags=None, *, chunk_baselines, magnitude=False, device=None, pin=True,
+                        **create_kw):
+    """Stream a cube whose output does not fit in HBM at once (BASELINE config 5: 44 baselines x 4
+    pols x 1024 x 16384 per GPU give 153 GB of patches) through `create_dataset` in contiguous
+    baseline chunks.  Yields `(b0, b1, dataset)`; release `dataset` (or hand it to `BatchWriter`)
+    before taking the next chunk and the caching allocator reuses the same output blocks -- the
+    "output ring" of SURVEY.md section 8d.
+
+    Every chunk is one `Preprocessor` over `data[b0:b1]` -- the reference's own unit of
+    parallelism (one Preprocessor per sample per worker, synthetic_generator.py:55-107) and the
+    same semantics as the per-rank baseline shards (`utils.sharding.baseline_shard`): blank-patch
+    removal and the shuffle are per chunk, and each chunk draws one `np.random.permutation` from
+    the global legacy generator, in chunk order.  Host input is uploaded chunk by chunk (pinned,
+    overlapped with phase 1), so the full cube never has to be resident either."""
+    n_bl = data.shape[0] if data.ndim == 4 else 1
+    if data.ndim == 3:
+        data = data[None, ...]
+    if chunk_baselines < 1:
+        raise ValueError("chunk_baselines must be >= 1")
+    for b0 in range(0, n_bl, int(chunk_baselines)):
+        b1 = min(n_bl, b0 + int(chunk_baselines))
+        pre = Preprocessor(data[b0:b1], None if flags is None else flags[b0:b1],
+                           magnitude=magnitude, device=device, pin=pin)
+        yield b0, b1, pre.create_dataset(**create_kw)

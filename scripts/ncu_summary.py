@@ -58,7 +58,7 @@ def main():
                 wr = float(d["dram__bytes_write.sum"]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[u["dram__bytes_write.sum"]]
                 t = float(d["gpu__time_duration.sum"]) * {"ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1}[u["gpu__time_duration.sum"]]
                 lines.append("")
-                kname = d.get("Kernel Name", "?").split("<")[0].replace("void ", "").strip()
+                kname = d.get("Kernel Name", "?").split("<")[0].split("(")[0].replace("void ", "").strip()
                 traffic[kname] = {"dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
                                   "duration_ms_under_ncu": t * 1e3, "report": rep.split("/")[-1]}
                 lines.append(f"DRAM traffic {rd + wr:.4g} B (read {rd:.4g}, write {wr:.4g}) in {t * 1e3:.3f} ms = "

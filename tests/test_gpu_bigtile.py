@@ -99,3 +99,21 @@ def test_p256_inference_mode(native_lib):
     ods, inter = _run_oracle(data, None, magnitude=True, **kw)
     _compare(ds, ods, inter, pre)
     assert int(ds.labels.sum()) == 0
+
+
+def test_chunked_stream_matches_per_chunk_oracle(native_lib):
+    """iter_dataset_chunks: each baseline chunk is one Preprocessor (own blank removal, own
+    shuffle drawn in chunk order from the global generator) -- config 5's streaming mode."""
+    import oracle
+    from rfi_toolbox_b200.preprocessing import iter_dataset_chunks
+    data, _ = make_cube(n_bl=3, n_pol=2, channels=256, times=512, dtype=np.float32, seed=91)
+    kw = dict(patch_size=256, stretch=None, flag_sigma=3, use_custom_flags=False)
+    np.random.seed(5)
+    got = [(b0, b1, ds.images.cpu().numpy(), ds.labels.cpu().numpy())
+           for b0, b1, ds in iter_dataset_chunks(data, chunk_baselines=2, **kw)]
+    assert [(g[0], g[1]) for g in got] == [(0, 2), (2, 3)]
+    np.random.seed(5)
+    for b0, b1, imgs, labs in got:
+        ods = oracle.create_dataset(data[b0:b1], None, **kw)
+        assert np.array_equal(labs, ods.labels)
+        assert np.allclose(imgs, ods.images, rtol=1e-6, atol=2e-5, equal_nan=True)
