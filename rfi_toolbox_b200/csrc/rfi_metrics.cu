@@ -83,7 +83,29 @@ RFI_DEVINL void count_range(const void* pred, const void* truth, long long begin
     const uint4* vt = reinterpret_cast<const uint4*>(at + (uintptr_t)head * ET);
     constexpr int LP = V / VP, LT = V / VT;  // 128-bit loads per step for each operand
     unsigned iter = 0;
-    for (long long s = tid; s < body; s += nthreads) {
+    long long s0 = tid;
+    if constexpr (EP == 1 && ET == 1) {
+        // byte masks (the common case): four 128-bit loads per operand in flight per thread, and the
+        // counts taken byte-parallel -- high bit of every non-zero byte, three popcounts per word
+        constexpr int U = 4;
+        auto hb = [](uint32_t v) { return (((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u; };
+        for (; s0 + (U - 1) * nthreads < body; s0 += U * nthreads) {
+            uint4 a[U], b[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) { a[k] = __ldg(vp + s0 + k * nthreads); b[k] = __ldg(vt + s0 + k * nthreads); }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const uint32_t pw[4] = {a[k].x, a[k].y, a[k].z, a[k].w}, tw[4] = {b[k].x, b[k].y, b[k].z, b[k].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t p = hb(pw[i]), t = hb(tw[i]);
+                    tpc += __popc(p & t); fpc += __popc(p & ~t); fnc += __popc(~p & t);
+                }
+            }
+            if ((++iter & 1023) == 0) { tp += tpc; fp += fpc; fn += fnc; tpc = fpc = fnc = 0; }
+        }
+    }
+    for (long long s = s0; s < body; s += nthreads) {
         uint32_t mp = 0, mt = 0;
 #pragma unroll
         for (int k = 0; k < LP; ++k) mp |= nz_mask16<EP, FP>(__ldg(vp + s * LP + k)) << (k * VP);
