@@ -180,6 +180,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     group = True if world > 1 else None
 
@@ -314,7 +315,8 @@ def run_ours(args):
                    "pixels_per_step_per_gpu": npix, "patches_kept": n_kept,
                    "l2": f"input cube {cube.numel() * 8 / 1e9:.1f} GB and {n_kept * w['patch'] ** 2 * 13 / 1e9:.1f} GB of output "
                          "per step exceed the 126 MB L2; no flush needed",
-                   "parallelism": f"baseline-sharded x{world}, NCCL all-reduce of TP/FP/FN" if world > 1 else "single GPU"},
+                   "parallelism": (f"baseline-sharded x{world}; TP/FP/FN summed inside the counting kernel over NVLink peer "
+                                   "memory (NCCL only for rendezvous / barriers)") if world > 1 else "single GPU"},
         "e2e": {"value": e2e_value, "unit": "Gpixel/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "note": "pinned host cube copied H2D every step; dataset stays in HBM, metric dict read back"},
         # per step: tile_stats_mono_kernel, write_patches_kernel, confusion_kernel

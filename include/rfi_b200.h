@@ -144,6 +144,29 @@ int rfi_confusion_counts(const void* pred, int elem_pred, int is_float_pred,
                          const void* truth, int elem_true, int is_float_true,
                          int64_t n, unsigned long long* counts, void* stream);
 
+/* Confusion counts SUMMED OVER THE RANKS of one box in the same kernel (masks sharded by baseline,
+ * SURVEY.md section 8e) -- replaces rfi_confusion_counts + an NCCL all-reduce.  Every rank calls it
+ * with the same `epoch` (1, 2, 3 ... per call); the last CTA of the reduction stores the rank's
+ * totals into every peer's exchange buffer over NVLink, publishes the epoch behind a system fence,
+ * waits for every peer's epoch in its own buffer and writes the sums.
+ *   peers   host array of `world` (<= 16) device pointers: the exchange buffers of all ranks
+ *           (own: rfi_peer_alloc; others: rfi_peer_open of the handle that rank exported)
+ *   counts  device uint64[4], WRITTEN: {TP, FP, FN} over all ranks, [3] != 0 if a peer never
+ *           arrived (the wait gives up after ~30 s instead of hanging the GPU) */
+int rfi_confusion_counts_allreduce(const void* pred, int elem_pred, int is_float_pred,
+                                   const void* truth, int elem_true, int is_float_true, int64_t n,
+                                   void* const* peers, int world, int rank, uint64_t epoch,
+                                   unsigned long long* counts, void* stream);
+
+/* Exchange buffers (RFI_PEER_BYTES used; allocated by the library so that the 64-byte CUDA IPC
+ * handle maps exactly this buffer).  Handles travel between the ranks by any host channel
+ * (torch.distributed.all_gather_object in the Python layer). */
+#define RFI_PEER_BYTES 4096
+int rfi_peer_alloc(void** buf, unsigned char* handle64);
+int rfi_peer_open(const unsigned char* handle64, void** peer);
+int rfi_peer_close(void* peer);
+int rfi_peer_free(void* buf);
+
 /* Same, one triple per consecutive segment of `seg` elements (per-pair sweep,
  * BASELINE config 4).  counts device uint64[n_seg][3], written. */
 int rfi_confusion_counts_segmented(const void* pred, int elem_pred, int is_float_pred,

@@ -64,6 +64,11 @@ SYMBOLS = {
     "rfi_tile_stats": (_I, [C.POINTER(RfiPlan), _VP, _VP, _VP, _VP, _VP]),
     "rfi_write_patches": (_I, [C.POINTER(RfiPlan), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "rfi_confusion_counts": (_I, [_VP, _I, _I, _VP, _I, _I, _I64, _VP, _VP]),
+    "rfi_confusion_counts_allreduce": (_I, [_VP, _I, _I, _VP, _I, _I, _I64, _VP, _I, _I, C.c_uint64, _VP, _VP]),
+    "rfi_peer_alloc": (_I, [C.POINTER(C.c_void_p), _VP]),
+    "rfi_peer_open": (_I, [_VP, C.POINTER(C.c_void_p)]),
+    "rfi_peer_close": (_I, [_VP]),
+    "rfi_peer_free": (_I, [_VP]),
     "rfi_confusion_counts_segmented": (_I, [_VP, _I, _I, _VP, _I, _I, _I64, _I64, _VP, _VP]),
     "rfi_statistics_workspace_bytes": (C.c_size_t, []),
     "rfi_statistics": (_I, [_VP, _I, _VP, _I64, _VP, _VP, _VP]),

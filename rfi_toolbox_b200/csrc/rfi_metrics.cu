@@ -4,6 +4,8 @@
 // rfi_toolbox/evaluation/metrics.py:25-172 with one streaming pass: 128-bit loads of both
 // masks, per-thread popcounts, warp-shuffle + block reduction, one 64-bit atomic per CTA.
 // The five ratios are formed on the host in float64 exactly as the reference does.
+#include <string.h>
+
 #include "rfi_common.cuh"
 
 namespace rfi {
@@ -142,18 +144,93 @@ RFI_DEVINL void block_sum3(unsigned long long& a, unsigned long long& b, unsigne
 
 constexpr int kMetricThreads = 256;
 
+// ---- counts + all-reduce in ONE kernel, over NVLink peer memory -----------------------------
+// evaluate_segmentation over a baseline-sharded cube needs the SUM of {TP, FP, FN} over the
+// ranks: a reduction followed by a collective.  Every rank owns one small
+// exchange buffer (cudaMalloc + CUDA IPC, opened by all ranks of the box); the last CTA of the
+// reduction stores the rank's three totals into slot [rank] of EVERY peer's buffer (plain stores
+// over NVLink), publishes the call's epoch in the peer's flag word behind a system fence, waits
+// for the same epoch from every peer in its OWN buffer and writes the sums -- no NCCL launch, no
+// extra stream hop, one kernel on the caller's stream.  Slots and flags are double-buffered by
+// epoch parity: a rank can only be one call ahead of a peer that still has to read its slots.
+constexpr int kPeerMax = 16;
+struct PeerBuf {
+    unsigned long long partial[2][4];          // this rank's CTAs accumulate here
+    unsigned int ticket[2], pad[2];
+    unsigned long long slots[2][kPeerMax][4];  // [parity][source rank] = {TP, FP, FN, -}
+    unsigned long long flag[2][kPeerMax];      // epoch published by the source rank
+    unsigned long long error;                  // epoch of a timed-out wait (0 = none)
+};
+struct PeerArgs {
+    PeerBuf* peer[kPeerMax];
+    int world, rank;
+    unsigned long long epoch;
+};
+constexpr long long kPeerTimeoutCycles = 60000000000LL;  // ~30 s: a hung peer must not hang the GPU
+
 template <int EP, bool FP, int ET, bool FT>
 __global__ void __launch_bounds__(kMetricThreads)
 confusion_kernel(const void* __restrict__ pred, const void* __restrict__ truth, long long n,
-                 unsigned long long* __restrict__ counts) {
+                 unsigned long long* __restrict__ counts, PeerArgs pa) {
     unsigned long long tp = 0, fp = 0, fn = 0;
     count_range<EP, FP, ET, FT>(pred, truth, 0, n, (long long)blockIdx.x * kMetricThreads + threadIdx.x,
                                 (long long)gridDim.x * kMetricThreads, tp, fp, fn);
     block_sum3<kMetricThreads>(tp, fp, fn);
+    if (pa.world == 0) {
+        if (threadIdx.x == 0) {
+            if (tp) atomicAdd(counts + 0, tp);
+            if (fp) atomicAdd(counts + 1, fp);
+            if (fn) atomicAdd(counts + 2, fn);
+        }
+        return;
+    }
+    const int par = (int)(pa.epoch & 1ull);
+    PeerBuf* me = pa.peer[pa.rank];
+    __shared__ int is_last;
     if (threadIdx.x == 0) {
-        if (tp) atomicAdd(counts + 0, tp);
-        if (fp) atomicAdd(counts + 1, fp);
-        if (fn) atomicAdd(counts + 2, fn);
+        if (tp) atomicAdd(&me->partial[par][0], tp);
+        if (fp) atomicAdd(&me->partial[par][1], fp);
+        if (fn) atomicAdd(&me->partial[par][2], fn);
+        __threadfence();
+        is_last = atomicAdd(&me->ticket[par], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    unsigned long long a = 0, b = 0, c = 0, missing = 0;
+    if ((int)threadIdx.x < pa.world) {   // one thread per peer (world <= 16: all inside warp 0)
+        const int q = threadIdx.x;
+        volatile unsigned long long* mine = me->partial[par];
+        const unsigned long long t0 = mine[0], t1 = mine[1], t2 = mine[2];
+        PeerBuf* dst = pa.peer[q];
+        volatile unsigned long long* sl = dst->slots[par][pa.rank];
+        sl[0] = t0; sl[1] = t1; sl[2] = t2;
+        __threadfence_system();
+        *(volatile unsigned long long*)&dst->flag[par][pa.rank] = pa.epoch;
+        volatile unsigned long long* f = &me->flag[par][q];
+        const long long start = clock64();
+        bool ok = true;
+        while (*f != pa.epoch) {
+            if (clock64() - start > kPeerTimeoutCycles) { ok = false; break; }
+            __nanosleep(64);
+        }
+        __threadfence_system();
+        if (ok) {
+            volatile unsigned long long* r = me->slots[par][q];
+            a = r[0]; b = r[1]; c = r[2];
+        } else {
+            missing = 1;
+        }
+    }
+    if (threadIdx.x < 32) {
+        a = warp_sum64(a); b = warp_sum64(b); c = warp_sum64(c); missing = warp_sum64(missing);
+        if (threadIdx.x == 0) {
+            counts[0] = a; counts[1] = b; counts[2] = c;
+            counts[3] = missing;               // peers that never arrived
+            if (missing) me->error = pa.epoch;
+            me->partial[par][0] = me->partial[par][1] = me->partial[par][2] = 0;  // next use: epoch + 2
+            me->ticket[par] = 0;
+        }
     }
 }
 
@@ -173,7 +250,7 @@ confusion_segmented_kernel(const void* __restrict__ pred, const void* __restrict
 
 template <int EP, bool FP, int ET, bool FT>
 static int launch_confusion(const void* pred, const void* truth, long long n, long long n_seg, long long seg,
-                            unsigned long long* counts, cudaStream_t st) {
+                            unsigned long long* counts, const PeerArgs& pa, cudaStream_t st) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -181,7 +258,7 @@ static int launch_confusion(const void* pred, const void* truth, long long n, lo
         long long want = (n / (16 / (EP < ET ? EP : ET)) + kMetricThreads * 8 - 1) / (kMetricThreads * 8);
         long long cap = (long long)sms * 8;  // 8 resident CTAs of 256 threads per SM
         unsigned grid = (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
-        confusion_kernel<EP, FP, ET, FT><<<grid, kMetricThreads, 0, st>>>(pred, truth, n, counts);
+        confusion_kernel<EP, FP, ET, FT><<<grid, kMetricThreads, 0, st>>>(pred, truth, n, counts, pa);
     } else {
         long long cap = (long long)sms * 8;
         unsigned grid = (unsigned)(n_seg < cap ? n_seg : cap);
@@ -193,33 +270,34 @@ static int launch_confusion(const void* pred, const void* truth, long long n, lo
 
 template <int EP, bool FP>
 static int dispatch_true(const void* pred, const void* truth, int et, int ft, long long n, long long n_seg,
-                         long long seg, unsigned long long* counts, cudaStream_t st) {
+                         long long seg, unsigned long long* counts, const PeerArgs& pa, cudaStream_t st) {
     switch (et * 2 + (ft ? 1 : 0)) {
-        case 2:  return launch_confusion<EP, FP, 1, false>(pred, truth, n, n_seg, seg, counts, st);
-        case 4:  return launch_confusion<EP, FP, 2, false>(pred, truth, n, n_seg, seg, counts, st);
-        case 5:  return launch_confusion<EP, FP, 2, true>(pred, truth, n, n_seg, seg, counts, st);
-        case 8:  return launch_confusion<EP, FP, 4, false>(pred, truth, n, n_seg, seg, counts, st);
-        case 9:  return launch_confusion<EP, FP, 4, true>(pred, truth, n, n_seg, seg, counts, st);
-        case 16: return launch_confusion<EP, FP, 8, false>(pred, truth, n, n_seg, seg, counts, st);
-        case 17: return launch_confusion<EP, FP, 8, true>(pred, truth, n, n_seg, seg, counts, st);
+        case 2:  return launch_confusion<EP, FP, 1, false>(pred, truth, n, n_seg, seg, counts, pa, st);
+        case 4:  return launch_confusion<EP, FP, 2, false>(pred, truth, n, n_seg, seg, counts, pa, st);
+        case 5:  return launch_confusion<EP, FP, 2, true>(pred, truth, n, n_seg, seg, counts, pa, st);
+        case 8:  return launch_confusion<EP, FP, 4, false>(pred, truth, n, n_seg, seg, counts, pa, st);
+        case 9:  return launch_confusion<EP, FP, 4, true>(pred, truth, n, n_seg, seg, counts, pa, st);
+        case 16: return launch_confusion<EP, FP, 8, false>(pred, truth, n, n_seg, seg, counts, pa, st);
+        case 17: return launch_confusion<EP, FP, 8, true>(pred, truth, n, n_seg, seg, counts, pa, st);
     }
     set_error("unsupported truth element size %d (float=%d)", et, ft);
     return RFI_E_INVALID;
 }
 
 static int dispatch(const void* pred, int ep, int fpf, const void* truth, int et, int ft, long long n,
-                    long long n_seg, long long seg, unsigned long long* counts, cudaStream_t st) {
+                    long long n_seg, long long seg, unsigned long long* counts, cudaStream_t st,
+                    const PeerArgs& pa = PeerArgs{{nullptr}, 0, 0, 0ull}) {
     if (!counts) { set_error("counts is NULL"); return RFI_E_INVALID; }
-    if (n == 0 || n_seg == 0) return RFI_OK;
-    if (!pred || !truth) { set_error("pred / truth is NULL"); return RFI_E_INVALID; }
+    if ((n == 0 && pa.world == 0) || n_seg == 0) return RFI_OK;  // a rank with an empty shard still takes part in the exchange
+    if (n != 0 && (!pred || !truth)) { set_error("pred / truth is NULL"); return RFI_E_INVALID; }
     switch (ep * 2 + (fpf ? 1 : 0)) {
-        case 2:  return dispatch_true<1, false>(pred, truth, et, ft, n, n_seg, seg, counts, st);
-        case 4:  return dispatch_true<2, false>(pred, truth, et, ft, n, n_seg, seg, counts, st);
-        case 5:  return dispatch_true<2, true>(pred, truth, et, ft, n, n_seg, seg, counts, st);
-        case 8:  return dispatch_true<4, false>(pred, truth, et, ft, n, n_seg, seg, counts, st);
-        case 9:  return dispatch_true<4, true>(pred, truth, et, ft, n, n_seg, seg, counts, st);
-        case 16: return dispatch_true<8, false>(pred, truth, et, ft, n, n_seg, seg, counts, st);
-        case 17: return dispatch_true<8, true>(pred, truth, et, ft, n, n_seg, seg, counts, st);
+        case 2:  return dispatch_true<1, false>(pred, truth, et, ft, n, n_seg, seg, counts, pa, st);
+        case 4:  return dispatch_true<2, false>(pred, truth, et, ft, n, n_seg, seg, counts, pa, st);
+        case 5:  return dispatch_true<2, true>(pred, truth, et, ft, n, n_seg, seg, counts, pa, st);
+        case 8:  return dispatch_true<4, false>(pred, truth, et, ft, n, n_seg, seg, counts, pa, st);
+        case 9:  return dispatch_true<4, true>(pred, truth, et, ft, n, n_seg, seg, counts, pa, st);
+        case 16: return dispatch_true<8, false>(pred, truth, et, ft, n, n_seg, seg, counts, pa, st);
+        case 17: return dispatch_true<8, true>(pred, truth, et, ft, n, n_seg, seg, counts, pa, st);
     }
     set_error("unsupported pred element size %d (float=%d)", ep, fpf);
     return RFI_E_INVALID;
@@ -233,6 +311,51 @@ extern "C" int rfi_confusion_counts(const void* pred, int elem_pred, int is_floa
     if (n < 0) { rfi::set_error("n < 0"); return RFI_E_INVALID; }
     return rfi::dispatch(pred, elem_pred, is_float_pred, truth, elem_true, is_float_true, n, -1, 0, counts,
                          (cudaStream_t)stream);
+}
+
+extern "C" int rfi_confusion_counts_allreduce(const void* pred, int elem_pred, int is_float_pred,
+                                              const void* truth, int elem_true, int is_float_true, int64_t n,
+                                              void* const* peers, int world, int rank, uint64_t epoch,
+                                              unsigned long long* counts, void* stream) {
+    if (n < 0) { rfi::set_error("n < 0"); return RFI_E_INVALID; }
+    if (!peers || world < 1 || world > rfi::kPeerMax || rank < 0 || rank >= world || epoch == 0) {
+        rfi::set_error("bad peer arguments (world 1..%d, 0 <= rank < world, epoch >= 1)", rfi::kPeerMax);
+        return RFI_E_INVALID;
+    }
+    rfi::PeerArgs pa;
+    for (int i = 0; i < rfi::kPeerMax; ++i) pa.peer[i] = i < world ? static_cast<rfi::PeerBuf*>(peers[i]) : nullptr;
+    for (int i = 0; i < world; ++i) if (!pa.peer[i]) { rfi::set_error("peer %d is NULL", i); return RFI_E_INVALID; }
+    pa.world = world; pa.rank = rank; pa.epoch = epoch;
+    return rfi::dispatch(pred, elem_pred, is_float_pred, truth, elem_true, is_float_true, n, -1, 0, counts,
+                         (cudaStream_t)stream, pa);
+}
+
+// exchange buffer of one rank: its own allocation (not the caller's caching allocator) so that the
+// CUDA IPC handle maps exactly this buffer in the peers
+extern "C" int rfi_peer_alloc(void** buf, unsigned char* handle64) {
+    if (!buf || !handle64) { rfi::set_error("NULL argument"); return RFI_E_INVALID; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    static_assert(sizeof(rfi::PeerBuf) <= RFI_PEER_BYTES, "exchange buffer size");
+    RFI_CUDA_TRY(cudaMalloc(buf, 2u << 20));
+    RFI_CUDA_TRY(cudaMemset(*buf, 0, 2u << 20));
+    RFI_CUDA_TRY(cudaDeviceSynchronize());
+    RFI_CUDA_TRY(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), *buf));
+    return RFI_OK;
+}
+extern "C" int rfi_peer_open(const unsigned char* handle64, void** peer) {
+    if (!peer || !handle64) { rfi::set_error("NULL argument"); return RFI_E_INVALID; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    RFI_CUDA_TRY(cudaIpcOpenMemHandle(peer, h, cudaIpcMemLazyEnablePeerAccess));
+    return RFI_OK;
+}
+extern "C" int rfi_peer_close(void* peer) {
+    if (peer) RFI_CUDA_TRY(cudaIpcCloseMemHandle(peer));
+    return RFI_OK;
+}
+extern "C" int rfi_peer_free(void* buf) {
+    if (buf) RFI_CUDA_TRY(cudaFree(buf));
+    return RFI_OK;
 }
 
 extern "C" int rfi_confusion_counts_segmented(const void* pred, int elem_pred, int is_float_pred,

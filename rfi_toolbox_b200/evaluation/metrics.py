@@ -65,13 +65,49 @@ def _counts_tensor(pred, true, n_seg=None, seg=None):
     return counts
 
 
+def _counts_allreduced(pred, true, ctx):
+    """{TP, FP, FN} summed over the ranks of `ctx` by ONE kernel: the reduction's last CTA exchanges
+    the totals through NVLink peer memory (`rfi_confusion_counts_allreduce`)."""
+    lib = _native.load()
+    device = ctx.device
+    p, ep, fp = _mask_operand(pred, device)
+    t, et, ft = _mask_operand(true, device)
+    if p.numel() != t.numel():
+        raise ValueError(f"pred and true must have the same number of elements ({p.numel()} vs {t.numel()})")
+    with torch.cuda.device(device):
+        counts = torch.empty(4, dtype=torch.int64, device=device)
+        rc = lib.rfi_confusion_counts_allreduce(p.data_ptr(), ep, fp, t.data_ptr(), et, ft, p.numel(),
+                                                ctx.ptrs, ctx.world, ctx.rank, ctx.next_epoch(),
+                                                counts.data_ptr(), current_stream_ptr(device))
+        _native.check(rc, "rfi_confusion_counts_allreduce")
+    tp, fpc, fn, missing = counts.tolist()
+    if missing:
+        raise RuntimeError(f"{missing} rank(s) never reached the metric exchange (epoch {ctx.epoch})")
+    return tp, fpc, fn
+
+
 def confusion_counts(pred, true, group=None):
-    """(TP, FP, FN) as Python ints; summed over `group` if given."""
-    counts = _counts_tensor(pred, true)
+    """(TP, FP, FN) as Python ints; summed over `group` if given (`True` = the default process
+    group).  On one box the sum happens inside the counting kernel, over NVLink peer memory;
+    `RFI_NO_PEER=1`, several hosts or missing CUDA IPC fall back to an NCCL all-reduce."""
     if group is not None:
+        import os
+
         import torch.distributed as dist
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=None if group is True else group)
-    tp, fp, fn = counts.tolist()
+        g = None if group is True else group
+        if dist.get_world_size(g) > 1:
+            device = _pick_device(pred, true)
+            ctx = None
+            if not os.environ.get("RFI_NO_PEER"):
+                from ..utils.peer import peer_context
+                ctx = peer_context(g, device)
+            if ctx is not None:
+                return _counts_allreduced(pred, true, ctx)
+            counts = _counts_tensor(pred, true)
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=g)
+            tp, fp, fn = counts.tolist()
+            return tp, fp, fn
+    tp, fp, fn = _counts_tensor(pred, true).tolist()
     return tp, fp, fn
 
 
