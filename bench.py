@@ -179,6 +179,8 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from rfi_toolbox_b200.utils.device import bind_host_to_device
+    cpus = bind_host_to_device(dev) if world > 1 else None  # pinned host buffers on the GPU's own socket
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=dev)
@@ -324,6 +326,7 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": {"value": cpu_v, "unit": "Gpixel/s", "cores": 1, "kind": "port",
                          "sample": f"{cpu_bl} baselines x 4 pols x {w['channels']}x{w['times']} ({cpu_npix} px) in {cpu_dt:.1f} s, one process"},
+        "host_affinity": (f"{len(cpus)} cores near GPU {local}" if cpus else None),
         "clocks": clocks, "wall_s": wall, "metrics_last_step": {k_: float(v) for k_, v in m.items()},
     }
     print(json.dumps(line))

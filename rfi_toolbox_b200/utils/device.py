@@ -72,3 +72,22 @@ def copy_stream(device: torch.device) -> torch.cuda.Stream:
     if s is None:
         s = _COPY_STREAMS[device.index] = torch.cuda.Stream(device=device)
     return s
+
+
+def bind_host_to_device(device) -> list | None:
+    """Pin the calling process to the CPU cores (hence, by first touch, the host memory node)
+    closest to `device`, as NVML reports them.  With one process per GPU this keeps every rank's
+    pinned upload buffers on its GPU's own socket: 8 concurrent H2D streams otherwise share one
+    inter-socket link.  Returns the CPU list, or None when NVML / the topology is unavailable."""
+    import os
+    try:
+        import pynvml
+        device = torch.device(device)
+        props = torch.cuda.get_device_properties(device)
+        bus = f"{props.pci_domain_id:08X}:{props.pci_bus_id:02X}:{props.pci_device_id:02X}.0"
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return None
