@@ -108,7 +108,14 @@ typedef struct rfi_tile_stat {
  *                       reference pads, because the pad follows the flip;
  * rfi_plan_num_patches  patches before blank removal = R * B * Npol * ceil(C/P) * ceil(T/P)
  *                       (R * B * Npol when patchify is skipped);
- * rfi_plan_workspace_bytes  device scratch the two phases share (0 on the fast path). */
+ * rfi_plan_workspace_bytes  device scratch the two phases share.  Fast path, float32 / complex64:
+ *                       64 KB per tile (part of every tile's keys, thread-private), laid out tile
+ *                       by tile, so a call over a sub-range of the waterfalls may be given the
+ *                       matching sub-range of the buffer; 0 for float64 / complex128. */
+#define RFI_PATH_FAST 0     /* P = 128, dims multiples of 128: one CTA per tile, tile on chip */
+#define RFI_PATH_BIG 1      /* P = 256 / 512 / 1024, dims multiples of P, float32 arithmetic, real branch */
+#define RFI_PATH_GENERIC 2  /* everything else */
+int rfi_plan_path(const rfi_plan_t* plan); /* which of the three the plan takes (-1: bad plan) */
 int64_t rfi_plan_num_tiles(const rfi_plan_t* plan);
 int64_t rfi_plan_num_patches(const rfi_plan_t* plan);
 size_t rfi_plan_workspace_bytes(const rfi_plan_t* plan);

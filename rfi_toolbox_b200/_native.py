@@ -15,6 +15,7 @@ RFI_F32, RFI_F64, RFI_C64, RFI_C128 = 0, 1, 2, 3
 RFI_STRETCH_NONE, RFI_STRETCH_SQRT, RFI_STRETCH_LOG10 = 0, 1, 2
 RFI_FLAGS_CUSTOM, RFI_FLAGS_MAD, RFI_FLAGS_INFERENCE = 0, 1, 2
 RFI_E_INVALID, RFI_E_UNSUPPORTED, RFI_E_CUDA = -1, -2, -3
+RFI_PATH_FAST, RFI_PATH_BIG, RFI_PATH_GENERIC = 0, 1, 2
 ABI_VERSION = 5
 
 
@@ -58,6 +59,7 @@ assert TILE_STAT_BYTES == 88
 # every symbol include/rfi_b200.h declares: name -> (restype, argtypes)
 _VP, _I, _I64 = C.c_void_p, C.c_int, C.c_int64
 SYMBOLS = {
+    "rfi_plan_path": (_I, [C.POINTER(RfiPlan)]),
     "rfi_plan_num_tiles": (_I64, [C.POINTER(RfiPlan)]),
     "rfi_plan_num_patches": (_I64, [C.POINTER(RfiPlan)]),
     "rfi_plan_workspace_bytes": (C.c_size_t, [C.POINTER(RfiPlan)]),

@@ -230,14 +230,24 @@ RFI_DEVINL void mono_resolve(const K* cand, uint32_t M, uint32_t q1, uint32_t q2
 
 // general algorithm (rfi_tiles.cu): any tile, register-resident radix select
 template <int DT, int NT>
-__device__ void tile_stats_general(const PlanDev& p, const void* __restrict__ data,
+__device__ __noinline__ void tile_stats_general(const PlanDev& p, const void* __restrict__ data,
                                    const uint8_t* __restrict__ flags, rfi_tile_stat_t* __restrict__ stats,
-                                   int route_bits);
+                                   int route_bits, typename Scalar<typename In<DT>::T>::key_t* stash_override = nullptr);
 
-template <int DT, int NT>
-__global__ void __launch_bounds__(NT, (sizeof(typename In<DT>::T) == 4) ? 2 : 1)
+// GK (float32 keys): only the first kMonoGS of the 8 key groups stay in shared memory; the rest
+// live in a global scratch (64 KB per tile, of which the upper part is used here and all of it by
+// the general fallback).  The scratch is THREAD-PRIVATE -- a thread only ever re-reads the keys it
+// wrote itself, with coalesced 16-byte accesses -- so it needs no fences and is served by L1 / L2.
+// Shared memory per CTA drops from 88 KB to 57 KB and three CTAs fit one SM instead of two:
+// more independent barrier domains per scheduler for a kernel whose warps mostly wait at
+// barriers (measured: 1.405 -> 1.297 ms on the bench workload; 1.36 ms with all keys in the
+// scratch, 1.32 / 1.335 ms with 6 / 5 groups in shared memory).
+constexpr int kMonoGKB = 3, kMonoGS = 4;
+template <int DT, int NT, bool GK = false, int GKB = kMonoGKB, int GS = kMonoGS>
+__global__ void __launch_bounds__(NT, GK ? GKB : ((sizeof(typename In<DT>::T) == 4) ? 2 : 1))
 tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __restrict__ flags,
-                       rfi_tile_stat_t* __restrict__ stats) {
+                       rfi_tile_stat_t* __restrict__ stats,
+                       typename Scalar<typename In<DT>::T>::key_t* __restrict__ gkeys = nullptr) {
     using T = typename In<DT>::T;
     using K = typename Scalar<T>::key_t;
     static_assert(NT == kMonoNT, "one sample per thread");
@@ -249,9 +259,17 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
     constexpr K kSignBit = K(1) << (Scalar<T>::kBits - 1);
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    K* keys = reinterpret_cast<K*>(smem_raw);   // [E/4][NT][4]
-    K* cand = keys + kP * kP;                   // [kMonoCap]
+    // keys: [E/4][NT][4]; with GK the first GS groups stay in shared memory, the rest live in the
+    // thread-private global scratch
+    K* skeys = reinterpret_cast<K*>(smem_raw);
+    K* gk = GK ? gkeys + (size_t)blockIdx.x * (kP * kP) : nullptr;
+    K* cand = GK ? skeys + (size_t)GS * NT * 4 : skeys + kP * kP;                             // [kMonoCap]
     K* samp = cand + kMonoCap;                  // [NT] sorted raw sample
+    const int tid_ = threadIdx.x;
+    auto kp = [&](int g) -> K* {   // this thread's 4 keys of group g
+        if (GK && g >= GS) return gk + ((size_t)g * NT + tid_) * 4;
+        return skeys + ((size_t)g * NT + tid_) * 4;
+    };
     __shared__ MonoShared<K> sh;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -266,7 +284,7 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
     //  scripts/diag_stats.py reads it)
     auto give_up = [&](int reason) {
         __syncthreads();  // shared memory is handed over
-        tile_stats_general<DT, NT>(p, data, flags, stats, RFI_TILE_GENERAL | (reason << 8));
+        tile_stats_general<DT, NT>(p, data, flags, stats, RFI_TILE_GENERAL | (reason << 8), GK ? gk : nullptr);
     };
 
     // ---- load: magnitude fused into the 128-bit loads, raw bit patterns to shared memory.
@@ -280,7 +298,9 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
     // 4 * lane + i): stratified so that every row AND every column of the tile gives 4 samples
     const int e_s = (((lane + warp * 3) & 7) << 2) | (((lane >> 3) + warp) & 3);
     K bmax = 0, bmin = kExcl;
-#pragma unroll
+    // (real input under the 40-register cap of the 3-CTA variant: the fully unrolled loop hoists all
+    //  32 loads and spills; two groups in flight are enough for a kernel that uses 1 TB/s of HBM)
+#pragma unroll (GK && !In<DT>::cplx ? 2 : G)
     for (int g = 0; g < G; ++g) {
         const size_t idx = origin + (size_t)(g * RS + warp) * p.times + lane * 4;
         T q[4];
@@ -293,11 +313,11 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
             bmin = k4[i] < bmin ? k4[i] : bmin;
         }
         if (sizeof(K) == 4) {
-            *reinterpret_cast<uint4*>(keys + ((size_t)g * NT + tid) * 4) =
+            *reinterpret_cast<uint4*>(kp(g)) =
                 make_uint4((uint32_t)k4[0], (uint32_t)k4[1], (uint32_t)k4[2], (uint32_t)k4[3]);
         } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) keys[((size_t)g * NT + tid) * 4 + i] = k4[i];
+            for (int i = 0; i < 4; ++i) kp(g)[i] = k4[i];
         }
     }
     bmax = warp_max(bmax);
@@ -322,7 +342,7 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
         for (int g = 0; g < G; ++g) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                K& x = keys[((size_t)g * NT + tid) * 4 + i];
+                K& x = kp(g)[i];
                 const K b = x;
                 const bool nan = (b & ~kSignBit) > kInfKey;
                 nodd += (!nan && ((b & kSignBit) != 0 || b == kInfKey)) ? 1u : 0u;
@@ -360,7 +380,10 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
     //      finds the global rank of its sample by binary searches in the other 15 sorted runs
     //      (ties broken by run index, so the ranks are a permutation) and scatters it.
     {
-        K x = keys[((size_t)(e_s >> 2) * NT + tid) * 4 + (e_s & 3)];  // own store: no barrier needed
+        K x = 0;  // own store: no barrier needed
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+            if (g == (e_s >> 2)) x = kp(g)[e_s & 3];
 #pragma unroll
         for (int k = 2; k <= 32; k <<= 1) {
 #pragma unroll
@@ -416,11 +439,11 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
         for (int g = 0; g < G; ++g) {
             K k4[4];
             if (sizeof(K) == 4) {
-                const uint4 q = *reinterpret_cast<const uint4*>(keys + ((size_t)g * NT + tid) * 4);
+                const uint4 q = *reinterpret_cast<const uint4*>(kp(g));
                 k4[0] = q.x; k4[1] = q.y; k4[2] = q.z; k4[3] = q.w;
             } else {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) k4[i] = keys[((size_t)g * NT + tid) * 4 + i];
+                for (int i = 0; i < 4; ++i) k4[i] = kp(g)[i];
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -447,11 +470,11 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
         for (int g = 0; g < G; ++g) {
             K k4[4];
             if (sizeof(K) == 4) {
-                const uint4 q = *reinterpret_cast<const uint4*>(keys + ((size_t)g * NT + tid) * 4);
+                const uint4 q = *reinterpret_cast<const uint4*>(kp(g));
                 k4[0] = q.x; k4[1] = q.y; k4[2] = q.z; k4[3] = q.w;
             } else {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) k4[i] = keys[((size_t)g * NT + tid) * 4 + i];
+                for (int i = 0; i < 4; ++i) k4[i] = kp(g)[i];
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -543,11 +566,11 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
         for (int g = 0; g < G; ++g) {
             K k4[4];
             if (sizeof(K) == 4) {
-                const uint4 q = *reinterpret_cast<const uint4*>(keys + ((size_t)g * NT + tid) * 4);
+                const uint4 q = *reinterpret_cast<const uint4*>(kp(g));
                 k4[0] = q.x; k4[1] = q.y; k4[2] = q.z; k4[3] = q.w;
             } else {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) k4[i] = keys[((size_t)g * NT + tid) * 4 + i];
+                for (int i = 0; i < 4; ++i) k4[i] = kp(g)[i];
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -575,11 +598,11 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
         for (int g = 0; g < G; ++g) {
             K k4[4];
             if (sizeof(K) == 4) {
-                const uint4 q = *reinterpret_cast<const uint4*>(keys + ((size_t)g * NT + tid) * 4);
+                const uint4 q = *reinterpret_cast<const uint4*>(kp(g));
                 k4[0] = q.x; k4[1] = q.y; k4[2] = q.z; k4[3] = q.w;
             } else {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) k4[i] = keys[((size_t)g * NT + tid) * 4 + i];
+                for (int i = 0; i < 4; ++i) k4[i] = kp(g)[i];
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -669,7 +692,7 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
         for (int g = 0; g < G; ++g) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const K x = keys[((size_t)g * NT + tid) * 4 + i];
+                const K x = kp(g)[i];
                 const bool f = (x != kExcl) && (all_hi || x > khi_cmp || x < klo);
                 nf += f ? 1u : 0u;
             }

@@ -35,7 +35,8 @@ namespace rfi {
 template <int DT, int NT>
 __device__ __noinline__ void tile_stats_general(const PlanDev& p, const void* __restrict__ data,
                                                 const uint8_t* __restrict__ flags,
-                                                rfi_tile_stat_t* __restrict__ stats, int route_bits) {
+                                                rfi_tile_stat_t* __restrict__ stats, int route_bits,
+                                                typename Scalar<typename In<DT>::T>::key_t* stash_override) {
     using T = typename In<DT>::T;
     using K = typename Scalar<T>::key_t;
     constexpr int E = kP * kP / NT;  // samples per thread
@@ -45,7 +46,7 @@ __device__ __noinline__ void tile_stats_general(const PlanDev& p, const void* __
     constexpr K kPosInf = to_key_const_inf<T>(false), kNegInf = to_key_const_inf<T>(true);
     constexpr K kNegZero = (K(1) << (Scalar<T>::kBits - 1)) - 1;  // key(-0.0); key(+0.0) is one above
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    K* stash = reinterpret_cast<K*>(smem_raw);  // [E][NT]
+    K* stash = stash_override ? stash_override : reinterpret_cast<K*>(smem_raw);  // [E][NT], thread-private
     __shared__ BlockScratch<NT> scr;
     __shared__ RoundCounter rc;
     __shared__ SelectScratch<K> sel;
@@ -225,7 +226,7 @@ template <int DT, int NT>
 __global__ void __launch_bounds__(NT, (sizeof(typename In<DT>::T) == 4) ? 2 : 1)
 tile_stats_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __restrict__ flags,
                   rfi_tile_stat_t* __restrict__ stats) {
-    tile_stats_general<DT, NT>(p, data, flags, stats, RFI_TILE_GENERAL);
+    tile_stats_general<DT, NT>(p, data, flags, stats, RFI_TILE_GENERAL, nullptr);
 }
 
 // custom flags / inference with nothing to measure on the data: flags only.
@@ -551,14 +552,23 @@ static int make_plan(const rfi_plan_t* plan, PlanDev& d) {
 
 template <int DT, int NT>
 static int launch_stats(const PlanDev& d, long long tiles, const void* data, const uint8_t* flags,
-                        rfi_tile_stat_t* stats, cudaStream_t st) {
+                        rfi_tile_stat_t* stats, void* scratch, cudaStream_t st) {
     using K = typename Scalar<typename In<DT>::T>::key_t;
-    auto mono = tile_stats_mono_kernel<DT, kMonoNT>;
-    size_t msmem = (size_t)(kP * kP + kMonoCap + kMonoNT) * sizeof(K);
-    RFI_CUDA_TRY(cudaFuncSetAttribute(mono, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+    if constexpr (sizeof(K) == 4) {
+        // float32 keys: half of them in the thread-private global scratch, 3 CTAs / SM
+        if (!scratch) { set_error("rfi_tile_stats needs the workspace rfi_plan_workspace_bytes() reports"); return RFI_E_INVALID; }
+        auto k = tile_stats_mono_kernel<DT, kMonoNT, true>;
+        const size_t gsmem = (size_t)(kMonoCap + kMonoNT + kMonoGS * kMonoNT * 4) * sizeof(K);
+        RFI_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+        k<<<(unsigned)tiles, kMonoNT, gsmem, st>>>(d, data, flags, stats, static_cast<K*>(scratch));
+    } else {
+        auto mono = tile_stats_mono_kernel<DT, kMonoNT>;
+        size_t msmem = (size_t)(kP * kP + kMonoCap + kMonoNT) * sizeof(K);
+        RFI_CUDA_TRY(cudaFuncSetAttribute(mono, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+        mono<<<(unsigned)tiles, kMonoNT, msmem, st>>>(d, data, flags, stats, nullptr);
+    }
     // tiles with negative / infinite / inf-filled samples, or whose sampled bracket missed, run
     // the general algorithm inside the same CTA (no second launch, no tail)
-    mono<<<(unsigned)tiles, kMonoNT, msmem, st>>>(d, data, flags, stats);
     static_assert(NT == kMonoNT, "the general path runs inside the monotone kernel's CTA");
     return RFI_OK;
 }
@@ -591,8 +601,18 @@ extern "C" int64_t rfi_plan_num_patches(const rfi_plan_t* plan) {
     if (plan_is_fast(plan)) return rfi_plan_num_tiles(plan) * plan->rotations;
     return generic_num_patches(plan);
 }
+extern "C" int rfi_plan_path(const rfi_plan_t* plan) {
+    if (!plan || plan->patch <= 0) return -1;
+    return plan_is_fast(plan) ? RFI_PATH_FAST : plan_is_big(plan) ? RFI_PATH_BIG : RFI_PATH_GENERIC;
+}
 extern "C" size_t rfi_plan_workspace_bytes(const rfi_plan_t* plan) {
-    if (!plan || plan->patch <= 0 || plan_is_fast(plan)) return 0;
+    if (!plan || plan->patch <= 0) return 0;
+    if (plan_is_fast(plan)) {
+        // float32 arithmetic: the statistics kernel keeps part of every tile's keys in a
+        // thread-private scratch (64 KB per tile = 4 B / px); float64 tiles stay on chip
+        if (plan->dtype != RFI_F32 && plan->dtype != RFI_C64) return 0;
+        return (size_t)rfi_plan_num_tiles(plan) * kP * kP * sizeof(uint32_t);
+    }
     if (plan_is_big(plan)) return big_workspace_bytes(plan);
     return generic_workspace_bytes(plan);
 }
@@ -619,10 +639,10 @@ extern "C" int rfi_tile_stats(const rfi_plan_t* plan, const void* data, const ui
         flags_count_kernel<512><<<(unsigned)tiles, 512, 0, st>>>(d, d.flag_mode == RFI_FLAGS_CUSTOM ? flags : nullptr, stats);
     } else {
         switch (plan->dtype) {
-            case RFI_F32: rc = launch_stats<RFI_F32, 512>(d, tiles, data, flags, stats, st); break;
-            case RFI_C64: rc = launch_stats<RFI_C64, 512>(d, tiles, data, flags, stats, st); break;
-            case RFI_F64: rc = launch_stats<RFI_F64, 512>(d, tiles, data, flags, stats, st); break;
-            default:      rc = launch_stats<RFI_C128, 512>(d, tiles, data, flags, stats, st); break;
+            case RFI_F32: rc = launch_stats<RFI_F32, 512>(d, tiles, data, flags, stats, workspace, st); break;
+            case RFI_C64: rc = launch_stats<RFI_C64, 512>(d, tiles, data, flags, stats, workspace, st); break;
+            case RFI_F64: rc = launch_stats<RFI_F64, 512>(d, tiles, data, flags, stats, workspace, st); break;
+            default:      rc = launch_stats<RFI_C128, 512>(d, tiles, data, flags, stats, workspace, st); break;
         }
         if (rc) return rc;
     }

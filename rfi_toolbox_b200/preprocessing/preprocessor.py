@@ -250,8 +250,8 @@ class Preprocessor:
                 ev[0].record()
             work = torch.empty(ws_bytes, dtype=torch.uint8, device=device) if ws_bytes else None
             wptr = work.data_ptr() if work is not None else None
-            pipelined = (host is not None and host.is_pinned() and ws_bytes == 0 and not skip_patchify
-                         and B > 1 and n_tiles > 0)
+            fast = lib.rfi_plan_path(C.byref(plan)) == _native.RFI_PATH_FAST
+            pipelined = host is not None and host.is_pinned() and fast and B > 1 and n_tiles > 0
             if host is not None and not pipelined:
                 data = host.to(device, non_blocking=True)
             if pipelined:
@@ -274,7 +274,8 @@ class Preprocessor:
                     rc = lib.rfi_tile_stats(C.byref(sub), data.data_ptr() + off * data.element_size(),
                                             fptr + off if fptr is not None else None,
                                             stats.data_ptr() + b0 * per_bl_tiles * _native.TILE_STAT_BYTES,
-                                            None, stream)
+                                            wptr + b0 * per_bl_tiles * (ws_bytes // n_tiles) if wptr else None,
+                                            stream)
                     _native.check(rc, "rfi_tile_stats")
                 data.record_stream(side)
             else:
@@ -283,6 +284,10 @@ class Preprocessor:
             if ev:
                 ev[1].record()
             self.last_tile_stats = stats
+            if fast:
+                # the fast path's scratch serves phase 1 only: hand its block back before the
+                # outputs are allocated (stream-ordered reuse)
+                work, wptr = None, None
 
             # ---- host: blank-patch compaction + shuffle -> destination slot of every patch
             #      (one native call on pinned buffers; draws the ONE np.random.permutation of

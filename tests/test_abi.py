@@ -37,9 +37,15 @@ def test_struct_layout_and_pure_host_calls(native_lib):
     plan.rotations = 3
     assert native_lib.rfi_tile_stats(C.byref(plan), None, None, None, None, None) == _native.RFI_E_INVALID
     assert b"rotations" in native_lib.rfi_last_error_string()
-    assert native_lib.rfi_plan_workspace_bytes(C.byref(plan)) == 0  # fast path: P = 128, dims divisible
+    # fast path (P = 128, dims divisible), float32: 64 KB of thread-private key scratch per tile; float64: none
+    assert native_lib.rfi_plan_path(C.byref(plan)) == _native.RFI_PATH_FAST
+    assert native_lib.rfi_plan_workspace_bytes(C.byref(plan)) == 8 * 8 * 16 * 65536
+    plan.dtype = _native.RFI_F64
+    assert native_lib.rfi_plan_workspace_bytes(C.byref(plan)) == 0
+    plan.dtype = _native.RFI_F32
     # generic geometries: statistic groups, patches and workspace (host arithmetic only)
     plan.rotations, plan.patch = 4, 256
+    assert native_lib.rfi_plan_path(C.byref(plan)) == _native.RFI_PATH_BIG
     assert native_lib.rfi_plan_num_tiles(C.byref(plan)) == 8 * 4 * 8
     assert native_lib.rfi_plan_num_patches(C.byref(plan)) == 8 * 4 * 8 * 4
     assert native_lib.rfi_plan_workspace_bytes(C.byref(plan)) > 0
