@@ -109,12 +109,16 @@ static int legacy_shuffle(uint32_t* mt_key, int32_t* mt_pos, int64_t n, int64_t*
     while (i >= 1) {
         if (pos == kN) { mt_regenerate(mt_key); temper_from(0); pos = 0; }
         int k = pos;
-        uint32_t mask = 0xffffffffu >> __builtin_clz(i);  // smallest 2^b - 1 >= i
-        for (; k < kN && i >= 1; ++k) {
-            if (i <= (mask >> 1)) mask >>= 1;  // rare and predictable: i crossed a power of two
-            const uint32_t v = tb[k] & mask;
-            js[i] = v;
-            i -= (v <= i) ? 1u : 0u;
+        // i stays inside (mask >> 1, mask] for a whole inner loop, so the mask is a loop constant
+        // and the only loop-carried chain is compare -> subtract
+        while (k < kN && i >= 1) {
+            const uint32_t mask = 0xffffffffu >> __builtin_clz(i);  // smallest 2^b - 1 >= i
+            const uint32_t low = mask >> 1;
+            for (; k < kN && i > low; ++k) {
+                const uint32_t v = tb[k] & mask;
+                js[i] = v;
+                i -= (v <= i) ? 1u : 0u;
+            }
         }
         pos = k;
     }
