@@ -265,6 +265,23 @@ int rfi_synth_waterfalls(const rfi_synth_t* sp, int64_t n_baselines, int64_t fir
                          const float* band_amp, const float* sweep, void* cube, uint8_t* mask,
                          void* stream);
 
+/* Raw complex patches -- replaces the tiling / blank removal / shuffle gathers of
+ * GPUPreprocessor.create_raw_patches (preprocessor.py:846-940, :942-972): non-overlapping P x P
+ * tiles of every waterfall (patchify with step P: remainders dropped, no padding), or the whole
+ * waterfall when it is no larger than the patch (:885-890); masks are the caller's flags or
+ * |z| > 0 (:881-883).  dtype RFI_C64 / RFI_C128 only (:832-836).
+ *   rfi_raw_num_tiles    tiles before blank removal (-1: bad arguments) and the tile shape
+ *   rfi_raw_tile_counts  counts device int32[tiles]: flagged samples per tile (mask.any(), :906)
+ *   rfi_raw_gather       dest_slot device int64[tiles] (-1 = dropped) -> patches device
+ *                        (N, rows, cols) in the input dtype, masks device uint8 (N, rows, cols) */
+int64_t rfi_raw_num_tiles(int dtype, int64_t n_waterfalls, int64_t channels, int64_t times, int32_t patch,
+                          int32_t* tile_rows, int32_t* tile_cols);
+int rfi_raw_tile_counts(const void* data, int dtype, const uint8_t* flags, int64_t n_waterfalls,
+                        int64_t channels, int64_t times, int32_t patch, int32_t* counts, void* stream);
+int rfi_raw_gather(const void* data, int dtype, const uint8_t* flags, int64_t n_waterfalls,
+                   int64_t channels, int64_t times, int32_t patch, const int64_t* dest_slot,
+                   void* patches, uint8_t* masks, void* stream);
+
 /* Self test (used by tests/): counts the inputs t in [1, 2] (all 2^23 + 1 float32 values) for
  * which the range-restricted square root of the magnitude kernel differs from sqrt.rn.f32.
  *   mismatches_dev  device uint64, ACCUMULATED into (caller zeroes); must end up 0 */

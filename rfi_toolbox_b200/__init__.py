@@ -25,4 +25,4 @@ from .evaluation import (  # noqa: F401,E402
     evaluate_segmentation_batch,
 )
 from .data_generation import SyntheticDataGenerator  # noqa: F401,E402
-from .preprocessing import Preprocessor, iter_dataset_chunks  # noqa: F401,E402
+from .preprocessing import GPUPreprocessor, Preprocessor, iter_dataset_chunks  # noqa: F401,E402
