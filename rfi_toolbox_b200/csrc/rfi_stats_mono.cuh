@@ -51,16 +51,18 @@ struct MonoShared {          // static part (must stay small: 3 CTAs / SM)
 template <typename K>
 RFI_DEVINL K shfl_xor_key(K v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
-template <typename K>
-RFI_DEVINL void warp_sort512(K (&v)[16], int lane) {
+// one warp sorts 32 * R keys held R per lane, element index e = r * 32 + lane (ascending)
+template <typename K, int R>
+RFI_DEVINL void warp_sort_regs(K (&v)[R], int lane) {
+    constexpr int N = 32 * R;
 #pragma unroll
-    for (int k = 2; k <= 512; k <<= 1) {
+    for (int k = 2; k <= N; k <<= 1) {
         // in-lane stages: partner register r ^ (j / 32); direction fixed by r at compile time
 #pragma unroll
         for (int j = k >> 1; j >= 32; j >>= 1) {
             const int jr = j >> 5;
 #pragma unroll
-            for (int r = 0; r < 16; ++r) {
+            for (int r = 0; r < R; ++r) {
                 if ((r & jr) == 0) {
                     const int r2 = r | jr;
                     const bool up = (((r << 5) & k) == 0);
@@ -73,11 +75,11 @@ RFI_DEVINL void warp_sort512(K (&v)[16], int lane) {
         }
         // cross-lane stages
         const int jstart = (k >> 1) < 16 ? (k >> 1) : 16;
-#pragma unroll 1
+#pragma unroll
         for (int j = jstart; j > 0; j >>= 1) {
             const bool lower = (lane & j) == 0;
 #pragma unroll
-            for (int r = 0; r < 16; ++r) {
+            for (int r = 0; r < R; ++r) {
                 const bool up = ((((r << 5) | lane) & k) == 0);
                 const K o = shfl_xor_key<K>(v[r], j);
                 const bool keep_min = (lower == up);
@@ -87,6 +89,8 @@ RFI_DEVINL void warp_sort512(K (&v)[16], int lane) {
         }
     }
 }
+template <typename K>
+RFI_DEVINL void warp_sort512(K (&v)[16], int lane) { warp_sort_regs<K, 16>(v, lane); }
 
 // raw key of a non-negative sample: its bit pattern (orders like the value); NaN -> all ones
 template <typename T>
@@ -97,14 +101,24 @@ RFI_DEVINL typename Scalar<T>::key_t raw_key(T a) {
 template <typename T>
 RFI_DEVINL T raw_val(typename Scalar<T>::key_t k) { return Scalar<T>::from_bits(k); }
 
-// processed sample WITHOUT the inf fill (the searches walk outside the tile's value range)
+// processed sample WITHOUT the inf fill (the searches walk outside the tile's value range).
+// `mode` packs the plan's switches (kProc*) so that the out-of-line chain reads no plan field.
+constexpr int kProcDivM = 1, kProcSqrt = 2, kProcLog10 = 4, kProcDivM2 = 8;
 template <typename T>
-__device__ __noinline__ T proc_nofill(T a, const PlanDev& p, T m, T m2) {
-    if (p.norm_before && m > T(0)) a = a / m;
-    if (p.stretch != RFI_STRETCH_NONE) a = apply_stretch<T>(a, p.stretch);
-    if (p.norm_after && m2 > T(0)) a = a / m2;
+RFI_DEVINL int proc_mode_of(const PlanDev& p, T m, T m2) {
+    return ((p.norm_before && m > T(0)) ? kProcDivM : 0) | (p.stretch == RFI_STRETCH_SQRT ? kProcSqrt : 0) |
+           (p.stretch == RFI_STRETCH_LOG10 ? kProcLog10 : 0) | ((p.norm_after && m2 > T(0)) ? kProcDivM2 : 0);
+}
+template <typename T>
+__device__ __noinline__ T proc_mode(T a, int mode, T m, T m2) {
+    if (mode & kProcDivM) a = a / m;
+    if (mode & kProcSqrt) a = Scalar<T>::sqrt_rn(fabs_(a));
+    else if (mode & kProcLog10) a = Scalar<T>::log10_(fabs_(a));
+    if (mode & kProcDivM2) a = a / m2;
     return a;
 }
+template <typename T>
+RFI_DEVINL T proc_nofill(T a, const PlanDev& p, T m, T m2) { return proc_mode<T>(a, proc_mode_of<T>(p, m, m2), m, m2); }
 
 // Exact rank resolution inside the candidate list cand[0 .. M): keys of ranks q1 <= q2 <= q1 + 1.
 // Block-wide, uniform control flow.  Rank q1 by a linear 512-bucket histogram over the list's
@@ -376,44 +390,45 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
     }
     if (nv < 64) { give_up(1); return; }
 
-    // ---- sort the 512-sample: every warp sorts its 32 samples with shuffles, then every thread
-    //      finds the global rank of its sample by binary searches in the other 15 sorted runs
-    //      (ties broken by run index, so the ranks are a permutation) and scatters it.
+    // ---- sort the 512-sample: warps 0..3 each sort 128 samples in registers (bitonic network, 4
+    //      keys per lane, shuffles across lanes), then EVERY thread finds the global rank of one
+    //      sorted key by binary searches in the other three runs (ties broken by run index, so the
+    //      ranks are a permutation) and scatters it.  (16 runs of 32 cost 15 searches per key.)
     {
         K x = 0;  // own store: no barrier needed
 #pragma unroll
         for (int g = 0; g < G; ++g)
             if (g == (e_s >> 2)) x = kp(g)[e_s & 3];
-#pragma unroll
-        for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                const K o = shfl_xor_key<K>(x, j);
-                const bool keep_min = (((lane & j) == 0) == ((lane & k) == 0));
-                const K mn = x < o ? x : o, mx = x < o ? o : x;
-                x = keep_min ? mn : mx;
-            }
-        }
-        K* runs = cand;  // [16][32], free until the first compaction
+        K* runs = cand;  // [4][128], free until the first compaction
         runs[tid] = x;
         const int nvalid_s = __syncthreads_count(x != kExcl);
-        uint32_t rank = lane;
-        auto count_in_run = [&](const K* run, auto incl_tag) {
-            constexpr bool incl = decltype(incl_tag)::value;  // earlier runs win ties
+        if (warp < 4) {
+            K v[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) v[r] = runs[warp * 128 + r * 32 + lane];
+            warp_sort_regs<K, 4>(v, lane);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) runs[warp * 128 + r * 32 + lane] = v[r];
+        }
+        __syncthreads();
+        const int run_id = tid >> 7;
+        x = runs[tid];
+        uint32_t rank = tid & 127;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            if (o == run_id) continue;  // warp-uniform
+            const K* run = runs + o * 128;
+            const bool incl = o < run_id;  // earlier runs win ties
             uint32_t pos = 0;
 #pragma unroll
-            for (int step = 16; step > 0; step >>= 1) {
+            for (int step = 64; step > 0; step >>= 1) {
                 const K y = run[pos + step - 1];
                 pos += (incl ? (y <= x) : (y < x)) ? step : 0;
             }
-            const K y = run[31];
-            pos += (pos == 31 && (incl ? (y <= x) : (y < x))) ? 1u : 0u;
-            return pos;
-        };
-#pragma unroll 3
-        for (int r = 0; r < warp; ++r) rank += count_in_run(runs + r * 32, std::true_type{});
-#pragma unroll 3
-        for (int r = warp + 1; r < NT / 32; ++r) rank += count_in_run(runs + r * 32, std::false_type{});
+            const K y = run[127];
+            pos += (pos == 127 && (incl ? (y <= x) : (y < x))) ? 1u : 0u;
+            rank += pos;
+        }
         samp[rank] = x;
         if (tid == 0) sh.acc[2] = (uint32_t)nvalid_s;
     }
@@ -500,9 +515,10 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
     }
     const PlanDev pp = [&]() { PlanDev q = p; if (!real_branch) { q.norm_before = q.norm_after = 0; q.stretch = RFI_STRETCH_NONE; } return q; }();
     // the extreme samples must stay finite through the chain (else: inf fill -> general kernel)
+    const int pmode = proc_mode_of<T>(pp, m, m2);
     {
-        const T pmin = proc_nofill<T>(raw_val<T>(tile_min), pp, m, m2);
-        const T pmax = proc_nofill<T>(raw_val<T>(tile_max), pp, m, m2);
+        const T pmin = proc_mode<T>(raw_val<T>(tile_min), pmode, m, m2);
+        const T pmax = proc_mode<T>(raw_val<T>(tile_max), pmode, m, m2);
         if (is_inf(pmin) || is_inf(pmax) || is_nan(pmin) || is_nan(pmax)) { give_up(5); return; }
     }
 
@@ -515,7 +531,7 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
         K* dsamp = cand;  // [NT], free until the candidates are compacted
         bool below_c = false;
         if (tid < sv) {
-            const T ps = proc_nofill<T>(raw_val<T>(samp[tid]), pp, m, m2);
+            const T ps = proc_mode<T>(raw_val<T>(samp[tid]), pmode, m, m2);
             below_c = ps < c;
             dsamp[tid] = to_key<T>(fabs_(ps - c));
         }
@@ -614,7 +630,7 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
         __syncthreads();
         // exact deviation of every candidate, in place
         for (uint32_t i = tid; i < M; i += NT) {
-            const T ps = proc_nofill<T>(raw_val<T>(cand[i]), pp, m, m2);
+            const T ps = proc_mode<T>(raw_val<T>(cand[i]), pmode, m, m2);
             cand[i] = to_key<T>(fabs_(ps - c));
         }
         __syncthreads();
@@ -637,7 +653,7 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
             const T thr = want_hi ? thr_hi : thr_lo;
             // predicate that is true on a PREFIX of the keys: hi: proc <= thr ; lo: proc < thr
             auto pre = [&](K k) {
-                const T v = proc_nofill<T>(raw_val<T>(k), pp, m, m2);
+                const T v = proc_mode<T>(raw_val<T>(k), pmode, m, m2);
                 return want_hi ? (v <= thr) : !(v >= thr);
             };
             K first_false;  // smallest key where the predicate fails (kTop if none below kTop)
