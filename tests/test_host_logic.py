@@ -115,7 +115,8 @@ def test_legacy_permutation_matches_numpy(native_lib):
     import numpy as np
     from rfi_toolbox_b200 import _native
     for seed in range(6):
-        for n in [0, 1, 2, 3, 5, 8, 9, 100, 623, 624, 625, 1248, 4097, 44368, 65537]:
+        # (16383 .. 32769 straddle the mask at which the vectorised draws switch block size)
+        for n in [0, 1, 2, 3, 5, 8, 9, 33, 100, 623, 624, 625, 1248, 4097, 16383, 16384, 16385, 32767, 32769, 44368, 65537, 131073]:
             np.random.seed(seed); np.random.random(seed * 13)
             a = np.random.permutation(n); ra = np.random.random(5); ga = np.random.standard_normal(3)
             np.random.seed(seed); np.random.random(seed * 13)
