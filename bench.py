@@ -321,8 +321,9 @@ def run_ours(args):
                                    "memory (NCCL only for rendezvous / barriers)") if world > 1 else "single GPU"},
         "e2e": {"value": e2e_value, "unit": "Gpixel/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "note": "pinned host cube copied H2D every step; dataset stays in HBM, metric dict read back"},
-        # per step: tile_stats_mono_kernel, write_patches_kernel, confusion_kernel
-        "gpu_launches": 3 * args.steps,
+        # per step, P = 128: tile_stats_mono_kernel, write_patches_kernel, confusion_kernel;
+        # P = 256: big_init / load / sample / pass<0> / median / pass<1> / mad / count / write + confusion_kernel
+        "gpu_launches": (3 if w["patch"] == 128 else 10) * args.steps,
         "roofline": roofline,
         "cpu_baseline": {"value": cpu_v, "unit": "Gpixel/s", "cores": 1, "kind": "port",
                          "sample": f"{cpu_bl} baselines x 4 pols x {w['channels']}x{w['times']} ({cpu_npix} px) in {cpu_dt:.1f} s, one process"},

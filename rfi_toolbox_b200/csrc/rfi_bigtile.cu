@@ -741,8 +741,6 @@ big_write_kernel(BigGeom g, const float* __restrict__ src, const uint8_t* __rest
         return sl < 0 ? nullptr : labels + (size_t)sl * PP + (size_t)br[r] * kP * P + (size_t)bc[r] * kP;
     };
     uint32_t nf_unused = 0;
-    const bool inference = p.flag_mode == RFI_FLAGS_INFERENCE;
-    (void)inference;
     if (bm.fast) big_pass_a<true, true>(g, t, bm, src, flags, Ls, halo, FbT, lab_at(slot0, 0), lab_at(slot1, 1), nf_unused);
     else big_pass_a<false, true>(g, t, bm, src, flags, Ls, halo, FbT, lab_at(slot0, 0), lab_at(slot1, 1), nf_unused);
     __syncthreads();

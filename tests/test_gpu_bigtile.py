@@ -117,3 +117,27 @@ def test_chunked_stream_matches_per_chunk_oracle(native_lib):
         ods = oracle.create_dataset(data[b0:b1], None, **kw)
         assert np.array_equal(labs, ods.labels)
         assert np.allclose(imgs, ods.images, rtol=1e-6, atol=2e-5, equal_nan=True)
+
+
+def _degenerate_cube(seed=0):
+    """Tiles that stress the sampled brackets: heavy duplicates, two-valued, constant, all-zero."""
+    rng = np.random.default_rng(seed)
+    d = np.abs(rng.normal(1.0, 0.1, (2, 2, 512, 512))).astype(np.float32)
+    d[0, 0] = np.round(d[0, 0] * 8) / 8                       # ~10 distinct values
+    d[0, 1] = np.where(rng.random((512, 512)) < 0.5, 1.0, 2.0)  # two values: the median sits on a tie
+    d[1, 0, :256] = 3.0                                       # constant tiles (MAD 0)
+    d[1, 0, 256:, :256] = 0.0                                 # all-zero tile
+    d[1, 1, 100:110, :] = 1e6                                 # a clean RFI line in plain noise
+    return d
+
+
+@pytest.mark.parametrize("patch", [128, 256])
+@pytest.mark.parametrize("stretch", [None, "SQRT"])
+def test_degenerate_tiles_match_oracle(native_lib, patch, stretch):
+    """Ties everywhere: exact order statistics must still come out bit-identical (duplicates end a
+    histogram refinement on a single key value; constant tiles have MAD 0 and flag nothing)."""
+    data = _degenerate_cube()
+    kw = dict(patch_size=patch, stretch=stretch, flag_sigma=3, use_custom_flags=False)
+    pre, ds = _run_gpu(data, None, **kw)
+    ods, inter = _run_oracle(data, None, **kw)
+    _compare(ds, ods, inter, pre)
