@@ -286,8 +286,9 @@ def run_ours(args):
         peaks = json.loads(pk.read_text())
     peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
     k = n_kept / (n_tiles * w["rot"])
-    # the big-tile writer (P > 128) reads the float32 magnitude scratch of phase 1, not the complex cube
-    alg_bytes = npix * ((cube.element_size() if w["patch"] == 128 else 4) + w["rot"] * k * 13.0)
+    # complex64 through the real branch: both writers read the exact float32 magnitudes phase 1 left in
+    # its scratch (4 B / px), not the complex cube (8 B / px); the cube itself is read once, by phase 1
+    alg_bytes = npix * (4 + w["rot"] * k * 13.0)
     write_ms = float(np.mean(kern_ms["write"]))
     stats_ms = float(np.mean(kern_ms["stats"]))
     achieved = alg_bytes / (write_ms * 1e-3) / 1e9
@@ -302,7 +303,9 @@ def run_ours(args):
                 "achieved": achieved, "peak": peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": write_ms,
-                "stats_kernel_ms": stats_ms, "stats_kernel_gbs": npix * cube.element_size() / (stats_ms * 1e-3) / 1e9,
+                "stats_kernel_ms": stats_ms, "stats_kernel_gbs": npix * (cube.element_size() + 4) / (stats_ms * 1e-3) / 1e9,
+                "bytes_per_pixel": {"phase1": cube.element_size() + 4, "writer": 4 + w["rot"] * k * 13.0,
+                                    "path_minimum": cube.element_size() + w["rot"] * k * 13.0},
                 "step_ms_device": dev_ms / args.steps}
 
     cpu_bl = 2 if w["channels"] * w["times"] <= 1 << 20 else 1

@@ -109,9 +109,11 @@ typedef struct rfi_tile_stat {
  * rfi_plan_num_patches  patches before blank removal = R * B * Npol * ceil(C/P) * ceil(T/P)
  *                       (R * B * Npol when patchify is skipped);
  * rfi_plan_workspace_bytes  device scratch the two phases share.  Fast path, float32 / complex64:
- *                       64 KB per tile (part of every tile's keys, thread-private), laid out tile
+ *                       64 KB per tile (the tile's keys, thread-private in phase 1), laid out tile
  *                       by tile, so a call over a sub-range of the waterfalls may be given the
- *                       matching sub-range of the buffer; 0 for float64 / complex128. */
+ *                       matching sub-range of the buffer; for complex64 with magnitude = 1 phase 2
+ *                       reads the exact magnitudes back from it (4 B / px instead of 8 B / px and
+ *                       |z| again; NULL there = read the cube); 0 for float64 / complex128. */
 #define RFI_PATH_FAST 0     /* P = 128, dims multiples of 128: one CTA per tile, tile on chip */
 #define RFI_PATH_BIG 1      /* P = 256 / 512 / 1024, dims multiples of P, float32 arithmetic, real branch */
 #define RFI_PATH_GENERIC 2  /* everything else */

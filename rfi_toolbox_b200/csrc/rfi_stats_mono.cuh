@@ -327,8 +327,14 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
             bmin = k4[i] < bmin ? k4[i] : bmin;
         }
         if (sizeof(K) == 4) {
-            *reinterpret_cast<uint4*>(kp(g)) =
-                make_uint4((uint32_t)k4[0], (uint32_t)k4[1], (uint32_t)k4[2], (uint32_t)k4[3]);
+            const uint4 packed = make_uint4((uint32_t)k4[0], (uint32_t)k4[1], (uint32_t)k4[2], (uint32_t)k4[3]);
+            *reinterpret_cast<uint4*>(kp(g)) = packed;
+            // complex input: the scratch tile ends up holding ALL magnitudes, row-major (element
+            // (g * 16 + warp, 4 * lane + i) sits at index row * 128 + col), and phase 2 reads them
+            // back (4 B / px) instead of the complex samples (8 B / px + |z| again)
+            if constexpr (GK && In<DT>::cplx) {
+                if (g < GS) *reinterpret_cast<uint4*>(gk + ((size_t)g * NT + tid_) * 4) = packed;
+            }
         } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) kp(g)[i] = k4[i];

@@ -283,7 +283,8 @@ template <int DT, int NT, bool kComplexBranch>
 __global__ void __launch_bounds__(NT, (sizeof(typename In<DT>::T) == 4 && !kComplexBranch) ? 2 : 1)
 write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __restrict__ flags,
                      const rfi_tile_stat_t* __restrict__ stats, const long long* __restrict__ dest_slot,
-                     float* __restrict__ images, uint8_t* __restrict__ labels) {
+                     float* __restrict__ images, uint8_t* __restrict__ labels,
+                     const float* __restrict__ mag_scratch) {
     using T = typename In<DT>::T;
     constexpr int E = kP * kP / NT;
     constexpr int RS = NT / 32;      // rows per step (one warp per row)
@@ -342,22 +343,30 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
     T llo = Scalar<T>::nan(), lhi = Scalar<T>::nan();
     const bool fast_route = std::is_same<T, float>::value && !kComplexBranch &&
                             (st.route & RFI_TILE_RAW_THRESHOLDS) != 0;
-    auto pass_a = [&](auto fast_tag) {
+    // kMag (fast route, complex input through the real branch): phase 1 left the tile's exact
+    // magnitudes in its scratch, row-major -- read 4 B / px from there instead of 8 B / px + |z|
+    auto pass_a = [&](auto fast_tag, auto mag_tag) {
         constexpr bool kFast = decltype(fast_tag)::value;
+        constexpr bool kMag = decltype(mag_tag)::value;
+        using Raw = typename std::conditional<kMag, RawSample<RFI_F32>, RawSample<DT>>::type;
+        constexpr int RDT = kMag ? RFI_F32 : DT;
+        const void* src = kMag ? static_cast<const void*>(mag_scratch + (size_t)tile * (kP * kP)) : data;
+        const size_t src_origin = kMag ? 0 : origin;
+        const size_t src_pitch = kMag ? (size_t)kP : (size_t)p.times;
         [[maybe_unused]] const float raw_lo = (float)st.raw_lo, raw_hi = (float)st.raw_hi;
         [[maybe_unused]] const float rm = (p.norm_before && med_before > T(0)) ? 1.0f / (float)med_before : 1.0f;
         [[maybe_unused]] const float rm2 = (p.norm_after && med_after > T(0)) ? 1.0f / (float)med_after : 1.0f;
-        RawSample<DT> cur[Q], nxt[Q];
+        Raw cur[Q], nxt[Q];
 #pragma unroll
         for (int q = 0; q < Q; ++q)
-            cur[q] = load_raw<DT>(data, origin + (size_t)warp * p.times + lane + 32 * q);
+            cur[q] = load_raw<RDT>(src, src_origin + (size_t)warp * src_pitch + lane + 32 * q);
 #pragma unroll 1
         for (int s = 0; s < STEPS; ++s) {
             const int row = s * RS + warp;
             if (s + 1 < STEPS) {
 #pragma unroll
                 for (int q = 0; q < Q; ++q)
-                    nxt[q] = load_raw<DT>(data, origin + (size_t)(row + RS) * p.times + lane + 32 * q);
+                    nxt[q] = load_raw<RDT>(src, src_origin + (size_t)(row + RS) * src_pitch + lane + 32 * q);
             }
             unsigned char fl[Q];
 #pragma unroll
@@ -372,7 +381,7 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
                 unsigned char f = fl[q];
                 T L;
                 if constexpr (kFast) {
-                    raw_to_mag_fast<DT>(cur[q], a);
+                    raw_to_mag_fast<RDT>(cur[q], a);
                     ph = T(0);
                     if (p.flag_mode == RFI_FLAGS_MAD) f = ((a > (T)raw_hi) || (a < (T)raw_lo)) ? 1 : 0;
                     float y;
@@ -388,7 +397,7 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
                     y = y * rm2;
                     L = (T)(lg2_fast(y + 1e-10f) * 0.30102999566f);
                 } else {
-                    raw_to_mag<DT, kComplexBranch>(cur[q], a, ph);
+                    if constexpr (!kMag) raw_to_mag<DT, kComplexBranch>(cur[q], a, ph);
                     T x = a;
                     if (real_branch) x = process_sample<T>(a, p, med_before, inf_fill, med_after);
                     if (p.flag_mode == RFI_FLAGS_MAD) f = ((x > thr_hi) || (x < thr_lo)) ? 1 : 0;
@@ -412,8 +421,14 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
             for (int q = 0; q < Q; ++q) cur[q] = nxt[q];
         }
     };
-    if (fast_route) pass_a(std::true_type{});
-    else pass_a(std::false_type{});
+    bool done = false;
+    if constexpr (DT == RFI_C64 && !kComplexBranch) {
+        if (fast_route && mag_scratch != nullptr) { pass_a(std::true_type{}, std::true_type{}); done = true; }
+    }
+    if (!done) {
+        if (fast_route) pass_a(std::true_type{}, std::false_type{});
+        else pass_a(std::false_type{}, std::false_type{});
+    }
     __syncthreads();
 
     // ---- pass B: min/max of the squared gradient for each distinct rotation variant
@@ -576,14 +591,14 @@ static int launch_stats(const PlanDev& d, long long tiles, const void* data, con
 template <int DT, int NT, bool CB>
 static int launch_write(const PlanDev& d, long long tiles, const void* data, const uint8_t* flags,
                         const rfi_tile_stat_t* stats, const long long* dest, float* images,
-                        uint8_t* labels, cudaStream_t st) {
+                        uint8_t* labels, const float* mag_scratch, cudaStream_t st) {
     using T = typename In<DT>::T;
     auto kern = write_patches_kernel<DT, NT, CB>;
     size_t smem = (size_t)kP * Phase2Smem<T>::kPitch * sizeof(T) +
                   (CB ? (size_t)kP * Phase2Smem<T>::kPitch * sizeof(float) : 0) +
                   (size_t)kP * Phase2Smem<T>::kFlagPitch + (size_t)(NT / 32) * (3 * kP * sizeof(float));
     RFI_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)tiles, NT, smem, st>>>(d, data, flags, stats, dest, images, labels);
+    kern<<<(unsigned)tiles, NT, smem, st>>>(d, data, flags, stats, dest, images, labels, mag_scratch);
     return RFI_OK;
 }
 
@@ -667,16 +682,20 @@ extern "C" int rfi_write_patches(const rfi_plan_t* plan, const void* data, const
     if (!data || !stats || !dest_slot) { set_error("data / stats / dest_slot is NULL"); return RFI_E_INVALID; }
     if (d.flag_mode == RFI_FLAGS_CUSTOM && !flags) { set_error("custom flag mode needs flags"); return RFI_E_INVALID; }
     const bool cb = plan->dtype >= RFI_C64 && !plan->magnitude;
+    // complex64 through the real branch: the statistics kernel left every monotone tile's exact
+    // magnitudes in the workspace (row-major per tile); NULL = read the cube again
+    const bool need_data = d.flag_mode == RFI_FLAGS_MAD || (d.norm_before || d.norm_after || d.stretch != RFI_STRETCH_NONE);
+    const float* mag = (plan->dtype == RFI_C64 && plan->magnitude && need_data) ? static_cast<const float*>(workspace) : nullptr;
     switch (plan->dtype) {
-        case RFI_F32: rc = launch_write<RFI_F32, 512, false>(d, tiles, data, flags, stats, dest, images, labels, st); break;
-        case RFI_F64: rc = launch_write<RFI_F64, 512, false>(d, tiles, data, flags, stats, dest, images, labels, st); break;
+        case RFI_F32: rc = launch_write<RFI_F32, 512, false>(d, tiles, data, flags, stats, dest, images, labels, mag, st); break;
+        case RFI_F64: rc = launch_write<RFI_F64, 512, false>(d, tiles, data, flags, stats, dest, images, labels, mag, st); break;
         case RFI_C64:
-            rc = cb ? launch_write<RFI_C64, 1024, true>(d, tiles, data, flags, stats, dest, images, labels, st)
-                    : launch_write<RFI_C64, 512, false>(d, tiles, data, flags, stats, dest, images, labels, st);
+            rc = cb ? launch_write<RFI_C64, 1024, true>(d, tiles, data, flags, stats, dest, images, labels, mag, st)
+                    : launch_write<RFI_C64, 512, false>(d, tiles, data, flags, stats, dest, images, labels, mag, st);
             break;
         default:
-            rc = cb ? launch_write<RFI_C128, 256, true>(d, tiles, data, flags, stats, dest, images, labels, st)
-                    : launch_write<RFI_C128, 512, false>(d, tiles, data, flags, stats, dest, images, labels, st);
+            rc = cb ? launch_write<RFI_C128, 256, true>(d, tiles, data, flags, stats, dest, images, labels, mag, st)
+                    : launch_write<RFI_C128, 512, false>(d, tiles, data, flags, stats, dest, images, labels, mag, st);
             break;
     }
     if (rc) return rc;

@@ -284,9 +284,10 @@ class Preprocessor:
             if ev:
                 ev[1].record()
             self.last_tile_stats = stats
-            if fast:
-                # the fast path's scratch serves phase 1 only: hand its block back before the
-                # outputs are allocated (stream-ordered reuse)
+            if fast and not (is_complex and self.magnitude):
+                # real input: the fast path's scratch serves phase 1 only -- hand its block back
+                # before the outputs are allocated (stream-ordered reuse).  Complex input through
+                # the real branch keeps it: phase 2 reads the exact magnitudes phase 1 left there.
                 work, wptr = None, None
 
             # ---- host: blank-patch compaction + shuffle -> destination slot of every patch
