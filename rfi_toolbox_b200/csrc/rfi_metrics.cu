@@ -90,7 +90,9 @@ RFI_DEVINL void count_range(const void* pred, const void* truth, long long begin
         // byte masks (the common case): four 128-bit loads per operand in flight per thread, and the
         // counts taken byte-parallel -- high bit of every non-zero byte, three popcounts per word
         constexpr int U = 4;
-        auto hb = [](uint32_t v) { return (((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u; };
+        // 0x01 in every non-zero byte; the three sums are then byte dot products (dp4a): p.t, p.1, t.1
+        auto nz01 = [](uint32_t v) { return ((((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u) >> 7; };
+        unsigned npc = 0, ntc = 0;  // predicted / true positives; FP = P - TP, FN = T - TP
         for (; s0 + (U - 1) * nthreads < body; s0 += U * nthreads) {
             uint4 a[U], b[U];
 #pragma unroll
@@ -100,12 +102,17 @@ RFI_DEVINL void count_range(const void* pred, const void* truth, long long begin
                 const uint32_t pw[4] = {a[k].x, a[k].y, a[k].z, a[k].w}, tw[4] = {b[k].x, b[k].y, b[k].z, b[k].w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const uint32_t p = hb(pw[i]), t = hb(tw[i]);
-                    tpc += __popc(p & t); fpc += __popc(p & ~t); fnc += __popc(~p & t);
+                    const uint32_t p = nz01(pw[i]), t = nz01(tw[i]);
+                    tpc = __dp4a(p, t, tpc); npc = __dp4a(p, 0x01010101u, npc); ntc = __dp4a(t, 0x01010101u, ntc);
                 }
             }
-            if ((++iter & 1023) == 0) { tp += tpc; fp += fpc; fn += fnc; tpc = fpc = fnc = 0; }
+            if ((++iter & 1023) == 0) {
+                tp += tpc; fp += npc - tpc; fn += ntc - tpc;
+                tpc = npc = ntc = 0;
+            }
         }
+        tp += tpc; fp += npc - tpc; fn += ntc - tpc;
+        tpc = 0;
     }
     for (long long s = s0; s < body; s += nthreads) {
         uint32_t mp = 0, mt = 0;
