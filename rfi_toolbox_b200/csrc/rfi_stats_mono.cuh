@@ -13,17 +13,19 @@
 //     with two compares on the raw sample, no division or square root.
 //
 // Selection is Floyd-Rivest style instead of bit-by-bit: a stratified 512-sample (every row and
-// every column of the tile contributes 4 samples) is sorted by ONE warp in registers (bitonic,
-// shuffles); two sample ranks 3 sigma either side of the target bracket it; one pass over
-// the 16384 keys in shared memory counts what lies below the bracket and compacts the ~2300
-// keys inside it; the exact rank inside that list is resolved by a 512-bucket linear
-// histogram + one <= 64 element ranking.  All brackets are validated (the answer must fall
-// strictly inside what was proven), otherwise the tile is handed to the general kernel
-// (tile_stats_general, RFI_TILE_GENERAL), which then runs in the same CTA -- results are exact
-// either way.
+// every column of the tile contributes 4 samples) is sorted (four warps sort 128 keys each in
+// registers, then every thread ranks one key in the other three runs); two sample ranks 3 sigma
+// either side of the target bracket it; one pass over the 16384 keys counts what lies below the
+// bracket and compacts the ~2300 keys inside it; the exact rank inside that list is resolved by
+// a 512-bucket linear histogram + one <= 64 element ranking.  All brackets are validated (the
+// answer must fall strictly inside what was proven), otherwise the tile is handed to the general
+// kernel (tile_stats_general, RFI_TILE_GENERAL), which then runs in the same CTA -- results are
+// exact either way.
 //
-// Cost: ~45 k warp instructions per tile instead of ~150 k for the 32-round register
-// bisection; keys live in shared memory (64 KB per float32 tile, 2 CTAs / SM).
+// Cost: ~80 k warp instructions per tile instead of ~150 k for the 32-round register bisection
+// (a third of them the NumPy-exact |z|).  float32 keys: half in shared memory, half in a
+// thread-private global scratch (57 KB of shared memory per CTA, 3 CTAs / SM; see the kernel);
+// float64 keys: all in shared memory, 1 CTA / SM.
 #pragma once
 #include "rfi_tiles.cuh"
 

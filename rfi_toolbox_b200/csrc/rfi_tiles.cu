@@ -1,13 +1,16 @@
-// rfi_tiles.cu -- the create_dataset hot path on sm_100a.
+// rfi_tiles.cu -- the create_dataset hot path on sm_100a, P = 128.
 //
-//   phase 1  tile_stats_kernel   one CTA per ORIGINAL P x P tile: load (complex -> magnitude
-//            fused into the 128-bit load), exact median / MAD by register-resident binary
-//            radix select, flag thresholds, flagged-sample count.
-//   (host)   keep mask -> np.random.permutation -> dest_slot[]        (Python)
-//   phase 2  write_patches_kernel one CTA per original tile: recompute the processed tile from
-//            the phase-1 statistics, log-amplitude tile in shared memory, gradient min/max,
-//            then every kept rotation is written as (P, P, 3) float32 + (P, P) uint8 with
-//            full-sector 128-bit stores.
+//   phase 1  tile_stats_mono_kernel (rfi_stats_mono.cuh)  one CTA per ORIGINAL P x P tile: load
+//            (complex -> NumPy-exact magnitude fused into the 128-bit loads), exact median / MAD by
+//            sampled brackets on the raw keys, flag thresholds mapped back exactly to the raw
+//            domain, flagged-sample count; tile_stats_general (below, same CTA) for tiles with
+//            negative / infinite / inf-filled samples or a missed bracket.  For complex input
+//            through the real branch the exact magnitudes stay in the workspace for phase 2.
+//   (host)   keep mask -> np.random.permutation -> dest_slot[]        (rfi_host.cpp)
+//   phase 2  write_patches_kernel one CTA per original tile: log-amplitude tile in shared memory
+//            (labels = two compares with the raw thresholds), gradient min/max, then every kept
+//            rotation is written as (P, P, 3) float32 + (P, P) uint8 with full-sector 128-bit
+//            stores, each patch once, at its final shuffled slot.
 //
 // Reference semantics: rfi_toolbox/preprocessing/preprocessor.py:22-42, 413-446, 562-783
 // (restated in SURVEY.md Appendix A).  Statistics are rotation invariant for dims divisible
