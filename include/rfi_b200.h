@@ -50,13 +50,16 @@ extern "C" {
 #define RFI_FLAGS_MAD 1       /* median +- sigma * MAD of the processed patch */
 #define RFI_FLAGS_INFERENCE 2 /* all-zero labels */
 
-/* Plan of one create_dataset call over a cube (B, Npol, C, T), C-order.
- * Fast path (one CTA per tile, tile resident on chip): P = 128, C and T multiples of P.
- * Every other geometry -- P = 256 / 512 / 1024 or any other size, C or T not a multiple of
- * P (the reference zero-pads bottom/right after the rotation, preprocessor.py:527-550),
- * waterfalls no larger than the patch (patchify skipped, preprocessor.py:261-269) -- runs
- * on the generic path (segmented multi-pass radix select over global memory) and needs the
- * workspace rfi_plan_workspace_bytes() reports. */
+/* Plan of one create_dataset call over a cube (B, Npol, C, T), C-order.  Three code paths
+ * (rfi_plan_path), same results:
+ *   fast     P = 128, C and T multiples of P: one CTA per tile, tile resident on chip;
+ *   big      P = 256 / 512 / 1024, C and T multiples of P, float32 / complex64 through the real
+ *            branch: sub-tile + group launches, 4-CTA cluster writer;
+ *   generic  any other size, C or T not a multiple of P (the reference zero-pads bottom/right after
+ *            the rotation, preprocessor.py:527-550), waterfalls no larger than the patch (patchify
+ *            skipped, preprocessor.py:261-269), float64 at P >= 256: segmented multi-pass radix
+ *            select over global memory.
+ * All of them take the workspace rfi_plan_workspace_bytes() reports. */
 typedef struct rfi_plan {
     int32_t dtype;       /* RFI_F32 .. RFI_C128 */
     int32_t magnitude;   /* complex input only: 1 = take |z| on load and run the real branch
@@ -129,8 +132,9 @@ size_t rfi_plan_workspace_bytes(const rfi_plan_t* plan);
  *   stats  device, rfi_plan_num_tiles() entries, written
  *   workspace device, rfi_plan_workspace_bytes() bytes (NULL when that is 0); the same buffer,
  *          untouched in between, must be passed to rfi_write_patches
- * One CTA per original tile; tile resident in registers, order statistics by
- * register-resident MSB-first binary radix select. */
+ * P = 128: one CTA per original tile, exact order statistics by sampled brackets on the raw keys
+ * (register-resident radix select as the in-CTA fallback).  P = 256 / 512 / 1024: the same
+ * selection split over sub-tile and group launches.  Everything else: segmented radix select. */
 int rfi_tile_stats(const rfi_plan_t* plan, const void* data, const uint8_t* flags,
                    rfi_tile_stat_t* stats, void* workspace, void* stream);
 
