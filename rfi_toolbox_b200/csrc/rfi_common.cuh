@@ -44,7 +44,9 @@ template <> struct Scalar<float> {
     // log10 of a float32, correctly rounded in practice (fp64 evaluation, one final rounding).
     // NumPy's float32 log10 is SVML on AVX-512 hosts (<= 3 ulp off); see DESIGN.md "numerics".
     RFI_DEVINL static float log10_(float x) { return (float)::log10((double)x); }
-    RFI_DEVINL static float atan2_(float y, float x) { return (float)::atan2((double)y, (double)x); }
+    // phase channel only (tolerance class: NumPy's float32 arctan2 is SVML, a few ulp): CUDA's atan2f
+    // (<= 2 ulp) instead of a float64 evaluation -- the complex-branch writer was bound by it
+    RFI_DEVINL static float atan2_(float y, float x) { return ::atan2f(y, x); }
 };
 template <> struct Scalar<double> {
     using key_t = unsigned long long;
