@@ -412,9 +412,10 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
                 if (slot0 >= 0) labels[(size_t)slot0 * kP * kP + (size_t)row * kP + col] = f;
                 if (slot1 >= 0) labels[(size_t)slot1 * kP * kP + (size_t)(kP - 1 - row) * kP + col] = f;
                 if constexpr (kComplexBranch) {
-                    // (phase + pi) / (2 pi) in T, cast to float32, then ImageNet (rotation invariant)
-                    T c2 = (ph + T(3.141592653589793)) / T(6.283185307179586);
-                    Ph[row * LP + col] = ((float)c2 - mean2) / std2;
+                    // (phase + pi) / (2 pi), then ImageNet (rotation invariant); tolerance class like the
+                    // other channels: reciprocal multiplies and one fma instead of two IEEE divisions
+                    const float c2 = (float)((ph + T(3.141592653589793)) * T(1.0 / 6.283185307179586));
+                    Ph[row * LP + col] = __fmaf_rn(c2, 1.0f / std2, nb2);
                 } else {
                     llo = Scalar<T>::fmin_nan(llo, L);
                     lhi = Scalar<T>::fmax_nan(lhi, L);
