@@ -44,6 +44,23 @@ WORKLOADS = {
                name="configs[4] (8-baseline chunk of one of 8 baseline shards)"),
 }
 METRIC = "waterfall Gpixel/s (create_dataset+metrics)"
+_JSON_FD = None  # the real stdout; fd 1 itself is pointed at stderr while the benchmark runs
+
+
+def _reserve_stdout():
+    """stdout must carry exactly ONE JSON line, but libraries write there too (NCCL prints its
+    version banner / NCCL_DEBUG output to stdout): keep a private handle on the real stdout and
+    send everything else that is written to fd 1 to stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + "\n").encode())
 ACTIVE = WORKLOAD  # set from --workload in main(); inherited by the forked CPU-baseline workers
 
 
@@ -107,7 +124,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "Gpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
@@ -182,7 +199,6 @@ def run_ours(args):
     from rfi_toolbox_b200.utils.device import bind_host_to_device
     cpus = bind_host_to_device(dev) if world > 1 else None  # pinned host buffers on the GPU's own socket
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     group = True if world > 1 else None
 
@@ -333,7 +349,7 @@ def run_ours(args):
         "host_affinity": (f"{len(cpus)} cores near GPU {local}" if cpus else None),
         "clocks": clocks, "wall_s": wall, "metrics_last_step": {k_: float(v) for k_, v in m.items()},
     }
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -350,6 +366,7 @@ def main():
     args = ap.parse_args()
     global ACTIVE
     ACTIVE = WORKLOADS[args.workload]
+    _reserve_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
