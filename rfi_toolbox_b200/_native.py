@@ -9,7 +9,10 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "_lib" / "librfi_b200.so"
+import os
+
+# RFI_B200_LIB: another build of the same library (kernel A/B experiments); default = the in-tree one
+LIB_PATH = Path(os.environ.get("RFI_B200_LIB") or Path(__file__).resolve().parent / "_lib" / "librfi_b200.so")
 
 RFI_F32, RFI_F64, RFI_C64, RFI_C128 = 0, 1, 2, 3
 RFI_STRETCH_NONE, RFI_STRETCH_SQRT, RFI_STRETCH_LOG10 = 0, 1, 2
