@@ -288,6 +288,15 @@ int rfi_raw_gather(const void* data, int dtype, const uint8_t* flags, int64_t n_
                    int64_t channels, int64_t times, int32_t patch, const int64_t* dest_slot,
                    void* patches, uint8_t* masks, void* stream);
 
+/* Rotated, zero-padded copies of the waterfalls -- view `rotation` of _apply_rotations
+ * (preprocessor.py:413-446: 0 = X, 1 = X[::-1, :], 2 = X.T, 3 = X.T[::-1, :]) followed by the bottom /
+ * right zero pad of _create_patches (:527-550).  A geometry whose dims are not multiples of P then runs
+ * through the on-chip kernels as single-view plans over these copies.
+ *   in   device (n_waterfalls, channels, times), elements of elem_bytes (1, 4, 8 or 16)
+ *   out  device (n_waterfalls, out_rows, out_cols) >= the rotated view, written */
+int rfi_rotate_pad(const void* in, void* out, int elem_bytes, int64_t n_waterfalls, int64_t channels,
+                   int64_t times, int64_t out_rows, int64_t out_cols, int rotation, void* stream);
+
 /* Self test (used by tests/): counts the inputs t in [1, 2] (all 2^23 + 1 float32 values) for
  * which the range-restricted square root of the magnitude kernel differs from sqrt.rn.f32.
  *   mismatches_dev  device uint64, ACCUMULATED into (caller zeroes); must end up 0 */

@@ -85,6 +85,7 @@ SYMBOLS = {
     "rfi_raw_num_tiles": (_I64, [_I, _I64, _I64, _I64, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "rfi_raw_tile_counts": (_I, [_VP, _I, _VP, _I64, _I64, _I64, C.c_int32, _VP, _VP]),
     "rfi_raw_gather": (_I, [_VP, _I, _VP, _I64, _I64, _I64, C.c_int32, _VP, _VP, _VP, _VP]),
+    "rfi_rotate_pad": (_I, [_VP, _VP, _I, _I64, _I64, _I64, _I64, _I64, _I, _VP]),
     "rfi_selftest_sqrt_unit": (_I, [_VP, _VP]),
     "rfi_last_error_string": (C.c_char_p, []),
     "rfi_abi_version": (_I, []),

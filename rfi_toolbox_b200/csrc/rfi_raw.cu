@@ -5,6 +5,8 @@
 // mask tiles (the caller's flags, or |z| > 0 when none are given, :881-883), blank tiles dropped
 // (:904-913) and the survivors written ONCE at their final shuffled position -- a tiled gather,
 // 2 x (element + 1) bytes of HBM traffic per kept sample.
+#include <string.h>
+
 #include "rfi_common.cuh"
 
 namespace rfi {
@@ -133,6 +135,75 @@ extern "C" int rfi_raw_gather(const void* data, int dtype, const uint8_t* flags,
     const dim3 grid((unsigned)tiles, (unsigned)chunks);
     if (g.esize == 8) raw_gather_kernel<8><<<grid, kRawThreads, 0, (cudaStream_t)stream>>>(g, data, flags, dest, patches, masks);
     else raw_gather_kernel<16><<<grid, kRawThreads, 0, (cudaStream_t)stream>>>(g, data, flags, dest, patches, masks);
+    RFI_CUDA_TRY(cudaGetLastError());
+    return RFI_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rotated, zero-padded copies of the waterfalls (preprocessor.py:413-446 `_apply_rotations`, then the
+// bottom / right zero pad of `_create_patches`, :527-550, which FOLLOWS the flip / transpose): view r
+// of every waterfall, padded to multiples of P, so that a geometry whose dims are not multiples of P
+// can run through the on-chip kernels as four single-view plans (every rotated patch is its own
+// statistics group there).  r0: X, r1: X[::-1, :], r2: X.T, r3: X.T[::-1, :].
+namespace rfi {
+
+template <typename V>
+__global__ void __launch_bounds__(256)
+rotate_pad_kernel(const V* __restrict__ in, V* __restrict__ out, long long C, long long T, long long Cp, long long Tp, int r) {
+    // out is (W, Cp, Tp); 32 x 32 tiles through shared memory so that the transposed views read AND
+    // write rows
+    __shared__ V tile[32][33];
+    const long long w = blockIdx.z;
+    const long long y0 = (long long)blockIdx.y * 32, x0 = (long long)blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const V* src = in + (size_t)w * C * T;
+    V* dst = out + (size_t)w * Cp * Tp;
+    V zero;
+    memset(&zero, 0, sizeof(V));
+    if (r <= 1) {
+        for (int k = ty; k < 32; k += 8) {
+            const long long y = y0 + k, x = x0 + tx;
+            if (y < Cp && x < Tp) {
+                const long long sy = (r == 0) ? y : C - 1 - y;
+                dst[(size_t)y * Tp + x] = (y < C && x < T) ? src[(size_t)sy * T + x] : zero;
+            }
+        }
+        return;
+    }
+    // transposed views: out[y][x] = X[x][y'] with y' = y (r2) or T - 1 - y (r3); y < T, x < C
+    for (int k = ty; k < 32; k += 8) {          // read a 32 x 32 block of X by rows of X
+        const long long sx = x0 + k;            // row of X  (= output column)
+        const long long oy = y0 + tx;           // output row
+        const long long sy = (r == 2) ? oy : T - 1 - oy;  // column of X
+        tile[k][tx] = (sx < C && oy < T) ? src[(size_t)sx * T + sy] : zero;
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        const long long y = y0 + k, x = x0 + tx;
+        if (y < Cp && x < Tp) dst[(size_t)y * Tp + x] = tile[tx][k];
+    }
+}
+
+}  // namespace rfi
+
+extern "C" int rfi_rotate_pad(const void* in, void* out, int elem_bytes, int64_t n_waterfalls, int64_t channels,
+                              int64_t times, int64_t out_rows, int64_t out_cols, int rotation, void* stream) {
+    if (rotation < 0 || rotation > 3) { set_error("rotation must be 0..3"); return RFI_E_INVALID; }
+    if (n_waterfalls < 0 || channels <= 0 || times <= 0) { set_error("bad shape"); return RFI_E_INVALID; }
+    const int64_t need_r = rotation <= 1 ? channels : times, need_c = rotation <= 1 ? times : channels;
+    if (out_rows < need_r || out_cols < need_c) { set_error("padded shape smaller than the rotated view"); return RFI_E_INVALID; }
+    if (n_waterfalls == 0) return RFI_OK;
+    if (!in || !out) { set_error("NULL buffer"); return RFI_E_INVALID; }
+    if (n_waterfalls > 65535 || (out_rows + 31) / 32 > 65535) { set_error("too many waterfalls / rows per call"); return RFI_E_UNSUPPORTED; }
+    const dim3 grid((unsigned)((out_cols + 31) / 32), (unsigned)((out_rows + 31) / 32), (unsigned)n_waterfalls);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (elem_bytes) {
+        case 1: rotate_pad_kernel<uint8_t><<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(in), static_cast<uint8_t*>(out), channels, times, out_rows, out_cols, rotation); break;
+        case 4: rotate_pad_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(in), static_cast<float*>(out), channels, times, out_rows, out_cols, rotation); break;
+        case 8: rotate_pad_kernel<float2><<<grid, 256, 0, st>>>(static_cast<const float2*>(in), static_cast<float2*>(out), channels, times, out_rows, out_cols, rotation); break;
+        case 16: rotate_pad_kernel<double2><<<grid, 256, 0, st>>>(static_cast<const double2*>(in), static_cast<double2*>(out), channels, times, out_rows, out_cols, rotation); break;
+        default: set_error("element size %d not supported", elem_bytes); return RFI_E_INVALID;
+    }
     RFI_CUDA_TRY(cudaGetLastError());
     return RFI_OK;
 }

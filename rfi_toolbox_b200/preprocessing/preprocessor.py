@@ -240,6 +240,15 @@ class Preprocessor:
         nh, nw = (1, 1) if skip_patchify else (-(-C_ // P), -(-T_ // P))
         ws_bytes = int(lib.rfi_plan_workspace_bytes(C.byref(plan)))
 
+        views = self._view_plans(lib, plan, R, C_, T_, P) if padded else None
+        if views is not None:
+            if host is not None:
+                data = host.to(device, non_blocking=True)
+            images, labels, order = self._create_padded(lib, device, plan, views, data, flags, R, B * npol, C_, T_, P,
+                                                        inference_mode, num_patches)
+            return self._finish(images, labels, order, patch_size, stretch, flag_sigma, normalize_before_stretch,
+                                normalize_after_stretch, augmentation_rotations)
+
         with torch.cuda.device(device):
             stream = current_stream_ptr(device)
             fptr = flags.data_ptr() if flags is not None else None
@@ -323,6 +332,89 @@ class Preprocessor:
                 logger.warning("No flagged patches found - keeping all patches")
             order = hb["order_np"][:n_out].copy()
 
+        return self._finish(images, labels, order, patch_size, stretch, flag_sigma, normalize_before_stretch,
+                            normalize_after_stretch, augmentation_rotations)
+
+    # ---------------------------------------------------------------- zero-padded geometries
+    @staticmethod
+    def _view_plans(lib, plan, R, C_, T_, P):
+        """Dims that are not multiples of P: the reference pads every ROTATED view bottom / right
+        (preprocessor.py:527-550), so each rotated patch is its own statistics group.  If a
+        single-view plan over the padded view takes one of the on-chip paths, run the R views as
+        R such plans over rotated, zero-padded copies (`rfi_rotate_pad`) instead of the generic
+        path.  -> list of (plan_r, rows, cols) or None."""
+        Cp, Tp = -(-C_ // P) * P, -(-T_ // P) * P
+        out = []
+        for r in range(R):
+            rows, cols = (Cp, Tp) if r <= 1 else (Tp, Cp)
+            pr = _native.RfiPlan.from_buffer_copy(plan)
+            pr.channels, pr.times, pr.rotations = rows, cols, 1
+            if lib.rfi_plan_path(C.byref(pr)) == _native.RFI_PATH_GENERIC:
+                return None
+            out.append((pr, rows, cols))
+        return out
+
+    def _create_padded(self, lib, device, plan, views, data, flags, R, n_wf, C_, T_, P, inference_mode, num_patches):
+        per = (-(-C_ // P)) * (-(-T_ // P))
+        n0 = n_wf * R * per
+        with torch.cuda.device(device):
+            stream = current_stream_ptr(device)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if self.profile else None
+            if ev:
+                ev[0].record()
+            state = []
+            for r, (pr, rows, cols) in enumerate(views):
+                rot = torch.empty((n_wf, rows, cols), dtype=data.dtype, device=device)
+                _native.check(lib.rfi_rotate_pad(data.data_ptr(), rot.data_ptr(), data.element_size(), n_wf, C_, T_,
+                                                 rows, cols, r, stream), "rfi_rotate_pad")
+                frot = None
+                if flags is not None:
+                    frot = torch.empty((n_wf, rows, cols), dtype=torch.uint8, device=device)
+                    _native.check(lib.rfi_rotate_pad(flags.data_ptr(), frot.data_ptr(), 1, n_wf, C_, T_, rows, cols,
+                                                     r, stream), "rfi_rotate_pad")
+                stats = torch.empty((n_wf * per, _native.TILE_STAT_BYTES), dtype=torch.uint8, device=device)
+                ws = int(lib.rfi_plan_workspace_bytes(C.byref(pr)))
+                work = torch.empty(ws, dtype=torch.uint8, device=device) if ws else None
+                _native.check(lib.rfi_tile_stats(C.byref(pr), rot.data_ptr(), frot.data_ptr() if frot is not None else None,
+                                                 stats.data_ptr(), work.data_ptr() if work is not None else None, stream),
+                              "rfi_tile_stats")
+                state.append((pr, rot, frot, stats, work))
+            if ev:
+                ev[1].record()
+            # canonical order of a padded geometry: [waterfall][view][tile of the rotated grid]
+            hb = _host_buffers(device, max(n0, 1), max(n0, 1))
+            hb["copied"].synchronize()
+            nflag = None
+            if not inference_mode:
+                counts = torch.stack([st[3].view(torch.int32)[:, 16].reshape(n_wf, per) for st in state], dim=1)
+                hb["nflag"][:n0].copy_(counts.reshape(-1), non_blocking=True)
+                hb["event"].record()
+                hb["event"].synchronize()
+                nflag = hb["nflag_np"][:n0]
+            n_out = _native.plan_slots(plan, nflag, not inference_mode, num_patches, hb["order_np"], hb["dest_np"])
+            dest = hb["dest"][:n0].to(device, non_blocking=True).view(n_wf, R, per)
+            hb["copied"].record()
+            images = torch.empty((n_out, P, P, 3), dtype=torch.float32, device=device)
+            labels = torch.empty((n_out, P, P), dtype=torch.uint8, device=device)
+            if ev:
+                ev[2].record()
+            for r, (pr, rot, frot, stats, work) in enumerate(state):
+                dest_r = dest[:, r, :].contiguous()
+                _native.check(lib.rfi_write_patches(C.byref(pr), rot.data_ptr(), frot.data_ptr() if frot is not None else None,
+                                                    stats.data_ptr(), dest_r.data_ptr(), images.data_ptr(), labels.data_ptr(),
+                                                    work.data_ptr() if work is not None else None, stream),
+                              "rfi_write_patches")
+            if ev:
+                ev[3].record()
+                self.events = {"stats": (ev[0], ev[1]), "write": (ev[2], ev[3])}
+            if not inference_mode and nflag is not None and not (nflag > 0).any():
+                logger.warning("No flagged patches found - keeping all patches")
+            order = hb["order_np"][:n_out].copy()
+            self.last_tile_stats = torch.stack([st[3].view(n_wf, per, -1) for st in state], dim=1).reshape(n0, -1)
+        return images, labels, order
+
+    def _finish(self, images, labels, order, patch_size, stretch, flag_sigma, normalize_before_stretch,
+                normalize_after_stretch, augmentation_rotations):
         self.order = order  # canonical index of every output patch (not in the reference)
         self.patch_flags = labels
         self.patches = None  # processed patches are never materialised on this path

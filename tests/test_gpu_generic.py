@@ -109,3 +109,20 @@ def test_generic_matches_fast_path_statistics(native_lib):
     torch.cuda.synchronize()
     assert a.labels.shape == (1, 256, 256) and b.labels.shape[1:] == (128, 128)
     assert int(a.labels[0, 17].sum()) == 256
+
+
+def test_padded_p128_takes_the_on_chip_kernels(native_lib):
+    """Dims that are not multiples of 128 run as one single-view plan per rotation over rotated,
+    zero-padded copies (`rfi_rotate_pad`), i.e. through the P = 128 kernels: their tile statistics
+    carry a route bit, the generic path's do not."""
+    from tests.test_gpu_bigtile import _routes
+    data, _ = make_cube(n_bl=2, n_pol=2, channels=200, times=300, dtype=np.complex64, seed=67)
+    kw = dict(patch_size=128, **MAD_SQRT)
+    pre, ds = _run_gpu(data, None, magnitude=True, **kw)
+    ods, inter = _run_oracle(data, None, magnitude=True, **kw)
+    _compare(ds, ods, inter, pre)
+    st = _routes(pre)
+    assert len(st) == 2 * 2 * 4 * 2 * 3 and (st["route"] & 3).all()
+    # an odd patch size still takes the generic path
+    pre2, _ = _run_gpu(data, None, magnitude=True, patch_size=100, **MAD_SQRT)
+    assert not (_routes(pre2)["route"] & 3).any()
