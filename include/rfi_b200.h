@@ -58,7 +58,9 @@ extern "C" {
  *   generic  any other size, C or T not a multiple of P (the reference zero-pads bottom/right after
  *            the rotation, preprocessor.py:527-550), waterfalls no larger than the patch (patchify
  *            skipped, preprocessor.py:261-269), float64 at P >= 256: segmented multi-pass radix
- *            select over global memory.
+ *            select over global memory.  (A caller can keep a padded geometry on the fast / big
+ *            kernels by running one rotations = 1 plan per view over rfi_rotate_pad copies -- the
+ *            Python layer does.)
  * All of them take the workspace rfi_plan_workspace_bytes() reports. */
 typedef struct rfi_plan {
     int32_t dtype;       /* RFI_F32 .. RFI_C128 */
