@@ -141,3 +141,15 @@ def test_degenerate_tiles_match_oracle(native_lib, patch, stretch):
     pre, ds = _run_gpu(data, None, **kw)
     ods, inter = _run_oracle(data, None, **kw)
     _compare(ds, ods, inter, pre)
+
+
+@pytest.mark.parametrize("rot", [2, 4])
+def test_p256_padded_views(native_lib, rot):
+    """Dims that are not multiples of 256: one single-view big-tile plan per rotation over rotated,
+    zero-padded copies; every rotated patch is its own statistics group (preprocessor.py:527-550)."""
+    data, _ = make_cube(n_bl=1, n_pol=2, channels=300, times=600, dtype=np.complex64, seed=93)
+    kw = dict(patch_size=256, stretch="SQRT", flag_sigma=4, use_custom_flags=False, augmentation_rotations=rot)
+    pre, ds = _run_gpu(data, None, magnitude=True, **kw)
+    ods, inter = _run_oracle(data, None, magnitude=True, **kw)
+    _compare(ds, ods, inter, pre)
+    assert (_routes(pre)["route"] & 3).all()
