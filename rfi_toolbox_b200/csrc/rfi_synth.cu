@@ -18,7 +18,9 @@
 //   pol >= 2  = N(noise, 0.1 noise), unflagged                               (:616-636)
 //   out       = pol_real * exp(i * U(0, 2 pi)), complex64                    (:639-640)
 //
-// HBM-bound by construction: 9 bytes written per (pixel, pol), nothing of cube size read.
+// 9 bytes written per (pixel, pol), nothing of cube size read.  Measured (45 x 4 x 1024 x 1024):
+// 0.77 ms, 2.1 TB/s -- issue-bound (77 % issue-active: two Philox4x32-10 blocks, two Box-Muller
+// pairs and four sincos per pixel), i.e. 245 Gpix/s, far from the critical path of any bench.
 #include "rfi_common.cuh"
 
 namespace rfi {
