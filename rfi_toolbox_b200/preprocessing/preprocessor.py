@@ -364,14 +364,16 @@ class Preprocessor:
                 ev[0].record()
             state = []
             for r, (pr, rows, cols) in enumerate(views):
-                rot = torch.empty((n_wf, rows, cols), dtype=data.dtype, device=device)
-                _native.check(lib.rfi_rotate_pad(data.data_ptr(), rot.data_ptr(), data.element_size(), n_wf, C_, T_,
-                                                 rows, cols, r, stream), "rfi_rotate_pad")
-                frot = None
-                if flags is not None:
-                    frot = torch.empty((n_wf, rows, cols), dtype=torch.uint8, device=device)
-                    _native.check(lib.rfi_rotate_pad(flags.data_ptr(), frot.data_ptr(), 1, n_wf, C_, T_, rows, cols,
-                                                     r, stream), "rfi_rotate_pad")
+                def rotate(src, esize, dtype):
+                    dst = torch.empty((n_wf, rows, cols), dtype=dtype, device=device)
+                    for w0 in range(0, n_wf, 65535):  # grid.z limit of one launch
+                        nw_ = min(65535, n_wf - w0)
+                        _native.check(lib.rfi_rotate_pad(src.data_ptr() + w0 * C_ * T_ * esize,
+                                                         dst.data_ptr() + w0 * rows * cols * esize, esize, nw_, C_, T_,
+                                                         rows, cols, r, stream), "rfi_rotate_pad")
+                    return dst
+                rot = rotate(data, data.element_size(), data.dtype)
+                frot = rotate(flags, 1, torch.uint8) if flags is not None else None
                 stats = torch.empty((n_wf * per, _native.TILE_STAT_BYTES), dtype=torch.uint8, device=device)
                 ws = int(lib.rfi_plan_workspace_bytes(C.byref(pr)))
                 work = torch.empty(ws, dtype=torch.uint8, device=device) if ws else None
