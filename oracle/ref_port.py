@@ -190,6 +190,39 @@ def extract_channels_complex(patch):
         return np.stack([_minmax(g), ch1, ch2], axis=-1)
 
 
+def images_exact64(patches):
+    """The channel extraction + ImageNet step (preprocessor.py:562-644, 765-783) evaluated in
+    FLOAT64 on the given processed patches (their float32 / complex64 values taken as exact).
+
+    Not the reference's arithmetic -- a yardstick for it: NumPy's float32 `log10`, `arctan2`
+    and the four rounded steps of min-max + ImageNet normalisation sit within a few ulp of this
+    chain, but the per-patch min-max divides that noise by (hi - lo), so the distance between
+    ANY two correct float32 implementations is `noise / (hi - lo) / std`, not 1e-6 relative.
+    Tests measure |reference - exact64| (NumPy's own noise) and require the CUDA path to stay
+    within the same distance of it.  Returns float64 (N, H, W, 3)."""
+    mean = IMAGENET_MEAN.astype(np.float64)
+    std = IMAGENET_STD.astype(np.float64)
+    # the reference subtracts / divides by the float32 constants
+    out = []
+    for patch in patches:
+        with np.errstate(all="ignore"):
+            if np.iscomplexobj(patch):
+                amp = np.abs(patch).astype(np.float64)      # np.abs(complex64) is reproduced bit-exactly
+                phase = np.arctan2(patch.imag.astype(np.float64), patch.real.astype(np.float64))
+            else:
+                amp, phase = np.abs(patch.astype(np.float64)), None
+            log_amp = np.log10(amp + 1e-10)
+            g = _gradient(log_amp)
+            if phase is not None:
+                ch1 = np.clip((log_amp + 3.0) / 7.0, 0, 1)
+                ch2 = (phase + np.pi) / (2 * np.pi)
+            else:
+                ch1, ch2 = _minmax(log_amp), np.zeros_like(log_amp)
+            img = np.stack([_minmax(g), ch1, ch2], axis=-1)
+        out.append((img - mean) / std)
+    return np.array(out, dtype=np.float64)
+
+
 # --------------------------------------------------------------------------- container
 class OracleDataset:
     """Duck-type of datasets/batched_dataset.py:10-45 holding NumPy arrays."""

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import logging
+import os
 import socket
 
 import torch
@@ -23,6 +24,13 @@ MAX_WORLD = 16
 
 
 class PeerContext:
+    """Exchange buffers of one (group, device).  Construction is COLLECTIVE and cannot diverge:
+    every rank always takes part in the one `all_gather_object` (publishing a failure marker
+    instead of raising before it) and in one `all_reduce(MIN)` of a success flag after the open
+    step, so either every rank ends up with `ok = True` or every rank ends up with `ok = False`
+    (and the caller all-reduces over NCCL on all of them).  On failure everything this rank
+    allocated or opened is released again."""
+
     def __init__(self, group, device):
         import torch.distributed as dist
         lib = _native.load()
@@ -31,30 +39,67 @@ class PeerContext:
         self.rank = dist.get_rank(group)
         self.device = device
         self.epoch = 0
+        self.ok = False
+        self.reason = None
+        self.ptrs = None
         self._own = C.c_void_p()
         self._opened = []
-        if self.world > MAX_WORLD:
-            raise RuntimeError(f"peer exchange supports at most {MAX_WORLD} ranks")
         with torch.cuda.device(device):
-            handle = (C.c_ubyte * 64)()
-            _native.check(lib.rfi_peer_alloc(C.byref(self._own), handle), "rfi_peer_alloc")
-            mine = (socket.gethostname(), bytes(handle))
+            handle, err = (C.c_ubyte * 64)(), None
+            try:
+                if self.world > MAX_WORLD:
+                    raise RuntimeError(f"peer exchange supports at most {MAX_WORLD} ranks")
+                if os.environ.get("RFI_PEER_FAIL_RANK") == str(self.rank):  # fault injection (tests)
+                    raise RuntimeError("injected failure (RFI_PEER_FAIL_RANK)")
+                _native.check(lib.rfi_peer_alloc(C.byref(self._own), handle), "rfi_peer_alloc")
+            except Exception as exc:  # published below: the other ranks must not wait for us
+                err = f"rank {self.rank}: {exc}"
+            mine = (socket.gethostname(), bytes(handle) if err is None else None, err)
             everyone = [None] * self.world
             dist.all_gather_object(everyone, mine, group=group)
-            if len({h for h, _ in everyone}) != 1:
-                raise RuntimeError("ranks span several hosts")
+            errs = [e for _, _, e in everyone if e]
+            if not errs and len({h for h, _, _ in everyone}) != 1:
+                errs = ["ranks span several hosts"]
             ptrs = []
-            for r, (_, h) in enumerate(everyone):
-                if r == self.rank:
-                    ptrs.append(self._own.value)
-                    continue
-                p = C.c_void_p()
-                buf = (C.c_ubyte * 64).from_buffer_copy(h)
-                _native.check(lib.rfi_peer_open(buf, C.byref(p)), "rfi_peer_open")
-                self._opened.append(p)
-                ptrs.append(p.value)
-            self.ptrs = (C.c_void_p * self.world)(*ptrs)
+            if not errs:
+                try:
+                    for r, (_, h, _) in enumerate(everyone):
+                        if r == self.rank:
+                            ptrs.append(self._own.value)
+                            continue
+                        p = C.c_void_p()
+                        buf = (C.c_ubyte * 64).from_buffer_copy(h)
+                        _native.check(lib.rfi_peer_open(buf, C.byref(p)), "rfi_peer_open")
+                        self._opened.append(p)
+                        ptrs.append(p.value)
+                except Exception as exc:
+                    errs = [f"rank {self.rank}: {exc}"]
+            # agreement: the peer path is used only if EVERY rank mapped every buffer
+            flag = torch.tensor([0 if errs else 1], dtype=torch.int32, device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 1:
+                self.ptrs = (C.c_void_p * self.world)(*ptrs)
+                self.ok = True
+            else:
+                self.reason = "; ".join(errs) if errs else "a peer rank could not map the exchange buffers"
+                self.close()
         dist.barrier(group=group)  # every buffer is mapped everywhere before its first use
+
+    def close(self):
+        """Unmap the peers' buffers and free this rank's own (idempotent)."""
+        lib = _native.load()
+        for p in self._opened:
+            try:
+                lib.rfi_peer_close(p)
+            except Exception:
+                pass
+        self._opened = []
+        if self._own.value:
+            try:
+                lib.rfi_peer_free(self._own)
+            except Exception:
+                pass
+            self._own = C.c_void_p()
 
     def next_epoch(self):
         self.epoch += 1
@@ -62,13 +107,14 @@ class PeerContext:
 
 
 def peer_context(group, device):
-    """The exchange context of (`group`, `device`), built on first use; None if the ranks cannot
-    share memory (then the caller all-reduces over NCCL)."""
+    """The exchange context of (`group`, `device`), built on first use (collectively: every rank of
+    the group must call this); None if the ranks cannot share memory -- on ALL ranks alike -- and
+    the caller then all-reduces over NCCL."""
     key = (id(group) if group is not None else 0, device.index)
     if key not in _CONTEXTS:
-        try:
-            _CONTEXTS[key] = PeerContext(group, device)
-        except Exception as exc:  # CUDA IPC unavailable, several hosts, ...
-            logger.warning("peer-memory exchange unavailable (%s): metric counts go through NCCL", exc)
-            _CONTEXTS[key] = None
+        ctx = PeerContext(group, device)
+        if not ctx.ok:
+            logger.warning("peer-memory exchange unavailable (%s): metric counts go through NCCL", ctx.reason)
+            ctx = None
+        _CONTEXTS[key] = ctx
     return _CONTEXTS[key]

@@ -61,3 +61,45 @@ def test_fused_count_allreduce_matches_global_counts(native_lib):
             assert got == want and nccl == want
             tp, fp, fn = want
             assert np.isclose(iou, tp / (tp + fp + fn))
+
+
+def _worker_partial_failure(rank, world, port, q):
+    """One rank cannot set up its exchange buffer: EVERY rank must fall back to NCCL (no hang)."""
+    import torch.distributed as dist
+
+    from rfi_toolbox_b200.evaluation.metrics import _counts_tensor, confusion_counts
+    from rfi_toolbox_b200.utils.sharding import baseline_shard
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RFI_PEER_FAIL_RANK="1")
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        g = torch.Generator().manual_seed(5)
+        true = (torch.rand((6, 2, 128, 128), generator=g) < 0.1).to(torch.uint8)
+        pred = true ^ (torch.rand(true.shape, generator=g) < 0.03).to(torch.uint8)
+        sl = baseline_shard(6, world, rank)
+        want = tuple(_counts_tensor(pred.to(dev), true.to(dev)).tolist())
+        got = [tuple(confusion_counts(pred[sl].to(dev), true[sl].to(dev), group=True)) for _ in range(3)]
+        from rfi_toolbox_b200.utils.peer import _CONTEXTS
+        q.put((rank, want, got, [c is None for c in _CONTEXTS.values()]))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_partial_peer_failure_falls_back_everywhere(native_lib):
+    import torch.multiprocessing as mp
+    world, port = 2, 29633
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_partial_failure, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, want, got, none_ctx in results:
+        assert none_ctx == [True], "a rank kept the peer path although rank 1 failed"
+        assert all(g == want for g in got)
