@@ -475,7 +475,8 @@ big_mad_kernel(BigGeom g, BigGroup* __restrict__ groups, uint32_t* __restrict__ 
 // ------------------------------------------------------------------------------------------
 // phase-2 arithmetic shared by big_range and big_write (identical ops -> consistent min / max)
 struct BigMath {
-    float med, fill, med2, thr_lo, thr_hi, raw_lo, raw_hi, rm, rm2;
+    float med, fill, med2, thr_lo, thr_hi, raw_lo, raw_hi;
+    FastChain chain;
     bool fast;   // monotone group: raw thresholds, approximate log amplitude (see rfi_tiles.cu phase 2)
 };
 
@@ -484,8 +485,7 @@ RFI_DEVINL BigMath big_math(const PlanDev& p, const rfi_tile_stat_t& st) {
     b.med = (float)st.median_before; b.fill = (float)st.inf_fill; b.med2 = (float)st.median_after;
     b.thr_lo = (float)st.thr_lo; b.thr_hi = (float)st.thr_hi;
     b.raw_lo = (float)st.raw_lo; b.raw_hi = (float)st.raw_hi;
-    b.rm = (p.norm_before && b.med > 0.f) ? 1.0f / b.med : 1.0f;
-    b.rm2 = (p.norm_after && b.med2 > 0.f) ? 1.0f / b.med2 : 1.0f;
+    b.chain = make_fast_chain(p, b.med, b.med2);
     b.fast = (st.route & RFI_TILE_RAW_THRESHOLDS) != 0;
     return b;
 }
@@ -495,16 +495,7 @@ template <bool kFast>
 RFI_DEVINL float big_eval(float a, const PlanDev& p, const BigMath& b, unsigned char& f) {
     if constexpr (kFast) {
         f = ((a > b.raw_hi) || (a < b.raw_lo)) ? 1 : 0;
-        float y;
-        if (p.stretch == RFI_STRETCH_LOG10) {
-            y = (p.norm_before && b.med > 0.f) ? a / b.med : a;
-            y = fabsf(log10f(y));
-        } else {
-            y = a * b.rm;
-            if (p.stretch == RFI_STRETCH_SQRT) y = sqrt_fast(y);
-        }
-        y = y * b.rm2;
-        return lg2_fast(y + 1e-10f) * 0.30102999566f;
+        return fast_log_amp(a, b.chain);
     } else {
         const float x = process_sample<float>(a, p, b.med, b.fill, b.med2);
         f = ((x > b.thr_hi) || (x < b.thr_lo)) ? 1 : 0;

@@ -357,8 +357,7 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
         const size_t src_origin = kMag ? 0 : origin;
         const size_t src_pitch = kMag ? (size_t)kP : (size_t)p.times;
         [[maybe_unused]] const float raw_lo = (float)st.raw_lo, raw_hi = (float)st.raw_hi;
-        [[maybe_unused]] const float rm = (p.norm_before && med_before > T(0)) ? 1.0f / (float)med_before : 1.0f;
-        [[maybe_unused]] const float rm2 = (p.norm_after && med_after > T(0)) ? 1.0f / (float)med_after : 1.0f;
+        [[maybe_unused]] const FastChain chain = make_fast_chain(p, (float)med_before, (float)med_after);
         Raw cur[Q], nxt[Q];
 #pragma unroll
         for (int q = 0; q < Q; ++q)
@@ -387,18 +386,7 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
                     raw_to_mag_fast<RDT>(cur[q], a);
                     ph = T(0);
                     if (p.flag_mode == RFI_FLAGS_MAD) f = ((a > (T)raw_hi) || (a < (T)raw_lo)) ? 1 : 0;
-                    float y;
-                    if (p.stretch == RFI_STRETCH_LOG10) {
-                        // log10 cancels near y = 1: the quotient must be the exactly rounded one and
-                        // the logarithm relatively accurate (log10f, 2 ulp); only the outer log is approximate
-                        y = (p.norm_before && med_before > T(0)) ? (float)a / (float)med_before : (float)a;
-                        y = fabsf(log10f(y));
-                    } else {
-                        y = (float)a * rm;
-                        if (p.stretch == RFI_STRETCH_SQRT) y = sqrt_fast(y);
-                    }
-                    y = y * rm2;
-                    L = (T)(lg2_fast(y + 1e-10f) * 0.30102999566f);
+                    L = (T)fast_log_amp((float)a, chain);
                 } else {
                     if constexpr (!kMag) raw_to_mag<DT, kComplexBranch>(cur[q], a, ph);
                     T x = a;

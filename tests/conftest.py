@@ -35,3 +35,19 @@ def native_lib():
 
     build()
     return _native.load()
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Measured image-channel distances (tests/test_gpu_parity.py::image_errors) -> gpurun_out/."""
+    try:
+        from tests.test_gpu_parity import IMAGE_ERRORS
+    except Exception:
+        return
+    if not IMAGE_ERRORS:
+        return
+    out = ROOT / "gpurun_out"
+    out.mkdir(exist_ok=True)
+    with open(out / "image_errors.txt", "w") as fh:
+        fh.write("# case | channel | max|numpy-exact64| | max|cuda-exact64| | max|cuda-numpy|\n")
+        for label, ch, e_np, e_gpu, e_d in IMAGE_ERRORS:
+            fh.write(f"{label or '-'} | {ch} | {e_np:.3e} | {e_gpu:.3e} | {e_d:.3e}\n")

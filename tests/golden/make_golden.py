@@ -51,6 +51,15 @@ CASES = {
                          dict(patch_size=128, stretch="SQRT", flag_sigma=5, use_custom_flags=False), False),
     "inference_special": (dict(dtype=np.float32, seed=108, special=True, n_bl=1), False,
                           dict(patch_size=128, stretch="SQRT", inference_mode=True), False),
+    # BASELINE configs[4]'s literal call (big-tile path): |complex64|, P = 256, MAD sigma 3, no stretch
+    "magnitude_p256_mad3": (dict(dtype=np.complex64, seed=109, channels=512, times=512), True,
+                            dict(patch_size=256, stretch=None, flag_sigma=3, use_custom_flags=False), False),
+    # dims that are not multiples of P: every ROTATED view is zero-padded bottom / right (:527-550)
+    "padded_sqrt_mad5": (dict(dtype=np.float32, seed=110, channels=200, times=300), False,
+                         dict(patch_size=128, stretch="SQRT", flag_sigma=5, use_custom_flags=False), False),
+    # BASELINE configs[2]'s literal call: |complex64|, LOG10 stretch, MAD sigma 5 (exact-zero rows -> inf fill)
+    "magnitude_log10_mad5": (dict(dtype=np.complex64, seed=111), True,
+                             dict(patch_size=128, stretch="LOG10", flag_sigma=5, use_custom_flags=False), False),
 }
 PERM_SEED = 4242
 N_SAMPLE = 8192
@@ -68,7 +77,7 @@ def main():
     for name, (ck, use_abs, kw, with_flags) in CASES.items():
         ck = dict(ck)
         ck.setdefault("n_bl", 1)
-        cube, mask = make_cube(n_pol=2, channels=256, times=256, **ck)
+        cube, mask = make_cube(**{"n_pol": 2, "channels": 256, "times": 256, **ck})
         data = np.abs(cube) if use_abs else cube
         np.random.seed(PERM_SEED)
         ds = Preprocessor(data, mask if with_flags else None).create_dataset(num_workers=0, **kw)

@@ -11,7 +11,7 @@ import torch
 
 import oracle
 from tests.test_gpu_bigtile import _routes
-from tests.test_gpu_parity import IMG_ATOL, IMG_RTOL
+from tests.test_gpu_parity import IMG_ATOL, IMG_RTOL, image_errors
 
 pytestmark = pytest.mark.gpu
 
@@ -72,8 +72,9 @@ def _check_properties(pre, ds, P, R, nh, nw, n_wf, sample=64):
     return st, tile
 
 
-def _slice_parity(cube, b, kw, P):
-    """oracle vs GPU on one baseline at the full waterfall size."""
+def _slice_parity(cube, b, kw, P, max_label_mismatch=0.0, label=""):
+    """oracle vs GPU on one baseline at the full waterfall size.  `max_label_mismatch` > 0: the
+    stretch is LOG10 (host-dependent upstream of the thresholds), mismatches are counted."""
     from rfi_toolbox_b200 import Preprocessor
     sl = cube[b:b + 1]
     np.random.seed(3)
@@ -82,8 +83,18 @@ def _slice_parity(cube, b, kw, P):
     np.random.seed(3)
     ods, inter = oracle.create_dataset(np.abs(sl.cpu().numpy()), None, return_intermediates=True, **kw)
     assert np.array_equal(pre.order, inter["order"])
-    assert np.array_equal(ds.labels.cpu().numpy(), ods.labels)
-    assert np.allclose(ds.images.cpu().numpy(), ods.images, rtol=IMG_RTOL, atol=IMG_ATOL, equal_nan=True)
+    labs, imgs = ds.labels.cpu().numpy(), ds.images.cpu().numpy()
+    diff = np.abs(imgs - ods.images)
+    print(f"[slice parity] {label}: {len(ods.images)} patches, label mismatch fraction {(labs != ods.labels).mean():.3e}, "
+          f"max |cuda - numpy| {np.nanmax(diff):.3e}")
+    if max_label_mismatch == 0.0:
+        assert np.array_equal(labs, ods.labels)
+        assert np.allclose(imgs, ods.images, rtol=IMG_RTOL, atol=IMG_ATOL, equal_nan=True)
+        image_errors(imgs, ods, inter, label, max_patches=256)
+    else:
+        assert (labs != ods.labels).mean() <= max_label_mismatch
+        ok = np.isclose(imgs, ods.images, rtol=IMG_RTOL, atol=IMG_ATOL, equal_nan=True)
+        assert (~ok).mean() <= 10 * max_label_mismatch + 1e-4
 
 
 def test_config2_full_size_properties(native_lib):
@@ -111,7 +122,7 @@ def test_config2_full_size_properties(native_lib):
     half = len(ds) // 2
     a, b = confusion_counts(ds.labels[:half], truth[:half]), confusion_counts(ds.labels[half:], truth[half:])
     assert (tp, fp, fn) == tuple(x + y for x, y in zip(a, b))
-    _slice_parity(cube, 7, kw, 128)
+    _slice_parity(cube, 7, kw, 128, label="configs[1] baseline 7")
 
 
 def test_config3_half_shard_properties(native_lib):
@@ -129,6 +140,9 @@ def test_config3_half_shard_properties(native_lib):
     # pol 0 carries the exact-zero bandpass edge rows (log10(0) = -inf -> MAD fill): general route there,
     # raw thresholds in the interior
     assert (route[0::4, 0] & 2).all() and (route[0::4, 31] & 2).all() and (route[:, 1:31] & 1).mean() > 0.95
+    del ds, pre
+    # the headline configuration's literal call against the oracle: one baseline at 4096 x 2048
+    _slice_parity(cube, 5, kw, 128, max_label_mismatch=1e-4, label="configs[2] baseline 5")
 
 
 def test_config5_chunk_properties(native_lib):
@@ -143,7 +157,7 @@ def test_config5_chunk_properties(native_lib):
     st, _ = _check_properties(pre, ds, 256, 4, 4, 64, 4 * 4, sample=24)
     assert (st["route"] & 1).mean() > 0.99
     del ds, pre
-    _slice_parity(cube[:, :2], 1, kw, 256)
+    _slice_parity(cube[:, :2], 1, kw, 256, label="configs[4] baseline 1, 2 pols")
 
 
 def test_config4_pair_sweep_properties(native_lib):

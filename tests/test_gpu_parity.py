@@ -3,10 +3,17 @@
 Bars:
   * bit-exact: labels, patch order, flag counts, medians / MADs / thresholds -- for real input
     with stretch None or SQRT every operation is a single IEEE op on both sides;
-  * images: |gpu - oracle| <= 1e-6 * |oracle| + IMG_ATOL.  The only non-identical primitive is
-    float32 log10 (NumPy's SIMD log10 is up to 3 ulp from correctly rounded on AVX-512 hosts;
-    the kernel evaluates it in fp64 and rounds once).  The log-amplitude channel spans ~10
-    decades, 3 ulp of which is ~1.5e-6 absolute before the 1/0.224 ImageNet scale;
+  * images: the channels sit downstream of float32 `log10` (NumPy's is SVML on AVX-512 hosts, up
+    to 3 ulp from correctly rounded, i.e. host dependent) and of a per-patch min-max that divides
+    any error by (hi - lo) -- 0.05 on a noise-only tile.  "1e-6 relative" therefore cannot be met
+    by ANY two float32 implementations, NumPy on two hosts included.  The yardstick is the float64
+    evaluation of the chain (`oracle.images_exact64`): every comparison measures, per channel,
+        e_np  = max |oracle  - exact64|     (NumPy's own noise on this input)
+        e_gpu = max |CUDA    - exact64|
+    and requires  e_gpu <= NOISE_FACTOR * e_np + ULP_FLOOR  and hence
+    |CUDA - oracle| <= (1 + NOISE_FACTOR) * e_np + ULP_FLOOR  -- the CUDA path is as close to the
+    exact chain as the reference is.  The measured values are printed (pytest -s) and recorded in
+    `IMAGE_ERRORS` (dumped to gpurun_out/ by tests/conftest.py at session end);
   * LOG10 stretch feeds that log10 into the flag thresholds: labels may differ only where the
     stretched value sits within 4 ulp of a threshold, and such pixels are counted.
 """
@@ -20,7 +27,36 @@ import oracle
 from tests.cubes import make_cube
 
 pytestmark = pytest.mark.gpu
-IMG_RTOL, IMG_ATOL = 1e-6, 2e-5
+# e_gpu <= NOISE_FACTOR * e_np + ULP_FLOOR per channel (ULP_FLOOR = 2.5 ulp of the largest
+# ImageNet-normalised value, 2.64: covers channels whose NumPy noise is ~0, e.g. the constant one)
+NOISE_FACTOR, ULP_FLOOR = 1.5, 6e-7
+IMG_RTOL, IMG_ATOL = 1e-6, 3e-6   # blanket bound where the exact chain is not evaluated (full-size slices)
+IMAGE_ERRORS = []                 # (label, channel, e_np, e_gpu, e_diff)
+
+
+def image_errors(gpu_images, ods, inter, label="", max_patches=None):
+    """Per-channel (e_np, e_gpu, e_diff) against the float64 chain; asserts the noise bound.
+    `max_patches`: evaluate the chain on an evenly spaced subset of the output patches."""
+    sel = np.arange(len(ods.images))
+    if max_patches is not None and len(sel) > max_patches:
+        sel = sel[:: -(-len(sel) // max_patches)]
+    exact = oracle.images_exact64(inter["processed"][inter["order"][sel]])
+    gpu = np.asarray(gpu_images[sel], dtype=np.float64)
+    ref = ods.images[sel].astype(np.float64)
+    assert np.array_equal(np.isnan(gpu), np.isnan(ref)), "NaN pattern of the images differs"
+    out = []
+    for c in range(3):
+        if gpu[..., c].size == 0 or np.isnan(ref[..., c]).all():
+            continue
+        e_np = float(np.nanmax(np.abs(ref[..., c] - exact[..., c])))
+        e_gpu = float(np.nanmax(np.abs(gpu[..., c] - exact[..., c])))
+        e_d = float(np.nanmax(np.abs(gpu[..., c] - ref[..., c])))
+        out.append((c, e_np, e_gpu, e_d))
+        IMAGE_ERRORS.append((label, c, e_np, e_gpu, e_d))
+        print(f"[image error] {label} ch{c}: numpy-exact64 {e_np:.3e}  cuda-exact64 {e_gpu:.3e}  cuda-numpy {e_d:.3e}")
+        assert e_gpu <= NOISE_FACTOR * e_np + ULP_FLOOR, \
+            f"{label} channel {c}: CUDA is {e_gpu:.3e} from the float64 chain, NumPy {e_np:.3e}"
+    return out
 
 
 def _run_gpu(data, flags, magnitude=False, seed=11, **kw):
@@ -38,21 +74,24 @@ def _run_oracle(data, flags, magnitude=False, seed=11, **kw):
     return oracle.create_dataset(d, flags, return_intermediates=True, **kw)
 
 
-def _compare(ds, ods, inter, pre, exact_labels=True, max_label_mismatch=0.0):
+def _compare(ds, ods, inter, pre, exact_labels=True, max_label_mismatch=0.0, label=""):
     imgs = ds.images.cpu().numpy()
     labs = ds.labels.cpu().numpy()
     assert imgs.shape == ods.images.shape and labs.shape == ods.labels.shape
     assert np.array_equal(pre.order, inter["order"]), "patch order differs"
     if exact_labels:
         assert np.array_equal(labs, ods.labels), f"{(labs != ods.labels).sum()} label mismatches"
+        image_errors(imgs, ods, inter, label)
     else:
+        # host-dependent log10 upstream of the thresholds AND of the processed values: a few
+        # stretched samples differ by an ulp, so the float64 yardstick (built on the oracle's
+        # processed values) applies to all but those pixels
         frac = (labs != ods.labels).mean()
+        print(f"[labels] {label}: mismatch fraction {frac:.3e}")
         assert frac <= max_label_mismatch, f"label mismatch fraction {frac}"
-    ok = np.isclose(imgs, ods.images, rtol=IMG_RTOL, atol=IMG_ATOL, equal_nan=True)
-    if exact_labels:
-        assert ok.all(), f"{(~ok).sum()} image values out of tolerance, max abs diff " \
-                         f"{np.nanmax(np.abs(imgs - ods.images))}"
-    else:
+        ok = np.isclose(imgs, ods.images, rtol=IMG_RTOL, atol=IMG_ATOL, equal_nan=True)
+        print(f"[image error] {label}: max |cuda - numpy| {np.nanmax(np.abs(imgs - ods.images)):.3e}, "
+              f"outside tolerance {(~ok).mean():.3e}")
         assert (~ok).mean() <= 10 * max_label_mismatch + 1e-4
     assert ds.metadata == ods.metadata
 
@@ -116,6 +155,42 @@ def test_complex_magnitude_route(native_lib):
     pre, ds = _run_gpu(data, None, magnitude=True, **kw)
     ods, inter = _run_oracle(data, None, magnitude=True, **kw)
     _compare(ds, ods, inter, pre)
+
+
+@pytest.mark.parametrize("patch", [128, 256])
+def test_complex_magnitude_log10(native_lib, patch):
+    """BASELINE configs[2]'s literal call: complex64 in, magnitude fused, LOG10 stretch, MAD flags
+    (the kFast && kMag LOG10 route of the writers; exact-zero bandpass rows -> inf fill), at
+    P = 128 and on the big-tile path (P = 256)."""
+    data, _ = make_cube(dtype=np.complex64, seed=29, channels=512, times=512)
+    kw = dict(patch_size=patch, stretch="LOG10", flag_sigma=5, use_custom_flags=False)
+    pre, ds = _run_gpu(data, None, magnitude=True, **kw)
+    ods, inter = _run_oracle(data, None, magnitude=True, **kw)
+    _compare(ds, ods, inter, pre, exact_labels=False, max_label_mismatch=1e-4, label=f"c64 |z| LOG10 P{patch}")
+
+
+@pytest.mark.parametrize("stretch", [None, "SQRT"])
+def test_complex_magnitude_p256(native_lib, stretch):
+    """BASELINE configs[4]'s literal call (big-tile path): complex64 magnitudes, P = 256, MAD sigma 3."""
+    data, _ = make_cube(dtype=np.complex64, seed=31, channels=512, times=512)
+    kw = dict(patch_size=256, stretch=stretch, flag_sigma=3, use_custom_flags=False)
+    pre, ds = _run_gpu(data, None, magnitude=True, **kw)
+    ods, inter = _run_oracle(data, None, magnitude=True, **kw)
+    _compare(ds, ods, inter, pre, label=f"c64 |z| {stretch} P256")
+
+
+@pytest.mark.parametrize("stretch", [None, "SQRT", "LOG10"])
+def test_noise_only_tiles_image_noise(native_lib, stretch):
+    """Worst case for the image tolerance: tiles without RFI, whose log amplitude spans ~0.05, so the
+    per-patch min-max multiplies every error of log10 by ~20 (then 1 / 0.224 for ImageNet)."""
+    data, _ = make_cube(n_bl=1, n_pol=4, dtype=np.complex64, seed=37, rfi=False)
+    kw = dict(stretch=stretch, flag_sigma=3, use_custom_flags=False)
+    pre, ds = _run_gpu(data[:, 2:], None, magnitude=True, **kw)
+    ods, inter = _run_oracle(data[:, 2:], None, magnitude=True, **kw)
+    exact = stretch != "LOG10"
+    _compare(ds, ods, inter, pre, exact_labels=exact, max_label_mismatch=1e-4, label=f"noise-only {stretch}")
+    if not exact and np.array_equal(ds.labels.cpu().numpy(), ods.labels):
+        image_errors(ds.images.cpu().numpy(), ods, inter, f"noise-only {stretch}")
 
 
 def test_complex_mad_flags_pool_semantics(native_lib):
@@ -183,7 +258,9 @@ def test_golden_fixture(native_lib, name):
         assert (labels != c["labels"]).mean() < 1e-4
     else:
         assert np.array_equal(labels, c["labels"])
-    assert np.allclose(images.reshape(-1)[c["image_pos"]], c["image_val"], rtol=1e-6, atol=2e-5, equal_nan=True)
+    err = np.nanmax(np.abs(images.reshape(-1)[c["image_pos"]] - c["image_val"]))
+    print(f"[image error] golden {name}: max |cuda - reference| {err:.3e}")
+    assert np.allclose(images.reshape(-1)[c["image_pos"]], c["image_val"], rtol=IMG_RTOL, atol=IMG_ATOL, equal_nan=True)
     assert int(np.isnan(images).sum()) == c["image_nan_count"]
     pred = c["labels"].astype(bool)
     truth = pred ^ (np.random.default_rng(9).random(pred.shape) < 0.02)
