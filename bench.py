@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- waterfall Gpixel/s of create_dataset + evaluate_segmentation (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--baselines B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload c2|c3|c5] [--baselines B] [--lookahead L] [--no-extra]
 
 One "step" = one pass of the hot path over one synthetic cube:
     Preprocessor(cube_c64, magnitude=True).create_dataset(patch_size=128, stretch="SQRT",
@@ -9,22 +10,36 @@ One "step" = one pass of the hot path over one synthetic cube:
 on BASELINE.json configs[1] (45 baselines x 4 pols x 1024 ch x 1024 times, complex64,
 SQRT stretch, 4-way augmentation).  N > 1 (torchrun, one rank per GPU): every rank owns its
 own 45-baseline shard (baselines shard with no data-path exchange; weak scaling) and the
-{TP, FP, FN} counts are all-reduced over NCCL.
+{TP, FP, FN} counts are summed over the ranks inside the counting kernel (NVLink peer memory).
 
-JSON keys follow the driver contract; see DESIGN.md "Measurement" for the definitions of
-`value` (inputs resident in HBM), `e2e` (host buffers, copies inside the timed region),
-`roofline` (write_patches kernel, algorithmic bytes / CUDA-event time / measured HBM peak)
-and `cpu_baseline` (the NumPy oracle port on the host cores, bounded sample).
+The K timed steps are issued the way a streaming caller issues them (one Preprocessor per
+sample / baseline chunk, the reference's own unit of work, synthetic_generator.py:55-107):
+`create_dataset_async` keeps `--lookahead` calls in flight, so the host phase of step k (flag
+counts D2H -> np.random.permutation -> destination slots H2D) hides behind phase 1 of step
+k + 1.  Exactly K complete steps -- pipeline fill and drain included -- lie inside the timed
+region; `--lookahead 0` is the plain sequential loop.
+
+JSON keys follow the driver contract; see DESIGN.md "Measurement":
+  value     inputs resident in HBM
+  e2e       pinned HOST cube copied H2D every step, metric dict read back (dataset stays in HBM)
+  e2e_host_result  as e2e, plus the whole dataset (images + labels) downloaded to pinned host
+            memory every step -- what the reference's callers hold after `create_dataset`
+  roofline  write_patches kernel (algorithmic bytes / CUDA-event time / measured HBM peak) and the
+            PATH-level fraction: (s_in + R k 13 [+ 2 B per label px]) * px / step time
+  extra     the other BASELINE configs measured in the same run: c3_shard, c5_chunk, c4_sweep
+  cpu_baseline  the reference's CPU path on one host core, bounded sample
+`--impl reference` times the UNMODIFIED reference package (baseline/_ref, installed by
+`__graft_entry__.build()`; the NumPy oracle port only if that is absent) on all host cores.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
+from collections import deque
 from pathlib import Path
 
 import numpy as np
@@ -33,11 +48,11 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 WORKLOAD = dict(n_bl=45, n_pol=4, channels=1024, times=1024, patch=128, stretch="SQRT", sigma=5, rot=4)
-# other BASELINE.json configs, runnable for the record (`--workload c3`): per-GPU shard of the
-# VLA-scale cube (351 baselines over 8 GPUs = 44 per GPU), LOG10 stretch
 WORKLOADS = {
     "c2": dict(WORKLOAD, name="configs[1]"),
-    "c3": dict(n_bl=44, n_pol=4, channels=4096, times=2048, patch=128, stretch="LOG10", sigma=5, rot=4, name="configs[2] (one of 8 baseline shards)"),
+    # per-GPU shard of the VLA-scale cube (351 baselines over 8 GPUs = 44 per GPU), LOG10 stretch
+    "c3": dict(n_bl=44, n_pol=4, channels=4096, times=2048, patch=128, stretch="LOG10", sigma=5, rot=4,
+               name="configs[2] (one of 8 baseline shards)"),
     # long-track cube, P = 256 (big-tile path): the per-GPU shard (44 baselines, 153 GB of output) is
     # streamed through create_dataset in baseline chunks; one step = one 8-baseline chunk
     "c5": dict(n_bl=8, n_pol=4, channels=1024, times=16384, patch=256, stretch=None, sigma=3, rot=4,
@@ -45,12 +60,14 @@ WORKLOADS = {
 }
 METRIC = "waterfall Gpixel/s (create_dataset+metrics)"
 _JSON_FD = None  # the real stdout; fd 1 itself is pointed at stderr while the benchmark runs
+ACTIVE = WORKLOAD  # set from --workload in main(); inherited by the forked CPU-baseline workers
 
 
 def _reserve_stdout():
     """stdout must carry exactly ONE JSON line, but libraries write there too (NCCL prints its
-    version banner / NCCL_DEBUG output to stdout): keep a private handle on the real stdout and
-    send everything else that is written to fd 1 to stderr."""
+    version banner / NCCL_DEBUG output to stdout, the reference package prints debug lines on
+    import): keep a private handle on the real stdout and send everything else written to fd 1 to
+    stderr."""
     global _JSON_FD
     if _JSON_FD is None:
         sys.stdout.flush()
@@ -61,10 +78,38 @@ def _reserve_stdout():
 def _emit(line):
     sys.stdout.flush()
     os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + "\n").encode())
-ACTIVE = WORKLOAD  # set from --workload in main(); inherited by the forked CPU-baseline workers
+
+
+def _workload_text(w, per_gpu=True):
+    return (f"{w.get('name', 'configs[1]')} {w['n_bl']}bl x {w['n_pol']}pol x {w['channels']}ch x {w['times']}t "
+            f"complex64{' per GPU' if per_gpu else ''}, magnitude fused, {w['stretch']}, MAD sigma={w['sigma']}, "
+            f"R={w['rot']}, P={w['patch']}")
 
 
 # ------------------------------------------------------------------------------------- CPU side
+def _reference_api():
+    """(create_dataset(data, **kw) -> dataset with .labels, evaluate_segmentation, kind).
+    The unmodified reference package when baseline/_ref holds it, else the NumPy oracle port."""
+    ref = ROOT / "baseline" / "_ref"
+    if (ref / "rfi_toolbox" / "__init__.py").exists():
+        if str(ref) not in sys.path:
+            sys.path.append(str(ref))  # at the END: it also ships a `tests` package
+        os.environ.setdefault("CI", "1")  # the reference then skips its own process pools (preprocessor.py:491)
+        from rfi_toolbox.evaluation import evaluate_segmentation as ref_eval
+        from rfi_toolbox.preprocessing import Preprocessor as RefPre
+
+        def create(data, **kw):
+            return RefPre(data, None).create_dataset(num_workers=0, **kw)
+
+        return create, (lambda ds: ds.labels.numpy()), ref_eval, "reference"
+    import oracle
+
+    def create(data, **kw):
+        return oracle.create_dataset(data, None, num_workers=0, **kw)
+
+    return create, (lambda ds: ds.labels), oracle.evaluate_segmentation, "port"
+
+
 def _cpu_cube(n_bl, seed):
     from tests.cubes import make_cube
     return make_cube(n_bl=n_bl, n_pol=ACTIVE["n_pol"], channels=ACTIVE["channels"],
@@ -72,28 +117,35 @@ def _cpu_cube(n_bl, seed):
 
 
 def _cpu_step(args):
-    """Reference path on one baseline slice: np.abs -> create_dataset -> evaluate_segmentation."""
-    import oracle
+    """Reference path on one baseline slice: np.abs -> create_dataset -> evaluate_segmentation.
+    Returns (pixels, seconds inside the two reference calls): the ground-truth mask and its random
+    numbers are made OUTSIDE the timed segments, as on the GPU arm."""
     cube, truth_seed = args
+    create, labels_of, evaluate, _ = _reference_api()
     np.random.seed(truth_seed)
-    ds = oracle.create_dataset(np.abs(cube), None, patch_size=ACTIVE["patch"], stretch=ACTIVE["stretch"],
-                               flag_sigma=ACTIVE["sigma"], use_custom_flags=False, num_workers=0)
-    truth = ds.labels ^ (np.random.default_rng(truth_seed).random(ds.labels.shape) < 0.01)
-    oracle.evaluate_segmentation(ds.labels, truth)
-    return cube.size
+    t0 = time.perf_counter()
+    ds = create(np.abs(cube), patch_size=ACTIVE["patch"], stretch=ACTIVE["stretch"],
+                flag_sigma=ACTIVE["sigma"], use_custom_flags=False)
+    t1 = time.perf_counter()
+    labels = labels_of(ds)
+    truth = labels ^ (np.random.default_rng(truth_seed).random(labels.shape) < 0.01)
+    t2 = time.perf_counter()
+    evaluate(labels, truth)
+    t3 = time.perf_counter()
+    return cube.size, (t1 - t0) + (t3 - t2)
 
 
 def cpu_baseline(n_bl=1, procs=1):
-    """Times the oracle port on `procs` processes, each over `n_bl` baselines. -> Gpixel/s."""
+    """Times the reference's CPU path on `procs` processes, each over `n_bl` baselines.
+    -> (Gpixel/s, pixels, seconds = the slowest process's time inside the reference calls)."""
     cubes = [_cpu_cube(n_bl, 100 + i)[0] for i in range(procs)]
-    t0 = time.perf_counter()
     if procs == 1:
-        npix = _cpu_step((cubes[0], 1))
+        npix, dt = _cpu_step((cubes[0], 1))
     else:
         import multiprocessing as mp
         with mp.get_context("fork").Pool(procs) as pool:
-            npix = sum(pool.map(_cpu_step, [(c, i) for i, c in enumerate(cubes)]))
-    dt = time.perf_counter() - t0
+            res = pool.map(_cpu_step, [(c, i) for i, c in enumerate(cubes)])
+        npix, dt = sum(r[0] for r in res), max(r[1] for r in res)
     return npix / dt / 1e9, npix, dt
 
 
@@ -101,8 +153,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    kind = _reference_api()[3]
     procs = os.cpu_count() or 1
-    for _ in range(args.warmup if args.warmup < 1 else 1):
+    for _ in range(1 if args.warmup >= 1 else 0):
         cpu_baseline(1, procs)
     times, npix = [], 0
     for _ in range(args.steps):
@@ -111,16 +164,14 @@ def run_reference(args):
     total = sum(times)
     value = npix * len(times) / total / 1e9
     sample = (f"{procs} processes x 1 baseline x 4 pols x {ACTIVE['channels']}x{ACTIVE['times']} per step "
-              "(one Preprocessor per process)")
+              f"(one Preprocessor per process, num_workers=0), "
+              f"{'unmodified reference package from baseline/_ref' if kind == 'reference' else 'NumPy oracle port'}")
     line = {
         "metric": METRIC, "value": value, "unit": "Gpixel/s", "impl": "reference", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{ACTIVE.get('name', 'configs[1]')} {ACTIVE['n_bl']}bl x {ACTIVE['n_pol']}pol x "
-                               f"{ACTIVE['channels']}ch x {ACTIVE['times']}t complex64, {ACTIVE['stretch']}, "
-                               f"MAD sigma={ACTIVE['sigma']}, R={ACTIVE['rot']}, P={ACTIVE['patch']}",
-                   "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "Gpixel/s", "cores": procs, "kind": "port", "sample": sample},
+        "config": {"workload": _workload_text(ACTIVE, per_gpu=False), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Gpixel/s", "cores": procs, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Gpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -184,11 +235,185 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------- GPU side
+class Runner:
+    """K pipelined steps of create_dataset + evaluate_segmentation over one input (device or pinned
+    host cube), timed with CUDA events on the current stream; max over ranks."""
+
+    def __init__(self, torch, dist, world, dev, kw, group, lookahead, phase1=None):
+        self.torch, self.dist, self.world, self.dev = torch, dist, world, dev
+        self.kw, self.group, self.lookahead, self.phase1 = kw, group, lookahead, phase1
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, seconds):
+        if self.world > 1:
+            t = self.torch.tensor([seconds], device=self.dev, dtype=self.torch.float64)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            return float(t.item())
+        return seconds
+
+    def submit(self, data, profile=False):
+        from rfi_toolbox_b200 import Preprocessor
+        pre = Preprocessor(data, None, magnitude=True, pin=True)
+        pre.profile = profile
+        pre.phase1_stream = self.phase1
+        return pre, pre.create_dataset_async(input_ready=True, **self.kw)
+
+    def steps(self, data, truth, n, profile=False, sink=None):
+        """n complete steps; returns (last metric dict, per-step kernel events, n_kept of the last step).
+        Issue order of step i: result(i) [host phase + writer] -> evaluate_segmentation_async(i) [counting
+        kernel + 24-byte download] -> create_dataset_async(i + lookahead + 1) -> read the metrics of step
+        i - 1: every step's metric dict reaches the host, but never by draining the queue."""
+        from rfi_toolbox_b200 import evaluate_segmentation, evaluate_segmentation_async
+        pending, evs, m, kept, metric = deque(), [], None, 0, None
+        issued = 0
+        while issued < min(n, self.lookahead + (1 if self.lookahead else 0)):
+            pending.append(self.submit(data, profile))
+            issued += 1
+        for i in range(n):
+            if not self.lookahead:
+                pending.append(self.submit(data, profile))
+                issued += 1
+            pre, pd = pending.popleft()
+            np.random.seed(0)  # every step draws the same permutation (same dataset every step)
+            ds = pd.result()
+            if truth is not None:
+                if self.lookahead:
+                    nxt = evaluate_segmentation_async(ds.labels, truth, group=self.group)
+                else:
+                    m = evaluate_segmentation(ds.labels, truth, group=self.group)
+            if sink is not None:
+                sink(ds)
+            if self.lookahead and issued < n:
+                pending.append(self.submit(data, profile))
+                issued += 1
+            if truth is not None and self.lookahead:
+                if metric is not None:
+                    m = metric.result()
+                metric = nxt
+            if profile:
+                evs.append(pre.events)
+            kept = len(ds)
+            del ds, pre, pd  # one dataset resident at a time (configs[2]: 76 GB of patches per step)
+        if metric is not None:
+            m = metric.result()
+        return m, evs, kept
+
+    def timed(self, data, truth, warmup, n, profile=False, sink=None, drain=None):
+        torch = self.torch
+        self.steps(data, truth, warmup, sink=sink)
+        if drain:
+            drain()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        m, evs, kept = self.steps(data, truth, n, profile=profile, sink=sink)
+        if drain:
+            drain()
+        e1.record()
+        self.barrier()
+        t1 = time.perf_counter()
+        dev_s = e0.elapsed_time(e1) / 1e3
+        return dict(seconds=self.max_over_ranks(dev_s), dev_ms=dev_s * 1e3, wall=(t0, t1), metrics=m, events=evs,
+                    kept=kept)
+
+
+def _kernel_ms(evs):
+    out = {"stats": [], "write": []}
+    for ev in evs:
+        for k in out:
+            out[k].append(ev[k][0].elapsed_time(ev[k][1]))
+    return {k: float(np.mean(v)) if v else None for k, v in out.items()}
+
+
+def _path_roofline(npix, s_in, rot, k, label_px, seconds_per_step, peak):
+    """Path-level HBM fraction of one step: the cube read once + every kept output written once
+    (SURVEY section 8d), with and without evaluate_segmentation's 2 B per label pixel."""
+    create = npix * (s_in + rot * k * 13.0)
+    full = create + 2.0 * label_px
+    return {"bytes_create_dataset": create, "bytes_with_metrics": full,
+            "achieved_gbs_create_dataset": create / seconds_per_step / 1e9,
+            "achieved_gbs_with_metrics": full / seconds_per_step / 1e9,
+            "frac_create_dataset": create / seconds_per_step / 1e9 / peak,
+            "frac_with_metrics": full / seconds_per_step / 1e9 / peak}
+
+
+def _measure_workload(R, w, rank, peak, warmup, steps, torch):
+    """One BASELINE config on this rank's GPU, inputs resident -> dict for `extra`."""
+    from rfi_toolbox_b200.utils.synth import device_cube
+    cube, _ = device_cube(w["n_bl"], w["n_pol"], w["channels"], w["times"], seed=1234, device=R.dev,
+                          first_baseline=rank * w["n_bl"])
+    npix = cube.numel()
+    kw = dict(patch_size=w["patch"], stretch=w["stretch"], flag_sigma=w["sigma"], use_custom_flags=False,
+              augmentation_rotations=w["rot"])
+    R2 = Runner(torch, R.dist, R.world, R.dev, kw, R.group, R.lookahead, R.phase1)
+    # ground truth of the metric = this configuration's own labels with 1 % of pixels toggled
+    np.random.seed(0)
+    from rfi_toolbox_b200 import Preprocessor
+    ds = Preprocessor(cube, None, magnitude=True).create_dataset(**kw)
+    truth = ds.labels ^ (torch.rand(ds.labels.shape, device=R.dev) < 0.01).to(torch.uint8)
+    del ds
+    res = R2.timed(cube, truth, warmup, steps, profile=True)
+    sec = res["seconds"] / steps
+    n_tiles = npix // (w["patch"] ** 2)
+    k = res["kept"] / (n_tiles * w["rot"])
+    km = _kernel_ms(res["events"])
+    out = {"workload": _workload_text(w), "gpixel_per_s_per_gpu": npix / sec / 1e9,
+           "gpixel_per_s_all_gpus": R.world * npix / sec / 1e9, "ms_per_step": sec * 1e3, "steps": steps,
+           "warmup": warmup, "patches_kept": res["kept"], "kept_fraction": k,
+           "phase1_ms": km["stats"], "writer_ms": km["write"],
+           "writer_frac_of_peak": npix * (4 + w["rot"] * k * 13.0) / (km["write"] * 1e-3) / 1e9 / peak,
+           "path": _path_roofline(npix, 8, w["rot"], k, truth.numel(), sec, peak)}
+    del truth, cube
+    torch.cuda.empty_cache()
+    return out
+
+
+def _measure_c4(R, peak, torch, n_pairs, warmup, steps):
+    """BASELINE configs[3]: compute_ffi + MAD reduction + IoU / F1 over n_pairs 128 x 128 pairs."""
+    from rfi_toolbox_b200 import compute_ffi_batch, evaluate_segmentation_batch
+    dev = R.dev
+    g = torch.Generator(device=dev).manual_seed(7)
+    true = torch.rand((n_pairs, 128, 128), generator=g, device=dev) < 0.10
+    pred = true ^ (torch.rand((n_pairs, 128, 128), generator=g, device=dev) < 0.02)
+    data = torch.view_as_complex(torch.randn((n_pairs, 128, 128, 2), generator=g, device=dev))
+    data = (data * (1.0 + 99.0 * true)).contiguous()
+    npix = true.numel()
+
+    def one():
+        f = compute_ffi_batch(data, pred, errors="nan")
+        m = evaluate_segmentation_batch(pred, true)
+        return f, m
+
+    for _ in range(warmup):
+        one()
+    R.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        f, m = one()
+    e1.record()
+    R.barrier()
+    sec = R.max_over_ranks(e0.elapsed_time(e1) / 1e3) / steps
+    alg = npix * 10.0  # complex64 + flags + truth, each read once (BASELINE.md section 4)
+    out = {"workload": f"configs[3] {n_pairs} pairs x 128 x 128 complex64: compute_ffi_batch + evaluate_segmentation_batch "
+                       "(per-pair FFI, MAD / std reduction, IoU, precision, recall, F1, dice)",
+           "gpixel_per_s_per_gpu": npix / sec / 1e9, "ms_per_sweep": sec * 1e3, "steps": steps, "warmup": warmup,
+           "algorithmic_bytes": alg, "achieved_gbs": alg / sec / 1e9, "frac_of_peak": alg / sec / 1e9 / peak,
+           "mean_ffi": float(np.nanmean(f["ffi"])), "mean_iou": float(np.mean(m["iou"]))}
+    del true, pred, data
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from rfi_toolbox_b200 import Preprocessor, evaluate_segmentation
     from rfi_toolbox_b200.utils.synth import device_cube
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -201,6 +426,16 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     group = True if world > 1 else None
+    if args.phase1_stream == "side":
+        # the caller's stream (host phase, writer, metrics) gets the SMs first; phase 1 of the calls in
+        # flight fills in from the library's low-priority side stream
+        torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=-1))
+
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
 
     w = dict(WORKLOADS[args.workload])
     if args.baselines:
@@ -208,105 +443,100 @@ def run_ours(args):
     # Philox seed 1234, one subsequence per baseline of the sharded cube
     cube, mask = device_cube(w["n_bl"], w["n_pol"], w["channels"], w["times"], seed=1234, device=dev,
                              first_baseline=rank * w["n_bl"])
+    del mask
     npix = cube.numel()
     kw = dict(patch_size=w["patch"], stretch=w["stretch"], flag_sigma=w["sigma"], use_custom_flags=False,
               augmentation_rotations=w["rot"])
-
-    def step(data, seed, profile=False):
-        np.random.seed(seed)
-        pre = Preprocessor(data, None, magnitude=True, pin=True)
-        pre.profile = profile
-        ds = pre.create_dataset(**kw)
-        return pre, ds
+    R = Runner(torch, dist, world, dev, kw, group, args.lookahead, args.phase1_stream if args.phase1_stream != 'main' else None)
 
     # ground truth for the metric: the labels of a first pass with 1 % of pixels toggled
-    pre, ds = step(cube, 0)
+    from rfi_toolbox_b200 import Preprocessor
+    np.random.seed(0)
+    ds = Preprocessor(cube, None, magnitude=True).create_dataset(**kw)
     truth = ds.labels ^ (torch.rand(ds.labels.shape, device=dev) < 0.01).to(torch.uint8)
     n_kept = len(ds)
-    del ds, pre
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    del ds
 
     # ---- resident-input arm
     sampler = ClockSampler(local)
     sampler.start()
-    for i in range(args.warmup):
-        pre, ds = step(cube, 0)
-        evaluate_segmentation(ds.labels, truth, group=group)
-        del ds, pre
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kern_ms = {"stats": [], "write": []}
-    t0 = time.perf_counter()
-    e0.record()
-    evs = []
-    for i in range(args.steps):
-        pre, ds = step(cube, 0, profile=True)
-        m = evaluate_segmentation(ds.labels, truth, group=group)
-        evs.append(pre.events)
-        del ds, pre  # one dataset resident at a time (configs[2]: 76 GB of patches per step)
-    e1.record()
-    barrier()
-    t1 = time.perf_counter()
-    wall = t1 - t0
+    res = R.timed(cube, truth, args.warmup, args.steps, profile=True)
     sampler.stop()
-    clocks = sampler.window(t0, t1)
-    dev_ms = e0.elapsed_time(e1)
-    for ev in evs:
-        for k in kern_ms:
-            kern_ms[k].append(ev[k][0].elapsed_time(ev[k][1]))
-    elapsed = max(dev_ms / 1e3, 0.0)
-    if world > 1:
-        t = torch.tensor([elapsed], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed = float(t.item())
+    clocks = sampler.window(*res["wall"])
+    elapsed = res["seconds"]
     value = world * npix * args.steps / elapsed / 1e9
+    km = _kernel_ms(res["events"])
+    m = res["metrics"]
 
     # ---- end-to-end arm: host (pinned) cube -> H2D -> create_dataset -> metrics -> D2H of the metric
     host = torch.empty(cube.shape, dtype=cube.dtype, pin_memory=True)
     host.copy_(cube)
-    for i in range(max(1, min(args.warmup, 2))):
-        pre, ds = step(host, 0)
-        evaluate_segmentation(ds.labels, truth, group=group)
-        del ds, pre
-    barrier()
     e2e_steps = max(1, min(args.steps, 5))
-    e0.record()
-    for i in range(e2e_steps):
-        pre, ds = step(host, 0)
-        m = evaluate_segmentation(ds.labels, truth, group=group)
-        del ds, pre
-    e1.record()
-    barrier()
-    e2e_elapsed = e0.elapsed_time(e1) / 1e3
-    if world > 1:
-        t = torch.tensor([e2e_elapsed], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_elapsed = float(t.item())
-    e2e_value = world * npix * e2e_steps / e2e_elapsed / 1e9
+    e2e = R.timed(host, truth, max(1, min(args.warmup, 2)), e2e_steps)
+    e2e_value = world * npix * e2e_steps / e2e["seconds"] / 1e9
     n_tiles = npix // (w["patch"] ** 2)
     h2d = cube.numel() * cube.element_size() + n_tiles * w["rot"] * 8
     d2h = n_tiles * 4 + 24
+
+    # ---- end-to-end with the RESULT on the host: images + labels downloaded to pinned memory every step
+    e2e_host = None
+    if not args.no_extra:
+        out_bytes = n_kept * w["patch"] ** 2 * 13
+        try:
+            himg = torch.empty((n_kept, w["patch"], w["patch"], 3), dtype=torch.float32, pin_memory=True)
+            hlab = torch.empty((n_kept, w["patch"], w["patch"]), dtype=torch.uint8, pin_memory=True)
+            side = torch.cuda.Stream(device=dev)
+            last = []
+
+            def sink(ds):
+                for ev in last:       # one download in flight: the pinned buffers are reused
+                    ev.synchronize()
+                last.clear()
+                _, ev = ds.to_host_async(himg, hlab, stream=side)
+                last.append(ev)
+
+            def drain():
+                for ev in last:
+                    ev.synchronize()
+                last.clear()
+
+            hsteps = max(1, min(args.steps, 3))
+            eh = R.timed(host, truth, 1, hsteps, sink=sink, drain=drain)
+            e2e_host = {"value": world * npix * hsteps / eh["seconds"] / 1e9, "unit": "Gpixel/s",
+                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h + out_bytes), "steps": hsteps,
+                        "ms_per_step": eh["seconds"] / hsteps * 1e3,
+                        "note": "as e2e, plus the whole dataset (images float32 + labels uint8) copied to pinned host "
+                                "memory on a side stream (TorchDataset.to_host_async), overlapped with the next step"}
+            del himg, hlab
+        except Exception as exc:  # e.g. the host cannot pin that much memory
+            e2e_host = {"unavailable": str(exc)[:200]}
+    del host
+
+    # ---- the other BASELINE configs, same run (inputs resident)
+    extra = {}
+    if not args.no_extra and args.workload == "c2" and not args.baselines:
+        del cube, truth
+        torch.cuda.empty_cache()
+        for key, name, (wu, st) in (("c3_shard", "c3", (3, 5)), ("c5_chunk", "c5", (3, 8))):
+            try:
+                extra[key] = _measure_workload(R, WORKLOADS[name], rank, peak, wu, st, torch)
+            except Exception as exc:
+                extra[key] = {"unavailable": str(exc)[:300]}
+        try:
+            extra["c4_sweep"] = _measure_c4(R, peak, torch, 100_000, 3, 5)
+        except Exception as exc:
+            extra["c4_sweep"] = {"unavailable": str(exc)[:300]}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    peaks = {}
-    pk = ROOT / "MEASURED_PEAKS.json"
-    if pk.exists():
-        peaks = json.loads(pk.read_text())
-    peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
     k = n_kept / (n_tiles * w["rot"])
     # complex64 through the real branch: both writers read the exact float32 magnitudes phase 1 left in
     # its scratch (4 B / px), not the complex cube (8 B / px); the cube itself is read once, by phase 1
     alg_bytes = npix * (4 + w["rot"] * k * 13.0)
-    write_ms = float(np.mean(kern_ms["write"]))
-    stats_ms = float(np.mean(kern_ms["stats"]))
+    write_ms, stats_ms = km["write"], km["stats"]
     achieved = alg_bytes / (write_ms * 1e-3) / 1e9
     # DRAM bytes of one launch from the committed `ncu --set full` capture of this very workload
     # (profiles/traffic.json, written by scripts/ncu_summary.py); null for any other workload
@@ -315,14 +545,16 @@ def run_ours(args):
     if tj.exists() and not args.baselines and args.workload in ("c2", "c5"):
         kname = "write_patches_kernel" if args.workload == "c2" else "big_write_kernel"
         traffic = json.loads(tj.read_text()).get(kname, {}).get("dram_bytes_per_launch")
+    sec_step = elapsed / args.steps
     roofline = {"bound": "hbm", "kernel": "write_patches_kernel" if w["patch"] == 128 else "big_write_kernel",
                 "achieved": achieved, "peak": peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": write_ms,
-                "stats_kernel_ms": stats_ms, "stats_kernel_gbs": npix * (cube.element_size() + 4) / (stats_ms * 1e-3) / 1e9,
-                "bytes_per_pixel": {"phase1": cube.element_size() + 4, "writer": 4 + w["rot"] * k * 13.0,
-                                    "path_minimum": cube.element_size() + w["rot"] * k * 13.0},
-                "step_ms_device": dev_ms / args.steps}
+                "stats_kernel_ms": stats_ms, "stats_kernel_gbs": npix * (8 + 4) / (stats_ms * 1e-3) / 1e9,
+                "bytes_per_pixel": {"phase1": 8 + 4, "writer": 4 + w["rot"] * k * 13.0,
+                                    "path_minimum": 8 + w["rot"] * k * 13.0},
+                "step_ms_device": res["dev_ms"] / args.steps,
+                "path": _path_roofline(npix, 8, w["rot"], k, n_kept * w["patch"] ** 2, sec_step, peak)}
 
     cpu_bl = 2 if w["channels"] * w["times"] <= 1 << 20 else 1
     cpu_v, cpu_npix, cpu_dt = cpu_baseline(cpu_bl, 1)
@@ -330,24 +562,29 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "Gpixel/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{w['name']} {w['n_bl']}bl x {w['n_pol']}pol x {w['channels']}ch x {w['times']}t "
-                               f"complex64 per GPU, magnitude fused, {w['stretch']}, MAD sigma={w['sigma']}, "
-                               f"R={w['rot']}, P={w['patch']}",
+        "config": {"workload": _workload_text(w),
                    "pixels_per_step_per_gpu": npix, "patches_kept": n_kept,
-                   "l2": f"input cube {cube.numel() * 8 / 1e9:.1f} GB and {n_kept * w['patch'] ** 2 * 13 / 1e9:.1f} GB of output "
+                   "issue": (f"streaming: create_dataset_async with {args.lookahead} call(s) in flight (host phase of step k "
+                             "behind phase 1 of step k+1; metrics of step k read after step k+1 is enqueued); K complete steps incl. "
+                             "fill and drain inside the timed region" + ("; phase 1 on a side stream" if args.phase1_stream == "side" else ""))
+                            if args.lookahead else "sequential: create_dataset, then evaluate_segmentation, per step",
+                   "l2": f"input cube {npix * 8 / 1e9:.1f} GB and {n_kept * w['patch'] ** 2 * 13 / 1e9:.1f} GB of output "
                          "per step exceed the 126 MB L2; no flush needed",
                    "parallelism": (f"baseline-sharded x{world}; TP/FP/FN summed inside the counting kernel over NVLink peer "
                                    "memory (NCCL only for rendezvous / barriers)") if world > 1 else "single GPU"},
         "e2e": {"value": e2e_value, "unit": "Gpixel/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "note": "pinned host cube copied H2D every step; dataset stays in HBM, metric dict read back"},
+        "e2e_host_result": e2e_host,
         # per step, P = 128: tile_stats_mono_kernel, write_patches_kernel, confusion_kernel;
         # P = 256: big_init / load / sample / pass<0> / median / pass<1> / mad / count / write + confusion_kernel
         "gpu_launches": (3 if w["patch"] == 128 else 10) * args.steps,
         "roofline": roofline,
-        "cpu_baseline": {"value": cpu_v, "unit": "Gpixel/s", "cores": 1, "kind": "port",
+        "extra": extra,
+        "cpu_baseline": {"value": cpu_v, "unit": "Gpixel/s", "cores": 1, "kind": _reference_api()[3],
                          "sample": f"{cpu_bl} baselines x 4 pols x {w['channels']}x{w['times']} ({cpu_npix} px) in {cpu_dt:.1f} s, one process"},
         "host_affinity": (f"{len(cpus)} cores near GPU {local}" if cpus else None),
-        "clocks": clocks, "wall_s": wall, "metrics_last_step": {k_: float(v) for k_, v in m.items()},
+        "clocks": clocks, "wall_s": res["wall"][1] - res["wall"][0],
+        "metrics_last_step": {k_: float(v) for k_, v in m.items()},
     }
     _emit(line)
     if world > 1:
@@ -363,6 +600,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--baselines", type=int, default=0, help="override the 45 baselines per GPU (debug)")
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = the bench workload (default)")
+    ap.add_argument("--lookahead", type=int, default=2, help="create_dataset_async calls kept in flight (0 = sequential)")
+    ap.add_argument("--phase1-stream", default="main", choices=["main", "side"],
+                    help="side: phase 1 of the calls in flight runs on a low-priority side stream (may share SMs with the writer)")
+    ap.add_argument("--no-extra", action="store_true", help="skip e2e_host_result and the c3 / c5 / c4 measurements")
     args = ap.parse_args()
     global ACTIVE
     ACTIVE = WORKLOADS[args.workload]

@@ -22,6 +22,7 @@ from .evaluation import (  # noqa: F401,E402
     compute_statistics,
     compute_statistics_batch,
     evaluate_segmentation,
+    evaluate_segmentation_async,
     evaluate_segmentation_batch,
 )
 from .data_generation import SyntheticDataGenerator  # noqa: F401,E402

@@ -814,8 +814,8 @@ big_write_kernel(BigGeom g, const float* __restrict__ src, const uint8_t* __rest
                 const float fd = (ocol > 0) ? c - Ls[at + db] : (has_left ? c - left0 : 0.f);
                 prev[q] = c;
                 const float gr = sqrt_fast(__fmaf_rn(td, td, fd * fd));
-                wstage[ocol * 3 + 0] = __fmaf_rn(gr, ga, gb);
-                wstage[ocol * 3 + 1] = __fmaf_rn(c, la, lb);
+                wstage[ocol * 3 + 0] = gs.ok ? __fmaf_rn(gr, ga, gb) : nb0;   // flat / all-NaN channel: exactly 0 before ImageNet
+                wstage[ocol * 3 + 1] = ls.ok ? __fmaf_rn(c, la, lb) : nb1;
                 wstage[ocol * 3 + 2] = nb2;
             }
             __syncwarp();

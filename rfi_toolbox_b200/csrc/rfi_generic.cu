@@ -543,7 +543,7 @@ gwrite_kernel(GGeom g, const void* __restrict__ data, const uint8_t* __restrict_
         const T td = (y > 0) ? c - eval_L<DT>(data, g, p, ctx, y - 1, x) : T(0);
         const T fd = (x > 0) ? c - eval_L<DT>(data, g, p, ctx, y, x - 1) : T(0);
         const T gr = sqrt_fast(td * td + fd * fd);
-        const float u0 = (float)((gr - gs.lo) * gs.inv);
+        const float u0 = gs.ok ? (float)((gr - gs.lo) * gs.inv) : 0.f;   // flat / all-NaN channel: zeros
         float o1, o2;
         if constexpr (kComplexBranch) {
             T u = (c - T(-3.0)) * T(1.0 / 7.0);
@@ -552,7 +552,7 @@ gwrite_kernel(GGeom g, const void* __restrict__ data, const uint8_t* __restrict_
             const T c2 = (ph + T(3.141592653589793)) / T(6.283185307179586);
             o2 = ((float)c2 - mean2) / std2;
         } else {
-            const float u1 = (float)((c - ls.lo) * ls.inv);
+            const float u1 = ls.ok ? (float)((c - ls.lo) * ls.inv) : 0.f;
             o1 = __fmaf_rn(u1, is1, nb1);
             o2 = nb2;
         }

@@ -459,56 +459,80 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
     // ================= median of the raw tile (two middle order statistics) =================
     K v1k = 0, v2k = 0;
     if (need_median) {
+        // A bracket that misses the target rank (~0.9 % of tiles at 3 sigma) is retried ONCE, on the side
+        // the counts point to (the adjoining 6 sigma of sample ranks: one more counting sweep, the same
+        // number of candidates), before the tile goes to the general algorithm (~8 monotone tiles).
         const int rho = (int)(((float)(2 * k1 + 1) * (float)sv) / (float)(2 * nv));
         const int ilo = rho - delta, ihi = rho + delta + 1;
-        const K lo = ilo < 0 ? K(0) : samp[ilo];
-        const K hi = ihi >= sv ? kExcl - 1 : samp[ihi];
-        const K span = hi - lo;
-        uint32_t below = 0, mine = 0;
+        K lo = ilo < 0 ? K(0) : samp[ilo];
+        K hi = ihi >= sv ? kExcl - 1 : samp[ihi];
+        uint32_t M = 0, B = 0;
+#pragma unroll 1
+        for (int attempt = 0;; ++attempt) {
+            const K span = hi - lo;
+            uint32_t below = 0, mine = 0;
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-            K k4[4];
-            if (sizeof(K) == 4) {
-                const uint4 q = *reinterpret_cast<const uint4*>(kp(g));
-                k4[0] = q.x; k4[1] = q.y; k4[2] = q.z; k4[3] = q.w;
-            } else {
+            for (int g = 0; g < G; ++g) {
+                K k4[4];
+                if (sizeof(K) == 4) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(kp(g));
+                    k4[0] = q.x; k4[1] = q.y; k4[2] = q.z; k4[3] = q.w;
+                } else {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) k4[i] = kp(g)[i];
+                    for (int i = 0; i < 4; ++i) k4[i] = kp(g)[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    below += (k4[i] < lo) ? 1u : 0u;
+                    mine += ((K)(k4[i] - lo) <= span) ? 1u : 0u;
+                }
+            }
+            // warp scan of `mine` -> write offsets; block totals through two shared atomics per warp
+            uint32_t incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            uint32_t base = 0;
+            const uint32_t wb = __reduce_add_sync(0xffffffffu, below);
+            if (lane == 31) { base = atomicAdd(&sh.cursor, incl); atomicAdd(&sh.below, wb); }
+            base = __shfl_sync(0xffffffffu, base, 31);
+            uint32_t at = base + incl - mine;
+            __syncthreads();
+            M = sh.cursor; B = sh.below;
+            const bool low = B > k1, high = k2 >= B + M;   // the target rank lies below / above the bracket
+            if (M > (uint32_t)kMonoCap || low || high) {
+                if (attempt == 1 || M > (uint32_t)kMonoCap || (low && lo == 0) || (high && hi >= kExcl - 1)) { give_up(3); return; }
+                if (low) {
+                    const int j = ilo - 2 * delta;
+                    hi = lo - 1;
+                    lo = j < 0 ? K(0) : samp[j];
+                } else {
+                    const int j = ihi + 2 * delta;
+                    lo = hi + 1;
+                    hi = j >= sv ? kExcl - 1 : samp[j];
+                }
+                __syncthreads();  // every thread has read the totals
+                if (tid == 0) { sh.cursor = 0; sh.below = 0; }
+                __syncthreads();
+                continue;
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                below += (k4[i] < lo) ? 1u : 0u;
-                mine += ((K)(k4[i] - lo) <= span) ? 1u : 0u;
+            for (int g = 0; g < G; ++g) {
+                K k4[4];
+                if (sizeof(K) == 4) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(kp(g));
+                    k4[0] = q.x; k4[1] = q.y; k4[2] = q.z; k4[3] = q.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) k4[i] = kp(g)[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if ((K)(k4[i] - lo) <= span) cand[at++] = k4[i];
             }
-        }
-        // warp scan of `mine` -> write offsets; block totals through two shared atomics per warp
-        uint32_t incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        uint32_t base = 0;
-        const uint32_t wb = __reduce_add_sync(0xffffffffu, below);
-        if (lane == 31) { base = atomicAdd(&sh.cursor, incl); atomicAdd(&sh.below, wb); }
-        base = __shfl_sync(0xffffffffu, base, 31);
-        uint32_t at = base + incl - mine;
-        __syncthreads();
-        const uint32_t M = sh.cursor, B = sh.below;
-        if (M > (uint32_t)kMonoCap || B > k1 || k2 >= B + M) { give_up(3); return; }
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-            K k4[4];
-            if (sizeof(K) == 4) {
-                const uint4 q = *reinterpret_cast<const uint4*>(kp(g));
-                k4[0] = q.x; k4[1] = q.y; k4[2] = q.z; k4[3] = q.w;
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) k4[i] = kp(g)[i];
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if ((K)(k4[i] - lo) <= span) cand[at++] = k4[i];
+            break;
         }
         __syncthreads();
         mono_resolve<K, NT>(cand, M, k1 - B, k2 - B, v1k, v2k, sh);

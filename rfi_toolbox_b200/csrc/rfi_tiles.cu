@@ -15,6 +15,8 @@
 // Reference semantics: rfi_toolbox/preprocessing/preprocessor.py:22-42, 413-446, 562-783
 // (restated in SURVEY.md Appendix A).  Statistics are rotation invariant for dims divisible
 // by P, so they are computed once per original tile and shared by the R rotated patches.
+#include <stdlib.h>
+
 #include "rfi_tiles.cuh"
 #include "rfi_stats_mono.cuh"
 
@@ -503,7 +505,9 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
                 const T fd = (ocol > 0) ? c - Ls[at + db] : T(0);
                 prev[q] = c;
                 const T g = sqrt_fast(Scalar<T>::fma(td, td, fd * fd));
-                const float o0 = (float)Scalar<T>::fma(g, ga, gb);  // ((g - lo) * inv) * (1/std) - mean/std, folded
+                // ((g - lo) * inv) * (1/std) - mean/std, folded; a flat (or all-NaN) channel is exactly 0
+                // before the ImageNet step, whatever its pixels hold (preprocessor.py:157-163)
+                const float o0 = gs.ok ? (float)Scalar<T>::fma(g, ga, gb) : nb0;
                 float o1, o2;
                 if constexpr (kComplexBranch) {
                     T u = (c - T(-3.0)) * T(1.0 / 7.0);
@@ -511,7 +515,7 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
                     o1 = __fmaf_rn((float)u, is1, nb1);
                     o2 = Ph[at];
                 } else {
-                    o1 = (float)Scalar<T>::fma(c, la, lb);
+                    o1 = ls.ok ? (float)Scalar<T>::fma(c, la, lb) : nb1;
                     o2 = nb2;
                 }
                 wstage[ocol * 3 + 0] = o0;
@@ -564,10 +568,21 @@ static int launch_stats(const PlanDev& d, long long tiles, const void* data, con
     if constexpr (sizeof(K) == 4) {
         // float32 keys: half of them in the thread-private global scratch, 3 CTAs / SM
         if (!scratch) { set_error("rfi_tile_stats needs the workspace rfi_plan_workspace_bytes() reports"); return RFI_E_INVALID; }
-        auto k = tile_stats_mono_kernel<DT, kMonoNT, true>;
-        const size_t gsmem = (size_t)(kMonoCap + kMonoNT + kMonoGS * kMonoNT * 4) * sizeof(K);
-        RFI_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-        k<<<(unsigned)tiles, kMonoNT, gsmem, st>>>(d, data, flags, stats, static_cast<K*>(scratch));
+        // experiment knobs (co-residency with the writer): RFI_MONO_GS=3 keeps 3 of the 8 key
+        // groups in shared memory (45 KB / CTA instead of 57 KB); RFI_STATS_SMEM_PAD_KB pads the request
+        static const int gs_env = getenv("RFI_MONO_GS") ? atoi(getenv("RFI_MONO_GS")) : kMonoGS;
+        static const int pad_kb = getenv("RFI_STATS_SMEM_PAD_KB") ? atoi(getenv("RFI_STATS_SMEM_PAD_KB")) : 0;
+        if (gs_env == 3) {
+            auto k = tile_stats_mono_kernel<DT, kMonoNT, true, kMonoGKB, 3>;
+            const size_t gsmem = (size_t)(kMonoCap + kMonoNT + 3 * kMonoNT * 4) * sizeof(K) + (size_t)pad_kb * 1024;
+            RFI_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+            k<<<(unsigned)tiles, kMonoNT, gsmem, st>>>(d, data, flags, stats, static_cast<K*>(scratch));
+        } else {
+            auto k = tile_stats_mono_kernel<DT, kMonoNT, true>;
+            const size_t gsmem = (size_t)(kMonoCap + kMonoNT + kMonoGS * kMonoNT * 4) * sizeof(K) + (size_t)pad_kb * 1024;
+            RFI_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+            k<<<(unsigned)tiles, kMonoNT, gsmem, st>>>(d, data, flags, stats, static_cast<K*>(scratch));
+        }
     } else {
         auto mono = tile_stats_mono_kernel<DT, kMonoNT>;
         size_t msmem = (size_t)(kP * kP + kMonoCap + kMonoNT) * sizeof(K);
@@ -586,9 +601,11 @@ static int launch_write(const PlanDev& d, long long tiles, const void* data, con
                         uint8_t* labels, const float* mag_scratch, cudaStream_t st) {
     using T = typename In<DT>::T;
     auto kern = write_patches_kernel<DT, NT, CB>;
+    static const int pad_kb = getenv("RFI_WRITER_SMEM_PAD_KB") ? atoi(getenv("RFI_WRITER_SMEM_PAD_KB")) : 0;  // experiment knob
     size_t smem = (size_t)kP * Phase2Smem<T>::kPitch * sizeof(T) +
                   (CB ? (size_t)kP * Phase2Smem<T>::kPitch * sizeof(float) : 0) +
-                  (size_t)kP * Phase2Smem<T>::kFlagPitch + (size_t)(NT / 32) * (3 * kP * sizeof(float));
+                  (size_t)kP * Phase2Smem<T>::kFlagPitch + (size_t)(NT / 32) * (3 * kP * sizeof(float)) +
+                  (size_t)pad_kb * 1024;
     RFI_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)tiles, NT, smem, st>>>(d, data, flags, stats, dest, images, labels, mag_scratch);
     return RFI_OK;

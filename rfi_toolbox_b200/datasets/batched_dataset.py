@@ -48,6 +48,41 @@ class TorchDataset:
     def to(self, device):
         return TorchDataset(self.images.to(device), self.labels.to(device), self.metadata)
 
+    def to_host_async(self, images_out=None, labels_out=None, stream=None):
+        """Device-resident dataset -> pinned host memory, asynchronously (the hand-over the
+        reference's callers get for free: its tensors are host tensors, batched_dataset.py:25-33).
+        `images_out` / `labels_out`: pinned buffers of at least this dataset's size to reuse
+        (pinning costs more than the copy); `stream`: side stream to copy on (default: the current
+        one).  Returns `(host_dataset, event)`; the host tensors are valid once `event` is done."""
+        if not self.images.is_cuda:
+            return self, None
+        n = len(self)
+        dev = self.images.device
+
+        def dst(out, src):
+            if out is None:
+                return torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+            assert out.is_pinned() and out.dtype == src.dtype and out.numel() >= src.numel()
+            return out.view(-1)[:src.numel()].view(src.shape)
+
+        hi, hl = dst(images_out, self.images), dst(labels_out, self.labels)
+        cur = torch.cuda.current_stream(dev)
+        st = stream or cur
+        if st is not cur:
+            st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            hi.copy_(self.images, non_blocking=True)
+            hl.copy_(self.labels, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(st)
+        if st is not cur:
+            self.images.record_stream(st)
+            self.labels.record_stream(st)
+        host = TorchDataset.__new__(TorchDataset)
+        host.images, host.labels, host.metadata = hi, hl, self.metadata
+        assert len(hi) == n
+        return host, ev
+
     def save_to_disk(self, path):
         path = Path(path)
         path.parent.mkdir(parents=True, exist_ok=True)

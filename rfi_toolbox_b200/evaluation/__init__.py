@@ -6,7 +6,9 @@ from .metrics import (
     compute_precision,
     compute_recall,
     confusion_counts,
+    confusion_counts_async,
     evaluate_segmentation,
+    evaluate_segmentation_async,
     evaluate_segmentation_batch,
 )
 from .statistics import (
@@ -21,6 +23,6 @@ from .statistics import (
 
 __all__ = [
     "compute_iou", "compute_precision", "compute_recall", "compute_f1", "compute_dice",
-    "evaluate_segmentation", "evaluate_segmentation_batch", "confusion_counts",
+    "evaluate_segmentation", "evaluate_segmentation_async", "evaluate_segmentation_batch", "confusion_counts", "confusion_counts_async",
     "compute_statistics", "compute_ffi", "compute_mad", "compute_statistics_batch", "compute_ffi_batch", "compute_calcquality", "print_statistics_comparison",
 ]

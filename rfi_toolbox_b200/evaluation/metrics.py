@@ -6,7 +6,7 @@ from the guard branches).  The boolean reductions run on the GPU in one pass
 in float64 with the reference's own guard branches, which reproduces it to the last bit
 (including f1 != dice in the last ulp, metrics.py:120-126 vs :145-152).
 
-Extensions (not in the reference): `confusion_counts`, `evaluate_segmentation_batch`
+Extensions (not in the reference): `confusion_counts`, `evaluate_segmentation_async`, `evaluate_segmentation_batch`
 (per-pair sweep in one launch) and the `group=` keyword, which all-reduces {TP, FP, FN}
 over a torch.distributed process group when masks are sharded by baseline across GPUs.
 """
@@ -66,8 +66,9 @@ def _counts_tensor(pred, true, n_seg=None, seg=None):
 
 
 def _counts_allreduced(pred, true, ctx):
-    """{TP, FP, FN} summed over the ranks of `ctx` by ONE kernel: the reduction's last CTA exchanges
-    the totals through NVLink peer memory (`rfi_confusion_counts_allreduce`)."""
+    """{TP, FP, FN, missing} (device int64[4]) summed over the ranks of `ctx` by ONE kernel: the
+    reduction's last CTA exchanges the totals through NVLink peer memory
+    (`rfi_confusion_counts_allreduce`)."""
     lib = _native.load()
     device = ctx.device
     p, ep, fp = _mask_operand(pred, device)
@@ -80,16 +81,47 @@ def _counts_allreduced(pred, true, ctx):
                                                 ctx.ptrs, ctx.world, ctx.rank, ctx.next_epoch(),
                                                 counts.data_ptr(), current_stream_ptr(device))
         _native.check(rc, "rfi_confusion_counts_allreduce")
-    tp, fpc, fn, missing = counts.tolist()
-    if missing:
-        raise RuntimeError(f"{missing} rank(s) never reached the metric exchange (epoch {ctx.epoch})")
-    return tp, fpc, fn
+    return counts, ctx.epoch
 
 
-def confusion_counts(pred, true, group=None):
-    """(TP, FP, FN) as Python ints; summed over `group` if given (`True` = the default process
-    group).  On one box the sum happens inside the counting kernel, over NVLink peer memory;
-    `RFI_NO_PEER=1`, several hosts or missing CUDA IPC fall back to an NCCL all-reduce."""
+class PendingCounts:
+    """{TP, FP, FN} of a `confusion_counts_async` call: the counting kernel and the copy of its three
+    totals to pinned host memory are enqueued; `result()` waits for that copy only -- not for
+    whatever the caller enqueued afterwards (a plain `.tolist()` would drain the stream)."""
+
+    def __init__(self, counts_dev, epoch=None):
+        self._epoch = epoch
+        self._host = torch.empty(counts_dev.shape, dtype=torch.int64, pin_memory=True)
+        self._host.copy_(counts_dev, non_blocking=True)
+        self._event = torch.cuda.Event()
+        self._event.record()
+        self._value = None
+
+    def result(self):
+        if self._value is None:
+            self._event.synchronize()
+            vals = self._host.tolist()
+            if len(vals) == 4 and vals[3]:
+                raise RuntimeError(f"{vals[3]} rank(s) never reached the metric exchange (epoch {self._epoch})")
+            self._value = tuple(vals[:3])
+            self._host = None
+        return self._value
+
+
+class PendingMetrics:
+    """`evaluate_segmentation_async` handle; `result()` -> the metric dict."""
+
+    def __init__(self, counts):
+        self._counts = counts
+
+    def result(self):
+        return _ratios(*self._counts.result())
+
+
+def confusion_counts_async(pred, true, group=None):
+    """`confusion_counts` without the host synchronisation: -> `PendingCounts`.  With `group`, the
+    sum over the ranks happens inside the counting kernel (NVLink peer memory); `RFI_NO_PEER=1`,
+    several hosts or missing CUDA IPC fall back to an NCCL all-reduce enqueued behind the kernel."""
     if group is not None:
         import os
 
@@ -102,13 +134,23 @@ def confusion_counts(pred, true, group=None):
                 from ..utils.peer import peer_context
                 ctx = peer_context(g, device)
             if ctx is not None:
-                return _counts_allreduced(pred, true, ctx)
+                counts, epoch = _counts_allreduced(pred, true, ctx)
+                with torch.cuda.device(device):
+                    return PendingCounts(counts, epoch)
             counts = _counts_tensor(pred, true)
             dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=g)
-            tp, fp, fn = counts.tolist()
-            return tp, fp, fn
-    tp, fp, fn = _counts_tensor(pred, true).tolist()
-    return tp, fp, fn
+            with torch.cuda.device(counts.device):
+                return PendingCounts(counts)
+    counts = _counts_tensor(pred, true)
+    with torch.cuda.device(counts.device):
+        return PendingCounts(counts)
+
+
+def confusion_counts(pred, true, group=None):
+    """(TP, FP, FN) as Python ints; summed over `group` if given (`True` = the default process
+    group).  On one box the sum happens inside the counting kernel, over NVLink peer memory;
+    `RFI_NO_PEER=1`, several hosts or missing CUDA IPC fall back to an NCCL all-reduce."""
+    return confusion_counts_async(pred, true, group=group).result()
 
 
 def _ratios(tp, fp, fn):
@@ -129,6 +171,13 @@ def _ratios(tp, fp, fn):
 def evaluate_segmentation(pred, true, group=None):
     """metrics.py:155-172 -> {'iou','precision','recall','f1','dice'}."""
     return _ratios(*confusion_counts(pred, true, group=group))
+
+
+def evaluate_segmentation_async(pred, true, group=None):
+    """`evaluate_segmentation` for streaming callers: the counting kernel and the download of its
+    three totals are enqueued, the ratios are formed in `result()`.  Reading the metrics of step k
+    after step k + 1 has been enqueued keeps the GPU queue from draining between steps."""
+    return PendingMetrics(confusion_counts_async(pred, true, group=group))
 
 
 def compute_iou(pred, true):

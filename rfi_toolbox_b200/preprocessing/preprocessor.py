@@ -20,13 +20,14 @@ from __future__ import annotations
 
 import ctypes as C
 import logging
+import threading
 
 import numpy as np
 import torch
 
 from .. import _native
 from ..datasets.batched_dataset import TorchDataset
-from ..utils.device import as_device_tensor, as_host_tensor, copy_stream, current_stream_ptr, require_cuda
+from ..utils.device import as_device_tensor, as_host_tensor, copy_stream, current_stream_ptr, phase1_stream, require_cuda
 
 logger = logging.getLogger(__name__)
 
@@ -88,24 +89,73 @@ def _keep_in_canonical_order(keep_tile, n_rot):
     return np.concatenate(parts, axis=1).reshape(-1)
 
 
-_HOST_BUFFERS = {}
+class _HostBuffers:
+    """Pinned staging buffers of ONE call in flight (flag counts down, destination slots up)."""
+
+    def __init__(self, n_groups, n_patches):
+        self.nflag = torch.empty(n_groups, dtype=torch.int32, pin_memory=True)
+        self.dest = torch.empty(n_patches, dtype=torch.int64, pin_memory=True)
+        self.order = torch.empty(n_patches, dtype=torch.int64)
+        self.nflag_np, self.dest_np, self.order_np = self.nflag.numpy(), self.dest.numpy(), self.order.numpy()
+        self.event = torch.cuda.Event()    # the flag counts have landed
+        self.copied = torch.cuda.Event()   # the destination slots have left the pinned buffer
+        self.busy = False
 
 
-def _host_buffers(device, n_groups, n_patches):
-    """Pinned staging buffers (flag counts down, destination slots up), grown on demand and
-    reused across calls: pinning memory costs more than the whole host phase."""
-    key = (device.index,)
-    hb = _HOST_BUFFERS.get(key)
-    if hb is None or hb["nflag"].numel() < n_groups or hb["dest"].numel() < n_patches:
-        g = max(n_groups, 2 * hb["nflag"].numel() if hb else 0)
-        n = max(n_patches, 2 * hb["dest"].numel() if hb else 0)
-        hb = {"nflag": torch.empty(g, dtype=torch.int32, pin_memory=True),
-              "dest": torch.empty(n, dtype=torch.int64, pin_memory=True),
-              "order": torch.empty(n, dtype=torch.int64),
-              "event": torch.cuda.Event(), "copied": torch.cuda.Event()}
-        hb["nflag_np"], hb["dest_np"], hb["order_np"] = hb["nflag"].numpy(), hb["dest"].numpy(), hb["order"].numpy()
-        _HOST_BUFFERS[key] = hb
+_HOST_POOL = {}
+_HOST_POOL_LOCK = threading.Lock()
+
+
+def _acquire_host_buffers(device, n_groups, n_patches):
+    """Pinned memory is expensive to allocate (more than the whole host phase), so the staging
+    buffers are pooled per device and grown on demand.  Every call in flight -- several when
+    `create_dataset_async` is used with lookahead, or from several threads -- owns its own set
+    from `acquire` until its destination slots have been uploaded (`_release_host_buffers`)."""
+    with _HOST_POOL_LOCK:
+        pool = _HOST_POOL.setdefault(device.index, [])
+        for hb in pool:
+            if not hb.busy and hb.nflag.numel() >= n_groups and hb.dest.numel() >= n_patches:
+                hb.busy = True
+                break
+        else:
+            big = max(pool, key=lambda h: h.dest.numel(), default=None)
+            g = max(n_groups, 2 * big.nflag.numel() if big and big.nflag.numel() < n_groups else 0)
+            n = max(n_patches, 2 * big.dest.numel() if big and big.dest.numel() < n_patches else 0)
+            hb = _HostBuffers(g, n)
+            hb.busy = True
+            pool[:] = [h for h in pool if h.busy or (h.nflag.numel() >= g and h.dest.numel() >= n)][-7:] + [hb]
+    hb.copied.synchronize()  # a previous owner's upload has left the pinned buffer
     return hb
+
+
+def _release_host_buffers(hb):
+    with _HOST_POOL_LOCK:
+        hb.busy = False
+
+
+class PendingDataset:
+    """Handle of a `create_dataset_async` call: phase 1 (statistics and flag counts) is enqueued, the
+    host phase and phase 2 run in `result()`.
+
+    `result()` draws the call's ONE `np.random.permutation` from the global legacy generator
+    (preprocessor.py:760), so call it in the order the reference would have called
+    `create_dataset` -- the k-th `result()` then consumes exactly the k-th call's share of the
+    stream.  Between `create_dataset_async` and `result()` the GPU works on this call's statistics
+    while the host (and the GPU) finish the previous call: the host phase of call k -- waiting for
+    the flag counts, the shuffle, the upload of the destination slots -- hides behind phase 1 of
+    call k + 1."""
+
+    def __init__(self, pre, ctx=None, dataset=None):
+        self._pre, self._ctx, self._dataset = pre, ctx, dataset
+
+    def done(self):
+        return self._dataset is not None
+
+    def result(self):
+        if self._dataset is None:
+            self._dataset = self._pre._complete(self._ctx)
+            self._ctx = None
+        return self._dataset
 
 
 class Preprocessor:
@@ -113,6 +163,12 @@ class Preprocessor:
 
     #: host (pinned) input is uploaded in this many baseline chunks, overlapped with phase 1
     upload_chunks = 8
+
+    #: "side": `create_dataset_async` enqueues phase 1 (and the download of the flag counts) on a
+    #: per-device side stream, so that the statistics kernel of call k + 1 can share the SMs with the
+    #: writer of call k (one is issue-bound, the other HBM-bound).  The side stream waits for the
+    #: work already queued on the current stream unless the call is told `input_ready=True`.
+    phase1_stream = None
 
     #: when True, CUDA events bracket the two kernels of every call (read by bench.py):
     #: `self.events = {"stats": (start, stop), "write": (start, stop)}` on the current stream.
@@ -165,6 +221,36 @@ class Preprocessor:
     ):
         """preprocessor.py:198-411.  `num_workers` is accepted and ignored (there is no
         process pool on the GPU path)."""
+        return self.create_dataset_async(
+            patch_size=patch_size, stretch=stretch, flag_sigma=flag_sigma, use_custom_flags=use_custom_flags,
+            num_patches=num_patches, normalize_before_stretch=normalize_before_stretch,
+            normalize_after_stretch=normalize_after_stretch, num_workers=num_workers,
+            enable_augmentation=enable_augmentation, augmentation_rotations=augmentation_rotations,
+            inference_mode=inference_mode).result()
+
+    def create_dataset_async(
+        self,
+        patch_size=128,
+        stretch=None,
+        flag_sigma=5,
+        use_custom_flags=True,
+        num_patches=None,
+        normalize_before_stretch=True,
+        normalize_after_stretch=False,
+        num_workers=4,
+        enable_augmentation=True,
+        augmentation_rotations=4,
+        inference_mode=False,
+        *,
+        input_ready=False,
+    ):
+        """Same arguments as `create_dataset`; enqueues phase 1 and returns a `PendingDataset` whose
+        `result()` is the dataset.  `create_dataset(...)` == `create_dataset_async(...).result()`.
+        Streaming callers (one Preprocessor per sample / baseline chunk, the reference's own unit of
+        work, synthetic_generator.py:55-107) keep one or two calls in flight so that the host phase
+        of each hides behind the statistics kernel of the next (`iter_dataset_chunks(lookahead=)`).
+        `input_ready=True` (only read when `phase1_stream == "side"`): the caller guarantees that the
+        input tensors are complete, so phase 1 need not wait for work queued on the current stream."""
         lib = _native.load()
         device = self._resolve_device()
         if stretch and stretch not in ("SQRT", "LOG10"):
@@ -182,7 +268,7 @@ class Preprocessor:
 
         custom = bool(use_custom_flags and self.flags is not None)
         flags = None
-        if custom and not inference_mode or custom:
+        if custom:
             if self.flags.ndim != 4:
                 # the reference fails unpacking `.shape` of a 1-D row here (quirk Q7)
                 raise ValueError("flags must be 4-D (baselines, pols, channels, times)")
@@ -246,10 +332,16 @@ class Preprocessor:
                 data = host.to(device, non_blocking=True)
             images, labels, order = self._create_padded(lib, device, plan, views, data, flags, R, B * npol, C_, T_, P,
                                                         inference_mode, num_patches)
-            return self._finish(images, labels, order, patch_size, stretch, flag_sigma, normalize_before_stretch,
-                                normalize_after_stretch, augmentation_rotations)
+            return PendingDataset(self, dataset=self._finish(
+                images, labels, order, patch_size, stretch, flag_sigma, normalize_before_stretch,
+                normalize_after_stretch, augmentation_rotations))
 
-        with torch.cuda.device(device):
+        side1 = None
+        if self.phase1_stream == "side" and host is None:
+            side1 = phase1_stream(device)
+            if not input_ready:
+                side1.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.device(device), torch.cuda.stream(side1 if side1 is not None else torch.cuda.current_stream(device)):
             stream = current_stream_ptr(device)
             fptr = flags.data_ptr() if flags is not None else None
             # ---- phase 1: statistics + flag counts per original tile
@@ -299,21 +391,50 @@ class Preprocessor:
                 # the real branch keeps it: phase 2 reads the exact magnitudes phase 1 left there.
                 work, wptr = None, None
 
+            # ---- flag counts down to pinned memory; the host phase (`_complete`) waits for them
+            hb = _acquire_host_buffers(device, max(n_tiles, 1), max(n0, 1))
+            if not inference_mode:
+                hb.nflag[:n_tiles].copy_(stats[:n_tiles].view(torch.int32)[:, 16], non_blocking=True)
+                hb.event.record()
+            done1 = None
+            if side1 is not None:
+                done1 = torch.cuda.Event()
+                done1.record()
+        ctx = dict(side1=side1, done1=done1, lib=lib, device=device, plan=plan, data=data, flags=flags, stats=stats, work=work, hb=hb, ev=ev,
+                   n_tiles=n_tiles, n0=n0, P=P, C_=C_, T_=T_, skip_patchify=skip_patchify,
+                   inference_mode=inference_mode, num_patches=num_patches,
+                   meta=(patch_size, stretch, flag_sigma, normalize_before_stretch, normalize_after_stretch,
+                         augmentation_rotations))
+        return PendingDataset(self, ctx=ctx)
+
+    def _complete(self, ctx):
+        """Host phase + phase 2 of a call whose phase 1 is enqueued (see `PendingDataset`)."""
+        lib, device, plan, hb, ev = ctx["lib"], ctx["device"], ctx["plan"], ctx["hb"], ctx["ev"]
+        data, flags, stats, work = ctx["data"], ctx["flags"], ctx["stats"], ctx["work"]
+        n_tiles, n0, P, C_, T_ = ctx["n_tiles"], ctx["n0"], ctx["P"], ctx["C_"], ctx["T_"]
+        skip_patchify, inference_mode, num_patches = ctx["skip_patchify"], ctx["inference_mode"], ctx["num_patches"]
+        with torch.cuda.device(device):
+            stream = current_stream_ptr(device)
+            if ctx["side1"] is not None:
+                # phase 1 ran on the side stream: phase 2 (this stream) starts after it and keeps its buffers
+                cur = torch.cuda.current_stream(device)
+                cur.wait_event(ctx["done1"])
+                for t in (stats, work):
+                    if t is not None:
+                        t.record_stream(cur)
+            fptr = flags.data_ptr() if flags is not None else None
+            wptr = work.data_ptr() if work is not None else None
             # ---- host: blank-patch compaction + shuffle -> destination slot of every patch
             #      (one native call on pinned buffers; draws the ONE np.random.permutation of
             #      preprocessor.py:760 from the global legacy stream)
-            hb = _host_buffers(device, max(n_tiles, 1), max(n0, 1))
-            hb["copied"].synchronize()  # the previous call's upload has left the pinned buffer
             nflag = None
             if not inference_mode:
-                hb["nflag"][:n_tiles].copy_(stats[:n_tiles].view(torch.int32)[:, 16], non_blocking=True)
-                hb["event"].record()
-                hb["event"].synchronize()
-                nflag = hb["nflag_np"][:n_tiles]
-            n_out = _native.plan_slots(plan, nflag, not inference_mode, num_patches, hb["order_np"], hb["dest_np"])
+                hb.event.synchronize()
+                nflag = hb.nflag_np[:n_tiles]
+            n_out = _native.plan_slots(plan, nflag, not inference_mode, num_patches, hb.order_np, hb.dest_np)
             dest_dev = torch.empty(max(n0, 1), dtype=torch.int64, device=device)
-            dest_dev.copy_(hb["dest"][:max(n0, 1)], non_blocking=True)
-            hb["copied"].record()
+            dest_dev.copy_(hb.dest[:max(n0, 1)], non_blocking=True)
+            hb.copied.record()
 
             # ---- phase 2: every kept patch written once, at its final position
             images = torch.empty((n_out, P if not skip_patchify else C_, P if not skip_patchify else T_, 3),
@@ -330,10 +451,10 @@ class Preprocessor:
             # host bookkeeping after the launch: the GPU idles between the phases, not here
             if not inference_mode and nflag is not None and not (nflag > 0).any():
                 logger.warning("No flagged patches found - keeping all patches")
-            order = hb["order_np"][:n_out].copy()
+            order = hb.order_np[:n_out].copy()
+            _release_host_buffers(hb)
 
-        return self._finish(images, labels, order, patch_size, stretch, flag_sigma, normalize_before_stretch,
-                            normalize_after_stretch, augmentation_rotations)
+        return self._finish(images, labels, order, *ctx["meta"])
 
     # ---------------------------------------------------------------- zero-padded geometries
     @staticmethod
@@ -384,18 +505,17 @@ class Preprocessor:
             if ev:
                 ev[1].record()
             # canonical order of a padded geometry: [waterfall][view][tile of the rotated grid]
-            hb = _host_buffers(device, max(n0, 1), max(n0, 1))
-            hb["copied"].synchronize()
+            hb = _acquire_host_buffers(device, max(n0, 1), max(n0, 1))
             nflag = None
             if not inference_mode:
                 counts = torch.stack([st[3].view(torch.int32)[:, 16].reshape(n_wf, per) for st in state], dim=1)
-                hb["nflag"][:n0].copy_(counts.reshape(-1), non_blocking=True)
-                hb["event"].record()
-                hb["event"].synchronize()
-                nflag = hb["nflag_np"][:n0]
-            n_out = _native.plan_slots(plan, nflag, not inference_mode, num_patches, hb["order_np"], hb["dest_np"])
-            dest = hb["dest"][:n0].to(device, non_blocking=True).view(n_wf, R, per)
-            hb["copied"].record()
+                hb.nflag[:n0].copy_(counts.reshape(-1), non_blocking=True)
+                hb.event.record()
+                hb.event.synchronize()
+                nflag = hb.nflag_np[:n0]
+            n_out = _native.plan_slots(plan, nflag, not inference_mode, num_patches, hb.order_np, hb.dest_np)
+            dest = hb.dest[:n0].to(device, non_blocking=True).view(n_wf, R, per)
+            hb.copied.record()
             images = torch.empty((n_out, P, P, 3), dtype=torch.float32, device=device)
             labels = torch.empty((n_out, P, P), dtype=torch.uint8, device=device)
             if ev:
@@ -411,7 +531,8 @@ class Preprocessor:
                 self.events = {"stats": (ev[0], ev[1]), "write": (ev[2], ev[3])}
             if not inference_mode and nflag is not None and not (nflag > 0).any():
                 logger.warning("No flagged patches found - keeping all patches")
-            order = hb["order_np"][:n_out].copy()
+            order = hb.order_np[:n_out].copy()
+            _release_host_buffers(hb)
             self.last_tile_stats = torch.stack([st[3].view(n_wf, per, -1) for st in state], dim=1).reshape(n0, -1)
         return images, labels, order
 
@@ -435,7 +556,7 @@ class Preprocessor:
 
 
 def iter_dataset_chunks(data, flags=None, *, chunk_baselines, magnitude=False, device=None, pin=True,
-                        **create_kw):
+                        lookahead=1, **create_kw):
     """Stream a cube whose output does not fit in HBM at once (BASELINE config 5: 44 baselines x 4
     pols x 1024 x 16384 per GPU give 153 GB of patches) through `create_dataset` in contiguous
     baseline chunks.  Yields `(b0, b1, dataset)`; release `dataset` (or hand it to `BatchWriter`)
@@ -447,14 +568,30 @@ def iter_dataset_chunks(data, flags=None, *, chunk_baselines, magnitude=False, d
     same semantics as the per-rank baseline shards (`utils.sharding.baseline_shard`): blank-patch
     removal and the shuffle are per chunk, and each chunk draws one `np.random.permutation` from
     the global legacy generator, in chunk order.  Host input is uploaded chunk by chunk (pinned,
-    overlapped with phase 1), so the full cube never has to be resident either."""
+    overlapped with phase 1), so the full cube never has to be resident either.
+
+    `lookahead` chunks are kept in flight through `create_dataset_async`: phase 1 (and the upload)
+    of chunk c + 1 .. c + lookahead is enqueued before chunk c's host phase, which therefore costs
+    no GPU time.  `lookahead=0` is the plain sequential loop.  The permutations are still drawn in
+    chunk order (they are drawn in `result()`)."""
+    from collections import deque
+
     n_bl = data.shape[0] if data.ndim == 4 else 1
     if data.ndim == 3:
         data = data[None, ...]
     if chunk_baselines < 1:
         raise ValueError("chunk_baselines must be >= 1")
+    if lookahead < 0:
+        raise ValueError("lookahead must be >= 0")
+    pending = deque()
     for b0 in range(0, n_bl, int(chunk_baselines)):
         b1 = min(n_bl, b0 + int(chunk_baselines))
         pre = Preprocessor(data[b0:b1], None if flags is None else flags[b0:b1],
                            magnitude=magnitude, device=device, pin=pin)
-        yield b0, b1, pre.create_dataset(**create_kw)
+        pending.append((b0, b1, pre.create_dataset_async(**create_kw)))
+        if len(pending) > lookahead:
+            c0, c1, pd = pending.popleft()
+            yield c0, c1, pd.result()
+    while pending:
+        c0, c1, pd = pending.popleft()
+        yield c0, c1, pd.result()

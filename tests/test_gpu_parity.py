@@ -298,3 +298,104 @@ def test_pinned_host_input_chunked_upload(native_lib, chunks):
     ds = pre.create_dataset(**kw)
     torch.cuda.synchronize()
     _compare(ds, ods, inter, pre)
+
+
+def test_async_calls_in_flight_match_sequential_calls(native_lib):
+    """`create_dataset_async` with several calls in flight: results, patch order and the position of
+    the global NumPy stream equal those of plain sequential `create_dataset` calls (the permutation
+    of call k is drawn in its `result()`), and equal the oracle's."""
+    from rfi_toolbox_b200 import Preprocessor
+    cubes = [make_cube(n_bl=2, n_pol=2, dtype=np.complex64, seed=40 + i)[0] for i in range(4)]
+    kw = dict(stretch="SQRT", flag_sigma=5, use_custom_flags=False)
+    np.random.seed(21)
+    seq = []
+    for c in cubes:
+        pre = Preprocessor(c, None, magnitude=True)
+        ds = pre.create_dataset(**kw)
+        seq.append((pre.order.copy(), ds.labels.cpu().numpy(), ds.images.cpu().numpy()))
+    after_seq = np.random.random()
+    np.random.seed(21)
+    pres = [Preprocessor(c, None, magnitude=True) for c in cubes]
+    pend = [p.create_dataset_async(**kw) for p in pres]          # four calls in flight
+    for (order, labs, imgs), p, pd in zip(seq, pres, pend):
+        ds = pd.result()
+        assert pd.result() is ds                                   # idempotent
+        assert np.array_equal(p.order, order)
+        assert np.array_equal(ds.labels.cpu().numpy(), labs) and np.array_equal(ds.images.cpu().numpy(), imgs)
+    assert np.random.random() == after_seq
+    np.random.seed(21)
+    for c, (order, labs, imgs) in zip(cubes, seq):
+        ods, inter = oracle.create_dataset(np.abs(c), None, return_intermediates=True, **kw)
+        assert np.array_equal(order, inter["order"]) and np.array_equal(labs, ods.labels)
+
+
+@pytest.mark.parametrize("lookahead", [0, 1, 3])
+def test_iter_dataset_chunks_lookahead(native_lib, lookahead):
+    from rfi_toolbox_b200.preprocessing import iter_dataset_chunks
+    data, _ = make_cube(n_bl=5, n_pol=2, dtype=np.complex64, seed=51)
+    kw = dict(patch_size=128, stretch="SQRT", flag_sigma=5, use_custom_flags=False)
+    np.random.seed(5)
+    got = [(b0, b1, ds.images.cpu().numpy(), ds.labels.cpu().numpy())
+           for b0, b1, ds in iter_dataset_chunks(data, chunk_baselines=2, magnitude=True, lookahead=lookahead, **kw)]
+    assert [(g[0], g[1]) for g in got] == [(0, 2), (2, 4), (4, 5)]
+    np.random.seed(5)
+    for b0, b1, imgs, labs in got:
+        ods = oracle.create_dataset(np.abs(data[b0:b1]), None, **kw)
+        assert np.array_equal(labs, ods.labels)
+        assert np.allclose(imgs, ods.images, rtol=IMG_RTOL, atol=IMG_ATOL, equal_nan=True)
+
+
+def test_batch_writer_async_download_overlaps_next_call(native_lib, tmp_path):
+    """CUDA datasets handed to BatchWriter are downloaded to pinned memory on a
+    side stream while the next create_dataset runs; files equal the datasets (batched_dataset.py:126-157)."""
+    import json
+    from rfi_toolbox_b200 import Preprocessor
+    from rfi_toolbox_b200.datasets import BatchWriter
+    kw = dict(stretch="SQRT", flag_sigma=5, use_custom_flags=False)
+    writer = BatchWriter(tmp_path, samples_per_batch=40)
+    want_i, want_l = [], []
+    np.random.seed(9)
+    for i in range(3):
+        data, _ = make_cube(n_bl=1, n_pol=2, dtype=np.complex64, seed=60 + i)
+        ds = Preprocessor(data, None, magnitude=True).create_dataset(**kw)
+        assert ds.images.is_cuda
+        writer.add_batch(ds)                    # async D2H starts here ...
+        want_i.append(ds.images.clone())
+        want_l.append(ds.labels.clone())
+        del ds                                  # ... and must survive the release of the device tensors
+    writer.finalize()
+    want_i, want_l = torch.cat(want_i).cpu(), torch.cat(want_l).cpu()
+    files = sorted(tmp_path.glob("batch_*.pt"))
+    blobs = [torch.load(f) for f in files]
+    assert all(set(b) == {"images", "labels"} for b in blobs)
+    assert all(len(b["images"]) <= 40 for b in blobs)
+    assert torch.equal(torch.cat([b["images"] for b in blobs]), want_i)
+    assert torch.equal(torch.cat([b["labels"] for b in blobs]), want_l)
+    meta = json.loads((tmp_path / "metadata.json").read_text())
+    assert meta["num_samples"] == len(want_i) and meta["num_batches"] == len(files) and meta["image_shape"] == [128, 128, 3]
+    # the pinned-download helper used by the bench's e2e_host_result arm
+    data, _ = make_cube(n_bl=1, n_pol=2, dtype=np.complex64, seed=70)
+    ds = Preprocessor(data, None, magnitude=True).create_dataset(**kw)
+    side = torch.cuda.Stream()
+    host, ev = ds.to_host_async(stream=side)
+    ev.synchronize()
+    assert host.images.is_pinned() and torch.equal(host.images, ds.images.cpu()) and torch.equal(host.labels, ds.labels.cpu())
+
+
+@pytest.mark.parametrize("patch", [128, 256])
+def test_flat_and_all_nan_channels_are_zero(native_lib, patch):
+    """normalize_channel returns zeros when max <= min (preprocessor.py:157-163) -- also for a
+    constant patch that holds NaNs and for an all-NaN patch (nanmin / nanmax are NaN there)."""
+    rng = np.random.default_rng(3)
+    n = 2 * patch
+    data = np.abs(rng.normal(1.0, 0.1, (1, 2, n, n))).astype(np.float32)
+    data[0, 0, :patch, :patch] = 2.0
+    data[0, 0, 5, 7] = np.nan              # constant tile with a NaN
+    data[0, 0, :patch, patch:] = np.nan    # all-NaN tile
+    data[0, 1, patch:, patch:] = 3.5       # plain constant tile
+    flags = np.zeros(data.shape, dtype=bool)
+    flags[..., ::7, ::5] = True
+    kw = dict(patch_size=patch, stretch=None, use_custom_flags=True, normalize_before_stretch=False)
+    pre, ds = _run_gpu(data, flags, **kw)
+    ods, inter = _run_oracle(data, flags, **kw)
+    _compare(ds, ods, inter, pre, label=f"flat / all-NaN P{patch}")
