@@ -60,6 +60,7 @@ WORKLOADS = {
 }
 METRIC = "waterfall Gpixel/s (create_dataset+metrics)"
 _JSON_FD = None  # the real stdout; fd 1 itself is pointed at stderr while the benchmark runs
+METRICS_SIDE = True  # --metrics-stream main switches the counting kernel back to the caller's stream (A/B)
 ACTIVE = WORKLOAD  # set from --workload in main(); inherited by the forked CPU-baseline workers
 
 
@@ -239,9 +240,10 @@ class Runner:
     """K pipelined steps of create_dataset + evaluate_segmentation over one input (device or pinned
     host cube), timed with CUDA events on the current stream; max over ranks."""
 
-    def __init__(self, torch, dist, world, dev, kw, group, lookahead, phase1=None):
+    def __init__(self, torch, dist, world, dev, kw, group, lookahead):
         self.torch, self.dist, self.world, self.dev = torch, dist, world, dev
-        self.kw, self.group, self.lookahead, self.phase1 = kw, group, lookahead, phase1
+        self.kw, self.group, self.lookahead = kw, group, lookahead
+        self.metrics_side = METRICS_SIDE
 
     def barrier(self):
         if self.world > 1:
@@ -259,8 +261,7 @@ class Runner:
         from rfi_toolbox_b200 import Preprocessor
         pre = Preprocessor(data, None, magnitude=True, pin=True)
         pre.profile = profile
-        pre.phase1_stream = self.phase1
-        return pre, pre.create_dataset_async(input_ready=True, **self.kw)
+        return pre, pre.create_dataset_async(**self.kw)
 
     def steps(self, data, truth, n, profile=False, sink=None):
         """n complete steps; returns (last metric dict, per-step kernel events, n_kept of the last step).
@@ -282,7 +283,7 @@ class Runner:
             ds = pd.result()
             if truth is not None:
                 if self.lookahead:
-                    nxt = evaluate_segmentation_async(ds.labels, truth, group=self.group)
+                    nxt = evaluate_segmentation_async(ds.labels, truth, group=self.group, side_stream=self.metrics_side)
                 else:
                     m = evaluate_segmentation(ds.labels, truth, group=self.group)
             if sink is not None:
@@ -323,10 +324,13 @@ class Runner:
 
 
 def _kernel_ms(evs):
-    out = {"stats": [], "write": []}
+    """Mean CUDA-event time of the launches of a step: {"fused"} on the single-launch path,
+    {"stats", "write"} on the two-launch path (None for what did not run)."""
+    out = {"stats": [], "write": [], "fused": []}
     for ev in evs:
         for k in out:
-            out[k].append(ev[k][0].elapsed_time(ev[k][1]))
+            if k in ev:
+                out[k].append(ev[k][0].elapsed_time(ev[k][1]))
     return {k: float(np.mean(v)) if v else None for k, v in out.items()}
 
 
@@ -350,7 +354,7 @@ def _measure_workload(R, w, rank, peak, warmup, steps, torch):
     npix = cube.numel()
     kw = dict(patch_size=w["patch"], stretch=w["stretch"], flag_sigma=w["sigma"], use_custom_flags=False,
               augmentation_rotations=w["rot"])
-    R2 = Runner(torch, R.dist, R.world, R.dev, kw, R.group, R.lookahead, R.phase1)
+    R2 = Runner(torch, R.dist, R.world, R.dev, kw, R.group, R.lookahead)
     # ground truth of the metric = this configuration's own labels with 1 % of pixels toggled
     np.random.seed(0)
     from rfi_toolbox_b200 import Preprocessor
@@ -365,9 +369,12 @@ def _measure_workload(R, w, rank, peak, warmup, steps, torch):
     out = {"workload": _workload_text(w), "gpixel_per_s_per_gpu": npix / sec / 1e9,
            "gpixel_per_s_all_gpus": R.world * npix / sec / 1e9, "ms_per_step": sec * 1e3, "steps": steps,
            "warmup": warmup, "patches_kept": res["kept"], "kept_fraction": k,
-           "phase1_ms": km["stats"], "writer_ms": km["write"],
-           "writer_frac_of_peak": npix * (4 + w["rot"] * k * 13.0) / (km["write"] * 1e-3) / 1e9 / peak,
+           "phase1_ms": km["stats"], "writer_ms": km["write"], "fused_ms": km["fused"],
            "path": _path_roofline(npix, 8, w["rot"], k, truth.numel(), sec, peak)}
+    if km["fused"]:   # single launch: cube read once, every kept patch written once
+        out["fused_frac_of_peak"] = npix * (8 + w["rot"] * k * 13.0) / (km["fused"] * 1e-3) / 1e9 / peak
+    if km["write"]:
+        out["writer_frac_of_peak"] = npix * (4 + w["rot"] * k * 13.0) / (km["write"] * 1e-3) / 1e9 / peak
     del truth, cube
     torch.cuda.empty_cache()
     return out
@@ -375,7 +382,7 @@ def _measure_workload(R, w, rank, peak, warmup, steps, torch):
 
 def _measure_c4(R, peak, torch, n_pairs, warmup, steps):
     """BASELINE configs[3]: compute_ffi + MAD reduction + IoU / F1 over n_pairs 128 x 128 pairs."""
-    from rfi_toolbox_b200 import compute_ffi_batch, evaluate_segmentation_batch
+    from rfi_toolbox_b200 import evaluate_pairs
     dev = R.dev
     g = torch.Generator(device=dev).manual_seed(7)
     true = torch.rand((n_pairs, 128, 128), generator=g, device=dev) < 0.10
@@ -385,9 +392,8 @@ def _measure_c4(R, peak, torch, n_pairs, warmup, steps):
     npix = true.numel()
 
     def one():
-        f = compute_ffi_batch(data, pred, errors="nan")
-        m = evaluate_segmentation_batch(pred, true)
-        return f, m
+        r = evaluate_pairs(data, pred, true, errors="nan")   # ONE launch (rfi_pair_sweep), results read back
+        return r, r
 
     for _ in range(warmup):
         one()
@@ -400,8 +406,8 @@ def _measure_c4(R, peak, torch, n_pairs, warmup, steps):
     R.barrier()
     sec = R.max_over_ranks(e0.elapsed_time(e1) / 1e3) / steps
     alg = npix * 10.0  # complex64 + flags + truth, each read once
-    out = {"workload": f"configs[3] {n_pairs} pairs x 128 x 128 complex64: compute_ffi_batch + evaluate_segmentation_batch "
-                       "(per-pair FFI, MAD / std reduction, IoU, precision, recall, F1, dice)",
+    out = {"workload": f"configs[3] {n_pairs} pairs x 128 x 128 complex64: evaluate_pairs = one rfi_pair_sweep launch "
+                       "(per-pair FFI, MAD / std reduction, IoU, precision, recall, F1, dice), results downloaded every sweep",
            "gpixel_per_s_per_gpu": npix / sec / 1e9, "ms_per_sweep": sec * 1e3, "steps": steps, "warmup": warmup,
            "algorithmic_bytes": alg, "achieved_gbs": alg / sec / 1e9, "frac_of_peak": alg / sec / 1e9 / peak,
            "mean_ffi": float(np.nanmean(f["ffi"])), "mean_iou": float(np.mean(m["iou"]))}
@@ -426,10 +432,6 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     group = True if world > 1 else None
-    if args.phase1_stream == "side":
-        # the caller's stream (host phase, writer, metrics) gets the SMs first; phase 1 of the calls in
-        # flight fills in from the library's low-priority side stream
-        torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=-1))
 
     peaks = {}
     pk = ROOT / "MEASURED_PEAKS.json"
@@ -447,7 +449,7 @@ def run_ours(args):
     npix = cube.numel()
     kw = dict(patch_size=w["patch"], stretch=w["stretch"], flag_sigma=w["sigma"], use_custom_flags=False,
               augmentation_rotations=w["rot"])
-    R = Runner(torch, dist, world, dev, kw, group, args.lookahead, args.phase1_stream if args.phase1_stream != 'main' else None)
+    R = Runner(torch, dist, world, dev, kw, group, args.lookahead)
 
     # ground truth for the metric: the labels of a first pass with 1 % of pixels toggled
     from rfi_toolbox_b200 import Preprocessor
@@ -533,28 +535,38 @@ def run_ours(args):
         return 0
 
     k = n_kept / (n_tiles * w["rot"])
-    # complex64 through the real branch: both writers read the exact float32 magnitudes phase 1 left in
-    # its scratch (4 B / px), not the complex cube (8 B / px); the cube itself is read once, by phase 1
-    alg_bytes = npix * (4 + w["rot"] * k * 13.0)
-    write_ms, stats_ms = km["write"], km["stats"]
-    achieved = alg_bytes / (write_ms * 1e-3) / 1e9
+    sec_step = elapsed / args.steps
     # DRAM bytes of one launch from the committed `ncu --set full` capture of this very workload
     # (profiles/traffic.json, written by scripts/ncu_summary.py); null for any other workload
-    traffic = None
-    tj = ROOT / "profiles" / "traffic.json"
-    if tj.exists() and not args.baselines and args.workload in ("c2", "c5"):
-        kname = "write_patches_kernel" if args.workload == "c2" else "big_write_kernel"
-        traffic = json.loads(tj.read_text()).get(kname, {}).get("dram_bytes_per_launch")
-    sec_step = elapsed / args.steps
-    roofline = {"bound": "hbm", "kernel": "write_patches_kernel" if w["patch"] == 128 else "big_write_kernel",
-                "achieved": achieved, "peak": peak,
-                "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": write_ms,
-                "stats_kernel_ms": stats_ms, "stats_kernel_gbs": npix * (8 + 4) / (stats_ms * 1e-3) / 1e9,
-                "bytes_per_pixel": {"phase1": 8 + 4, "writer": 4 + w["rot"] * k * 13.0,
-                                    "path_minimum": 8 + w["rot"] * k * 13.0},
+    def committed_traffic(kname):
+        tj = ROOT / "profiles" / "traffic.json"
+        if tj.exists() and not args.baselines and args.workload in ("c2", "c5"):
+            return json.loads(tj.read_text()).get(kname, {}).get("dram_bytes_per_launch")
+        return None
+    if km["fused"]:
+        # single launch per step (tile_fused_kernel): the cube is read once (8 B / px), every kept patch
+        # is written once (13 B per output px), nothing else moves: the path minimum of SURVEY 8d
+        kname = "tile_fused_kernel"
+        alg_bytes = npix * (8 + w["rot"] * k * 13.0)
+        kernel_ms = km["fused"]
+        bpp = {"fused": 8 + w["rot"] * k * 13.0, "path_minimum": 8 + w["rot"] * k * 13.0}
+    else:
+        # two launches; complex64 through the real branch: the writer reads the exact float32 magnitudes
+        # phase 1 left in its scratch (4 B / px), the cube itself is read once, by phase 1
+        kname = "write_patches_kernel" if w["patch"] == 128 else "big_write_kernel"
+        alg_bytes = npix * (4 + w["rot"] * k * 13.0)
+        kernel_ms = km["write"]
+        bpp = {"phase1": 8 + 4, "writer": 4 + w["rot"] * k * 13.0, "path_minimum": 8 + w["rot"] * k * 13.0}
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
+                "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": committed_traffic(kname),
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
+                "stats_kernel_ms": km["stats"], "bytes_per_pixel": bpp,
                 "step_ms_device": res["dev_ms"] / args.steps,
                 "path": _path_roofline(npix, 8, w["rot"], k, n_kept * w["patch"] ** 2, sec_step, peak)}
+    if km["stats"]:
+        roofline["stats_kernel_gbs"] = npix * (8 + 4) / (km["stats"] * 1e-3) / 1e9
+    launches_per_step = (2 if km["fused"] else 3) if w["patch"] == 128 else 10
 
     cpu_bl = 2 if w["channels"] * w["times"] <= 1 << 20 else 1
     cpu_v, cpu_npix, cpu_dt = cpu_baseline(cpu_bl, 1)
@@ -564,9 +576,12 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": _workload_text(w),
                    "pixels_per_step_per_gpu": npix, "patches_kept": n_kept,
-                   "issue": (f"streaming: create_dataset_async with {args.lookahead} call(s) in flight (host phase of step k "
-                             "behind phase 1 of step k+1; metrics of step k read after step k+1 is enqueued); K complete steps incl. "
-                             "fill and drain inside the timed region" + ("; phase 1 on a side stream" if args.phase1_stream == "side" else ""))
+                   "launches": ("single launch per create_dataset (tile_fused_kernel: statistics + patches of a tile in one CTA; "
+                                "destination slots drawn ahead, flag counts checked in result())") if km["fused"] else
+                               "two launches per create_dataset (statistics, host shuffle, writer)",
+                   "issue": (f"streaming: create_dataset_async with {args.lookahead} call(s) in flight (the host side of step k "
+                             "behind the kernels of step k+1; metrics of step k read after step k+1 is enqueued); K complete steps incl. "
+                             "fill and drain inside the timed region")
                             if args.lookahead else "sequential: create_dataset, then evaluate_segmentation, per step",
                    "l2": f"input cube {npix * 8 / 1e9:.1f} GB and {n_kept * w['patch'] ** 2 * 13 / 1e9:.1f} GB of output "
                          "per step exceed the 126 MB L2; no flush needed",
@@ -575,9 +590,10 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "Gpixel/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "note": "pinned host cube copied H2D every step; dataset stays in HBM, metric dict read back"},
         "e2e_host_result": e2e_host,
-        # per step, P = 128: tile_stats_mono_kernel, write_patches_kernel, confusion_kernel;
+        # per step, P = 128: tile_fused_kernel + confusion_kernel (two-launch path: tile_stats_mono_kernel,
+        # write_patches_kernel, confusion_kernel);
         # P = 256: big_init / load / sample / pass<0> / median / pass<1> / mad / count / write + confusion_kernel
-        "gpu_launches": (3 if w["patch"] == 128 else 10) * args.steps,
+        "gpu_launches": launches_per_step * args.steps,
         "roofline": roofline,
         "extra": extra,
         "cpu_baseline": {"value": cpu_v, "unit": "Gpixel/s", "cores": 1, "kind": _reference_api()[3],
@@ -601,12 +617,18 @@ def main():
     ap.add_argument("--baselines", type=int, default=0, help="override the 45 baselines per GPU (debug)")
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = the bench workload (default)")
     ap.add_argument("--lookahead", type=int, default=2, help="create_dataset_async calls kept in flight (0 = sequential)")
-    ap.add_argument("--phase1-stream", default="main", choices=["main", "side"],
-                    help="side: phase 1 of the calls in flight runs on a low-priority side stream (may share SMs with the writer)")
+    ap.add_argument("--metrics-stream", default="side", choices=["side", "main"],
+                    help="side: the counting kernel of step k runs on a side stream, next to the statistics kernel of step k+2")
+    ap.add_argument("--single-launch", action="store_true",
+                    help="A/B: opt into the single-launch path (Preprocessor.speculate = True; falls back per call when a tile is blank)")
     ap.add_argument("--no-extra", action="store_true", help="skip e2e_host_result and the c3 / c5 / c4 measurements")
     args = ap.parse_args()
-    global ACTIVE
+    global ACTIVE, METRICS_SIDE
     ACTIVE = WORKLOADS[args.workload]
+    METRICS_SIDE = args.metrics_stream == "side"
+    if args.single_launch:
+        from rfi_toolbox_b200 import Preprocessor
+        Preprocessor.speculate = True
     _reserve_stdout()
     if args.impl == "reference":
         return run_reference(args)

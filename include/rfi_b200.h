@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RFI_B200_ABI_VERSION 5
+#define RFI_B200_ABI_VERSION 6
 
 /* status codes */
 #define RFI_OK 0
@@ -151,6 +151,23 @@ int rfi_write_patches(const rfi_plan_t* plan, const void* data, const uint8_t* f
                       const rfi_tile_stat_t* stats, const int64_t* dest_slot,
                       float* images, uint8_t* labels, void* workspace, void* stream);
 
+/* Phase 1 + phase 2 in ONE launch (P = 128 on-chip path, float32 arithmetic, real branch) -- replaces
+ * the same reference lines as rfi_tile_stats + rfi_write_patches (preprocessor.py:22-42, 413-446,
+ * 562-783) for a caller that knows `dest_slot` BEFORE the statistics exist: inference_mode
+ * (:345-353, no compaction, no shuffle), or MAD flags with the slots of the all-kept case drawn ahead
+ * and the flag counts in `stats` checked afterwards (if a tile came out blank the caller completes
+ * through rfi_write_patches with these `stats`, workspace NULL).  One CTA per original tile keeps the
+ * tile in shared memory from the 128-bit loads to the bulk (TMA) stores of its R patches: the cube
+ * is read once, nothing but the output is written (60 B / px for complex64, R = 4).
+ *   rfi_plan_fusable  1 if the plan can take this path (RFI_PATH_FAST, RFI_F32 or RFI_C64 with
+ *                     magnitude, RFI_FLAGS_MAD or RFI_FLAGS_INFERENCE), else 0
+ *   stats     device, rfi_plan_num_tiles() entries, written (as by rfi_tile_stats)
+ *   other arguments as for rfi_write_patches; no workspace */
+int rfi_plan_fusable(const rfi_plan_t* plan);
+int rfi_fused_patches(const rfi_plan_t* plan, const void* data, const uint8_t* flags,
+                      rfi_tile_stat_t* stats, const int64_t* dest_slot, float* images,
+                      uint8_t* labels, void* stream);
+
 /* Confusion counts -- replaces the boolean reductions of evaluation/metrics.py:36-40,
  * 63-68, 95-99, 142-147.  `elem_*` is the element size in bytes (1, 2, 4 or 8) and
  * `is_float_*` selects float semantics (x != 0, NaN counts as True) over integer ones.
@@ -218,6 +235,28 @@ int rfi_statistics(const void* data, int dtype, const uint8_t* flags, int64_t n,
  *        [i][1] over its unflagged samples (:74), n_flagged filled in [i][1] */
 int rfi_statistics_segmented(const void* data, int dtype, const uint8_t* flags, int64_t n_seg,
                              int64_t seg, rfi_stats_t* out, void* stream);
+
+/* Fused per-pair sweep (BASELINE config 4) -- replaces, for every pair i, compute_ffi(data[i],
+ * flags[i]) (statistics.py:59-97, i.e. compute_statistics before and after flagging, :16-56) AND the
+ * boolean reductions behind evaluate_segmentation(flags[i], truth[i]) (metrics.py:36-40, 63-68, 95-99,
+ * 142-147, 155-172) in ONE launch that reads data, flags and truth once (10 B / px for complex64).
+ *   data     device, n_pairs x seg samples, RFI_F32 or RFI_C64 (|z| fused into the load); seg <= 16384
+ *   flags    device uint8 / bool [n_pairs x seg], the predicted mask (non-zero = flagged), or NULL
+ *   truth    device uint8 / bool [n_pairs x seg], the ground-truth mask, or NULL (counts stay 0)
+ *   stats    device rfi_stats_t[n_pairs][2] as rfi_statistics_segmented writes them, or NULL
+ *   results  device rfi_pair_result_t[n_pairs], or NULL
+ * status: 0 = ffi valid; 1 = the reference's guard (all flagged, or NaN among the unflagged samples,
+ * statistics.py:77-78: ffi = reductions = 0, flagged_fraction = 1); 2 = constant data (MAD or std of 0
+ * before flagging: the reference raises ZeroDivisionError; the fields hold NaN). */
+typedef struct rfi_pair_result {
+    double ffi, mad_reduction, std_reduction, flagged_fraction;   /* statistics.py:80-97, float64 like Python floats */
+    uint32_t tp, fp, fn;                                          /* pred & true, pred & ~true, ~pred & true */
+    int32_t status;
+} rfi_pair_result_t;
+
+int rfi_pair_sweep(const void* data, int dtype, const uint8_t* flags, const uint8_t* truth,
+                   int64_t n_pairs, int64_t seg, rfi_stats_t* stats, rfi_pair_result_t* results,
+                   void* stream);
 
 /* Host helper (no CUDA): np.random.permutation(n) of NumPy's legacy MT19937 generator --
  * replaces the shuffle of preprocessor.py:758-763 at ~3 ns per element instead of ~30.

@@ -21,6 +21,7 @@ from .evaluation import (  # noqa: F401,E402
     compute_recall,
     compute_statistics,
     compute_statistics_batch,
+    evaluate_pairs,
     evaluate_segmentation,
     evaluate_segmentation_async,
     evaluate_segmentation_batch,

@@ -19,7 +19,7 @@ RFI_STRETCH_NONE, RFI_STRETCH_SQRT, RFI_STRETCH_LOG10 = 0, 1, 2
 RFI_FLAGS_CUSTOM, RFI_FLAGS_MAD, RFI_FLAGS_INFERENCE = 0, 1, 2
 RFI_E_INVALID, RFI_E_UNSUPPORTED, RFI_E_CUDA = -1, -2, -3
 RFI_PATH_FAST, RFI_PATH_BIG, RFI_PATH_GENERIC = 0, 1, 2
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class RfiPlan(C.Structure):
@@ -48,6 +48,14 @@ class RfiStats(C.Structure):
     ]
 
 
+class RfiPairResult(C.Structure):
+    _fields_ = [
+        ("ffi", C.c_double), ("mad_reduction", C.c_double), ("std_reduction", C.c_double),
+        ("flagged_fraction", C.c_double), ("tp", C.c_uint32), ("fp", C.c_uint32), ("fn", C.c_uint32),
+        ("status", C.c_int32),
+    ]
+
+
 class RfiSynth(C.Structure):
     _fields_ = [
         ("channels", C.c_int64), ("times", C.c_int64), ("n_pol", C.c_int32), ("enable_bandpass", C.c_int32),
@@ -68,6 +76,8 @@ SYMBOLS = {
     "rfi_plan_workspace_bytes": (C.c_size_t, [C.POINTER(RfiPlan)]),
     "rfi_tile_stats": (_I, [C.POINTER(RfiPlan), _VP, _VP, _VP, _VP, _VP]),
     "rfi_write_patches": (_I, [C.POINTER(RfiPlan), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "rfi_plan_fusable": (_I, [C.POINTER(RfiPlan)]),
+    "rfi_fused_patches": (_I, [C.POINTER(RfiPlan), _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "rfi_confusion_counts": (_I, [_VP, _I, _I, _VP, _I, _I, _I64, _VP, _VP]),
     "rfi_confusion_counts_allreduce": (_I, [_VP, _I, _I, _VP, _I, _I, _I64, _VP, _I, _I, C.c_uint64, _VP, _VP]),
     "rfi_peer_alloc": (_I, [C.POINTER(C.c_void_p), _VP]),
@@ -78,6 +88,7 @@ SYMBOLS = {
     "rfi_statistics_workspace_bytes": (C.c_size_t, []),
     "rfi_statistics": (_I, [_VP, _I, _VP, _I64, _VP, _VP, _VP]),
     "rfi_statistics_segmented": (_I, [_VP, _I, _VP, _I64, _I64, _VP, _VP]),
+    "rfi_pair_sweep": (_I, [_VP, _I, _VP, _VP, _I64, _I64, _VP, _VP, _VP]),
     "rfi_legacy_permutation": (_I, [_VP, C.POINTER(C.c_int32), _I64, _VP]),
     "rfi_plan_slots": (_I, [C.POINTER(RfiPlan), _VP, _I64, _I, _VP, C.POINTER(C.c_int32), _I64, _VP, _VP,
                             C.POINTER(C.c_int64)]),

@@ -6,6 +6,8 @@
 // The five ratios are formed on the host in float64 exactly as the reference does.
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "rfi_common.cuh"
 
 namespace rfi {
@@ -263,7 +265,10 @@ static int launch_confusion(const void* pred, const void* truth, long long n, lo
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (n_seg < 0) {
         long long want = (n / (16 / (EP < ET ? EP : ET)) + kMetricThreads * 8 - 1) / (kMetricThreads * 8);
-        long long cap = (long long)sms * 8;  // 8 resident CTAs of 256 threads per SM
+        // CTAs per SM: 8 x 256 threads fill an SM's thread slots; RFI_CONFUSION_CTAS_PER_SM (experiment knob)
+        // leaves room for another kernel's CTAs when the counts run on a side stream
+        static const int per_sm = getenv("RFI_CONFUSION_CTAS_PER_SM") ? atoi(getenv("RFI_CONFUSION_CTAS_PER_SM")) : 8;
+        long long cap = (long long)sms * (per_sm > 0 ? per_sm : 8);
         unsigned grid = (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
         confusion_kernel<EP, FP, ET, FT><<<grid, kMetricThreads, 0, st>>>(pred, truth, n, counts, pa);
     } else {

@@ -416,6 +416,10 @@ extern "C" int rfi_statistics_segmented(const void* data, int dtype, const uint8
                                         int64_t seg, rfi_stats_t* out, void* stream) {
     using namespace rfi;
     if (n_seg < 0 || seg <= 0 || (n_seg > 0 && (!data || !out))) { set_error("bad arguments to rfi_statistics_segmented"); return RFI_E_INVALID; }
+    // float32 arithmetic: the sampled-bracket kernel of rfi_pairs.cu (2 CTAs / SM, ~6x the rate of the
+    // register-resident radix selects below, which stay for float64 / complex128)
+    if ((dtype == RFI_F32 || dtype == RFI_C64) && seg <= (int64_t)kSegNT * kSegE)
+        return rfi_pair_sweep(data, dtype, flags, nullptr, n_seg, seg, out, nullptr, stream);
     if (seg > (int64_t)kSegNT * kSegE) {
         set_error("segment of %lld samples: the per-pair kernel holds at most %d (use rfi_statistics per segment)",
                   (long long)seg, kSegNT * kSegE);

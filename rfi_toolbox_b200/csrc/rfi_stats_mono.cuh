@@ -266,14 +266,26 @@ __device__ __noinline__ void tile_stats_general(const PlanDev& p, const void* __
 // barriers (measured: 1.405 -> 1.297 ms on the bench workload; 1.36 ms with all keys in the
 // scratch, 1.32 / 1.335 ms with 6 / 5 groups in shared memory).
 constexpr int kMonoGKB = 3, kMonoGS = 4;
-template <int DT, int NT, bool GK = false, int GKB = kMonoGKB, int GS = kMonoGS>
-__global__ void __launch_bounds__(NT, GK ? GKB : ((sizeof(typename In<DT>::T) == 4) ? 2 : 1))
-tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __restrict__ flags,
-                       rfi_tile_stat_t* __restrict__ stats,
-                       typename Scalar<typename In<DT>::T>::key_t* __restrict__ gkeys = nullptr) {
+
+// The body of phase 1 as a device function, shared by the stand-alone statistics kernel below and by
+// the single-launch kernel of rfi_tiles.cu (tile_fused_kernel, FUSED = true), which goes on to write
+// the tile's patches from the magnitudes this function leaves in shared memory.  FUSED changes two
+// things: (1) the key tile uses the WRITER's layout -- element (row, col) at row * 128 +
+// (col ^ (row & 31)), conflict-free by rows and by columns; aligned groups of four columns stay
+// aligned groups, so every access below is still one 128-bit access per thread, only the slot of the
+// group and the order inside it change; (2) the tile's statistics also go to `st_sh` (shared memory).
+// Returns true when the monotone algorithm finished (keys intact, raw thresholds valid), false when
+// the tile was handed to the general algorithm (shared memory clobbered, statistics in `stats[tile]`).
+template <int DT, int NT, bool GK, int GS, bool FUSED>
+RFI_DEVINL bool mono_tile_stats(const PlanDev& p, const void* __restrict__ data, const uint8_t* __restrict__ flags,
+                                rfi_tile_stat_t* __restrict__ stats,
+                                typename Scalar<typename In<DT>::T>::key_t* __restrict__ gkeys,
+                                unsigned char* smem_raw, MonoShared<typename Scalar<typename In<DT>::T>::key_t>& sh,
+                                rfi_tile_stat_t* st_sh) {
     using T = typename In<DT>::T;
     using K = typename Scalar<T>::key_t;
     static_assert(NT == kMonoNT, "one sample per thread");
+    static_assert(!(FUSED && GK), "the fused kernel keeps the whole tile in shared memory");
     constexpr int E = kP * kP / NT;  // 32 keys per thread
     constexpr int G = E / 4;
     constexpr int RS = NT / 32;
@@ -281,7 +293,6 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
     constexpr K kInfKey = sizeof(T) == 4 ? K(0x7f800000u) : (K(0x7ff00000u) << 32);
     constexpr K kSignBit = K(1) << (Scalar<T>::kBits - 1);
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     // keys: [E/4][NT][4]; with GK the first GS groups stay in shared memory, the rest live in the
     // thread-private global scratch
     K* skeys = reinterpret_cast<K*>(smem_raw);
@@ -291,9 +302,9 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
     const int tid_ = threadIdx.x;
     auto kp = [&](int g) -> K* {   // this thread's 4 keys of group g
         if (GK && g >= GS) return gk + ((size_t)g * NT + tid_) * 4;
+        if (FUSED) return skeys + ((size_t)g * NT + (tid_ ^ (((g * RS + (tid_ >> 5)) >> 2) & 7))) * 4;
         return skeys + ((size_t)g * NT + tid_) * 4;
     };
-    __shared__ MonoShared<K> sh;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long tile = blockIdx.x;
@@ -308,6 +319,7 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
     auto give_up = [&](int reason) {
         __syncthreads();  // shared memory is handed over
         tile_stats_general<DT, NT>(p, data, flags, stats, RFI_TILE_GENERAL | (reason << 8), GK ? gk : nullptr);
+        return false;
     };
 
     // ---- load: magnitude fused into the 128-bit loads, raw bit patterns to shared memory.
@@ -336,6 +348,12 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
             bmin = k4[i] < bmin ? k4[i] : bmin;
         }
         if (sizeof(K) == 4) {
+            if constexpr (FUSED) {
+                // writer layout: column c of row r sits at c ^ (r & 31); r & 3 == warp & 3 here
+                K t;
+                if (warp & 1) { t = k4[0]; k4[0] = k4[1]; k4[1] = t; t = k4[2]; k4[2] = k4[3]; k4[3] = t; }
+                if (warp & 2) { t = k4[0]; k4[0] = k4[2]; k4[2] = t; t = k4[1]; k4[1] = k4[3]; k4[3] = t; }
+            }
             const uint4 packed = make_uint4((uint32_t)k4[0], (uint32_t)k4[1], (uint32_t)k4[2], (uint32_t)k4[3]);
             *reinterpret_cast<uint4*>(kp(g)) = packed;
             // complex input: the scratch tile ends up holding ALL magnitudes, row-major (element
@@ -401,9 +419,9 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
         __syncthreads();
         nv -= sh.acc[0];
         tile_min = sh.kmin; tile_max = sh.kmax;
-        if (sh.acc[1] != 0) { give_up(1); return; }
+        if (sh.acc[1] != 0) return give_up(1);
     }
-    if (nv < 64) { give_up(1); return; }
+    if (nv < 64) return give_up(1);
 
     // ---- sort the 512-sample: warps 0..3 each sort 128 samples in registers (bitonic network, 4
     //      keys per lane, shuffles across lanes), then EVERY thread finds the global rank of one
@@ -449,7 +467,7 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
     }
     __syncthreads();
     const int sv = (int)sh.acc[2];  // valid samples (sorted first)
-    if (sv < 64) { give_up(2); return; }
+    if (sv < 64) return give_up(2);
     const int delta = (int)(kMonoSigma * 0.5f * sqrtf((float)sv)) + 2;  // kMonoSigma sigma of a sample rank
 
     const bool real_branch = !In<DT>::cplx || p.magnitude;
@@ -503,7 +521,7 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
             M = sh.cursor; B = sh.below;
             const bool low = B > k1, high = k2 >= B + M;   // the target rank lies below / above the bracket
             if (M > (uint32_t)kMonoCap || low || high) {
-                if (attempt == 1 || M > (uint32_t)kMonoCap || (low && lo == 0) || (high && hi >= kExcl - 1)) { give_up(3); return; }
+                if (attempt == 1 || M > (uint32_t)kMonoCap || (low && lo == 0) || (high && hi >= kExcl - 1)) return give_up(3);
                 if (low) {
                     const int j = ilo - 2 * delta;
                     hi = lo - 1;
@@ -558,7 +576,7 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
     {
         const T pmin = proc_mode<T>(raw_val<T>(tile_min), pmode, m, m2);
         const T pmax = proc_mode<T>(raw_val<T>(tile_max), pmode, m, m2);
-        if (is_inf(pmin) || is_inf(pmax) || is_nan(pmin) || is_nan(pmax)) { give_up(5); return; }
+        if (is_inf(pmin) || is_inf(pmax) || is_nan(pmin) || is_nan(pmax)) return give_up(5);
     }
 
     T c = T(0), d = T(0), thr_lo = T(0), thr_hi = T(0);
@@ -584,7 +602,7 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
         const int ju = (int)sh.acc[3];  // first sample on the upper arm (proc >= c)
         const int rho = (int)(((float)(2 * k1 + 1) * (float)sv) / (float)(2 * nv));
         const int r_in = rho - delta, r_out = rho + delta + 2;  // samples inside the inner / outer window
-        if (r_in < 1 || r_out > sv - 1) { give_up(6); return; }
+        if (r_in < 1 || r_out > sv - 1) return give_up(6);
         // window of r consecutive samples holding the r smallest deviations: smallest start i
         // with (i + r past the end) or (d[i] <= d[i + r] and i + r on the upper arm)
         for (int which = 0; which < 2; ++which) {
@@ -600,11 +618,11 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
         }
         __syncthreads();
         int il = sh.win[0], iu = sh.win[1], il2 = sh.win[2], iu2 = sh.win[3];
-        if (il < 0 || il2 < 0) { give_up(7); return; }
+        if (il < 0 || il2 < 0) return give_up(7);
         il2 = il2 < il ? il2 : il;
         iu2 = iu2 > iu ? iu2 : iu;
         // both windows must straddle the centre (V-shape argument)
-        if (!(il2 <= il && il < ju && ju <= iu && iu <= iu2 && il2 < ju)) { give_up(8); return; }
+        if (!(il2 <= il && il < ju && ju <= iu && iu <= iu2 && il2 < ju)) return give_up(8);
         // candidates reach one sample BEYOND the outer window on each side (or to the end of the
         // value range), so that everything outside is proven to deviate at least d_out
         const K L1 = samp[il], U1 = samp[iu];
@@ -648,7 +666,7 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
         uint32_t at = base + incl - mine;
         __syncthreads();
         const uint32_t M = sh.cursor, B = sh.below;
-        if (M > (uint32_t)kMonoCap || B > k1 || k2 >= B + M) { give_up(9); return; }
+        if (M > (uint32_t)kMonoCap || B > k1 || k2 >= B + M) return give_up(9);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             K k4[4];
@@ -676,7 +694,7 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
         K r1k, r2k;
         mono_resolve<K, NT>(cand, M, k1 - B, k2 - B, r1k, r2k, sh);
         // the answers must lie inside what the windows prove
-        if (r1k < d_in || r2k > d_out) { give_up(11); return; }
+        if (r1k < d_in || r2k > d_out) return give_up(11);
         d = median_of_pair<T>(from_key<T>(r1k), from_key<T>(r2k), nv);
         const T ds = d * (T)p.sigma;
         thr_hi = c + ds;
@@ -786,7 +804,19 @@ tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* 
         st.route = RFI_TILE_RAW_THRESHOLDS;  // monotone tile: raw thresholds valid (0 / +inf when labels are not MAD flags)
         st.raw_lo = (double)raw_lo; st.raw_hi = (double)raw_hi;
         stats[tile] = st;
+        if constexpr (FUSED) *st_sh = st;
     }
+    return true;
+}
+
+template <int DT, int NT, bool GK = false, int GKB = kMonoGKB, int GS = kMonoGS>
+__global__ void __launch_bounds__(NT, GK ? GKB : ((sizeof(typename In<DT>::T) == 4) ? 2 : 1))
+tile_stats_mono_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __restrict__ flags,
+                       rfi_tile_stat_t* __restrict__ stats,
+                       typename Scalar<typename In<DT>::T>::key_t* __restrict__ gkeys = nullptr) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ MonoShared<typename Scalar<typename In<DT>::T>::key_t> sh;
+    mono_tile_stats<DT, NT, GK, GS, false>(p, data, flags, stats, gkeys, smem_raw, sh, nullptr);
 }
 
 }  // namespace rfi

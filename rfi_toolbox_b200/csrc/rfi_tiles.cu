@@ -284,49 +284,62 @@ template <typename T> struct Phase2Smem {
     static constexpr int kFlagPitch = kP + 4;  // bytes; 33 words -> column reads hit 32 banks
 };
 
-template <int DT, int NT, bool kComplexBranch>
-__global__ void __launch_bounds__(NT, (sizeof(typename In<DT>::T) == 4 && !kComplexBranch) ? 2 : 1)
-write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __restrict__ flags,
-                     const rfi_tile_stat_t* __restrict__ stats, const long long* __restrict__ dest_slot,
-                     float* __restrict__ images, uint8_t* __restrict__ labels,
-                     const float* __restrict__ mag_scratch) {
+// Position of element (row, col) of the log-amplitude tile in shared memory.  Stand-alone writer:
+// pitch 129.  Single-launch kernel (SWZ): pitch 128 with the column XOR-ed by the row's low five
+// bits -- the layout phase 1 left its keys in, so the tile is transformed in place; rows and
+// columns are both conflict-free.
+template <bool SWZ>
+struct TileIdx {
+    static constexpr int kPitch = SWZ ? kP : kP + 1;
+    RFI_DEVINL static int at(int r, int c) { return SWZ ? (r * kP + (c ^ (r & 31))) : (r * kPitch + c); }
+};
+
+// One output row (128 px x 3 channels x float32 = 1536 contiguous bytes) leaves shared memory as ONE
+// bulk asynchronous copy (cp.async.bulk, the non-tensor TMA path; SASS UBLKCP) issued by one lane,
+// instead of 3 LDS.128 + 3 STG.128 per lane: the staging buffer is handed to the async proxy behind
+// a proxy fence, and reused once the copy has READ it (wait_group.read).
+RFI_DEVINL void bulk_store(void* dst_global, const void* src_shared, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\tcp.async.bulk.commit_group;"
+                 :: "l"(dst_global), "r"((uint32_t)__cvta_generic_to_shared(src_shared)), "r"(bytes) : "memory");
+}
+RFI_DEVINL void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+RFI_DEVINL void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Phase 2 for one original tile.  FUSED (single-launch kernel, float32 real branch): shared memory
+// holds [tile 64 KB | transposed labels (in the 18 KB of phase 1's candidate list + sample) | stage];
+// with `keys_in_smem` the tile region holds the exact magnitudes phase 1 left there (as bit
+// patterns) and pass A is an in-place transform; otherwise (tile went through the general
+// algorithm) pass A reads the cube like the stand-alone writer.
+template <int DT, int NT, bool kComplexBranch, bool FUSED>
+RFI_DEVINL void write_tile(const PlanDev& p, const void* __restrict__ data, const uint8_t* __restrict__ flags,
+                           const rfi_tile_stat_t& st, long long tile, long long slot0, long long slot1,
+                           long long slot2, long long slot3, float* __restrict__ images,
+                           uint8_t* __restrict__ labels, const float* __restrict__ mag_scratch,
+                           unsigned char* smem_raw, bool keys_in_smem) {
     using T = typename In<DT>::T;
+    using IX = TileIdx<FUSED>;
     constexpr int E = kP * kP / NT;
     constexpr int RS = NT / 32;      // rows per step (one warp per row)
     constexpr int STEPS = kP / RS;   // row steps
     constexpr int Q = kP / 32;       // columns per lane per row (4)
-    constexpr int LP = Phase2Smem<T>::kPitch;
+    constexpr int LP = IX::kPitch;
     constexpr int FP = Phase2Smem<T>::kFlagPitch;
     static_assert(E == STEPS * Q, "tile / thread mapping");
+    static_assert(!FUSED || (std::is_same<T, float>::value && !kComplexBranch && NT == kMonoNT), "fused: float32 real branch");
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     T* Ls = reinterpret_cast<T*>(smem_raw);                                    // [kP][LP]
     float* Ph = reinterpret_cast<float*>(Ls + (size_t)kP * LP);               // [kP][LP] (complex branch)
     // transposed label tile (rotations 2, 3); rotations 0, 1 store their label rows from pass A
     unsigned char* FbT = reinterpret_cast<unsigned char*>(Ph + (kComplexBranch ? (size_t)kP * LP : 0));
-    float* stage = reinterpret_cast<float*>(FbT + (size_t)kP * FP);           // [warps][3*kP]
-    __shared__ BlockScratch<NT> scr;
-    int parity = 0;
+    float* stage = reinterpret_cast<float*>(FbT + (FUSED ? (size_t)(kMonoCap + kMonoNT) * 4 : (size_t)kP * FP));  // [warps][3*kP]
 
-    const long long tile = blockIdx.x;
     const int per = p.nh * p.nw;
     const long long w = tile / per;
     const int ti = (int)((tile % per) / p.nw), tj = (int)(tile % p.nw);
     const int R = p.rotations;
-    const long long base = w * R * per;
-
-    // canonical patch index of each rotation of this tile
-    long long slot0 = dest_slot[base + (long long)ti * p.nw + tj], slot1 = -1, slot2 = -1, slot3 = -1;
-    if (R >= 2) slot1 = dest_slot[base + per + (long long)(p.nh - 1 - ti) * p.nw + tj];
-    if (R >= 4) {
-        slot2 = dest_slot[base + 2LL * per + (long long)tj * p.nh + ti];
-        slot3 = dest_slot[base + 3LL * per + (long long)(p.nw - 1 - tj) * p.nh + ti];
-    }
-    if (slot0 < 0 && slot1 < 0 && slot2 < 0 && slot3 < 0) return;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t origin = ((size_t)w * p.channels + (size_t)ti * kP) * p.times + (size_t)tj * kP;
-    const rfi_tile_stat_t st = stats[tile];
     const T med_before = (T)st.median_before, inf_fill = (T)st.inf_fill, med_after = (T)st.median_after;
     const T thr_lo = (T)st.thr_lo, thr_hi = (T)st.thr_hi;
     const bool real_branch = !kComplexBranch;
@@ -344,7 +357,7 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
     // Fast route (float32, tile measured by the monotone kernel): the label
     // is two compares of the exact magnitude with the raw-domain thresholds of phase 1 -- no
     // division, no square root -- and the log amplitude, which only feeds the tolerance-class
-    // image channels, comes from reciprocal-multiply, sqrt.approx and lg2.approx (|dL| < 2e-7).
+    // image channels, comes from the float32 chain of rfi_tiles.cuh (fast_log_amp).
     T llo = Scalar<T>::nan(), lhi = Scalar<T>::nan();
     const bool fast_route = std::is_same<T, float>::value && !kComplexBranch &&
                             (st.route & RFI_TILE_RAW_THRESHOLDS) != 0;
@@ -396,7 +409,7 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
                     if (p.flag_mode == RFI_FLAGS_MAD) f = ((x > thr_hi) || (x < thr_lo)) ? 1 : 0;
                     L = log10_img(fabs_(x) + T(1e-10));
                 }
-                Ls[row * LP + col] = L;
+                Ls[IX::at(row, col)] = L;
                 FbT[col * FP + row] = f;
                 // label rows of the untransposed rotations go out now: 32 lanes x 1 byte = one full sector
                 if (slot0 >= 0) labels[(size_t)slot0 * kP * kP + (size_t)row * kP + col] = f;
@@ -405,7 +418,7 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
                     // (phase + pi) / (2 pi), then ImageNet (rotation invariant); tolerance class like the
                     // other channels: reciprocal multiplies and one fma instead of two IEEE divisions
                     const float c2 = (float)((ph + T(3.141592653589793)) * T(1.0 / 6.283185307179586));
-                    Ph[row * LP + col] = __fmaf_rn(c2, 1.0f / std2, nb2);
+                    Ph[IX::at(row, col)] = __fmaf_rn(c2, 1.0f / std2, nb2);
                 } else {
                     llo = Scalar<T>::fmin_nan(llo, L);
                     lhi = Scalar<T>::fmax_nan(lhi, L);
@@ -415,8 +428,47 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
             for (int q = 0; q < Q; ++q) cur[q] = nxt[q];
         }
     };
+    // single-launch kernel: the tile region holds the exact magnitudes as bit patterns, in this very
+    // layout -- every thread turns its own four keys of each row into L values IN PLACE (no barrier,
+    // no second buffer) and emits the four label bytes of the row as one 32-bit word
+    [[maybe_unused]] auto pass_a_inplace = [&]() {
+        if constexpr (FUSED) {
+            const float raw_lo = (float)st.raw_lo, raw_hi = (float)st.raw_hi;
+            const FastChain chain = make_fast_chain(p, (float)med_before, (float)med_after);
+            uint32_t* keys = reinterpret_cast<uint32_t*>(smem_raw);
+            const int px = warp & 3;  // position j of a group holds column 4 * lane + (j ^ px)
+            const bool mad = p.flag_mode == RFI_FLAGS_MAD;
+#pragma unroll 2
+            for (int g = 0; g < STEPS; ++g) {
+                const int row = g * RS + warp;
+                uint32_t* slot = keys + ((size_t)g * NT + (threadIdx.x ^ ((row >> 2) & 7))) * 4;
+                const uint4 kq = *reinterpret_cast<const uint4*>(slot);
+                const uint32_t kk[4] = {kq.x, kq.y, kq.z, kq.w};
+                float Lq[4];
+                uint32_t fw = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float a = __uint_as_float(kk[j]);
+                    const uint32_t f = (mad && ((a > raw_hi) || (a < raw_lo))) ? 1u : 0u;
+                    const float L = fast_log_amp(a, chain);
+                    Lq[j] = L;
+                    const int i = j ^ px;
+                    fw |= f << (8 * i);
+                    FbT[(4 * lane + i) * FP + row] = (unsigned char)f;
+                    llo = fminf(llo, L);
+                    lhi = fmaxf(lhi, L);
+                }
+                *reinterpret_cast<float4*>(slot) = make_float4(Lq[0], Lq[1], Lq[2], Lq[3]);
+                if (slot0 >= 0) reinterpret_cast<uint32_t*>(labels + (size_t)slot0 * kP * kP + (size_t)row * kP)[lane] = fw;
+                if (slot1 >= 0) reinterpret_cast<uint32_t*>(labels + (size_t)slot1 * kP * kP + (size_t)(kP - 1 - row) * kP)[lane] = fw;
+            }
+        }
+    };
     bool done = false;
-    if constexpr (DT == RFI_C64 && !kComplexBranch) {
+    if constexpr (FUSED) {
+        if (keys_in_smem) { pass_a_inplace(); done = true; }
+    }
+    if constexpr (DT == RFI_C64 && !kComplexBranch && !FUSED) {
         if (fast_route && mag_scratch != nullptr) { pass_a(std::true_type{}, std::true_type{}); done = true; }
     }
     if (!done) {
@@ -435,19 +487,19 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
             const int j = lane + 32 * q;
-            const T c = Ls[i * LP + j];
-            const T bi = (i > 0) ? c - Ls[(i - 1) * LP + j] : T(0);
-            const T bj = (j > 0) ? c - Ls[i * LP + j - 1] : T(0);
+            const T c = Ls[IX::at(i, j)];
+            const T bi = (i > 0) ? c - Ls[IX::at(i - 1, j)] : T(0);
+            const T bj = (j > 0) ? c - Ls[IX::at(i, j - 1)] : T(0);
             const T bi2 = bi * bi, bj2 = bj * bj;
             const T ss0 = Scalar<T>::fma(bi, bi, bj2);
             s0lo = Scalar<T>::fmin_nan(s0lo, ss0); s0hi = Scalar<T>::fmax_nan(s0hi, ss0);
             if (R >= 2) {
-                const T fi = (i < kP - 1) ? c - Ls[(i + 1) * LP + j] : T(0);
+                const T fi = (i < kP - 1) ? c - Ls[IX::at(i + 1, j)] : T(0);
                 const T ss1 = Scalar<T>::fma(fi, fi, bj2);
                 s1lo = Scalar<T>::fmin_nan(s1lo, ss1); s1hi = Scalar<T>::fmax_nan(s1hi, ss1);
             }
             if (R >= 4) {
-                const T fj = (j < kP - 1) ? c - Ls[i * LP + j + 1] : T(0);
+                const T fj = (j < kP - 1) ? c - Ls[IX::at(i, j + 1)] : T(0);
                 const T ss3 = Scalar<T>::fma(fj, fj, bi2);
                 s3lo = Scalar<T>::fmin_nan(s3lo, ss3); s3hi = Scalar<T>::fmax_nan(s3hi, ss3);
             }
@@ -477,68 +529,141 @@ write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __
         if (sl < 0) return;  // uniform across the block
         float* out_img = images + (size_t)sl * kP * kP * 3;
         [[maybe_unused]] unsigned char* out_lab = labels + (size_t)sl * kP * kP;
-        // source index of output (orow, ocol) = base_at + orow * srow + ocol * scol;
-        // db = offset of the column-derivative neighbour (output column - 1)
-        constexpr int srow = (rot == 0) ? LP : (rot == 1) ? -LP : (rot == 2) ? 1 : -1;
-        constexpr int scol = (rot <= 1) ? 1 : LP;
-        constexpr int base_at = (rot == 0) ? 0 : (rot == 1) ? (kP - 1) * LP : (rot == 2) ? 0 : (kP - 1);
-        constexpr int db = -scol;
+        // source element of output (orow, ocol): rot 0 (orow, ocol); rot 1 (127 - orow, ocol);
+        // rot 2 (ocol, orow); rot 3 (ocol, 127 - orow).  dcol = 1: the column-derivative neighbour
+        // (output column - 1)
+        auto src_at = [&](int orow, int ocol, int dcol) {
+            const int oc = ocol - dcol;
+            if constexpr (rot == 0) return IX::at(orow, oc);
+            else if constexpr (rot == 1) return IX::at(kP - 1 - orow, oc);
+            else if constexpr (rot == 2) return IX::at(oc, orow);
+            else return IX::at(oc, kP - 1 - orow);
+        };
         const int row0 = warp * STEPS;
         // u = (v - lo) * inv, out = u / std - mean / std  ==  v * (inv / std) + (-lo * inv / std - mean / std)
         const T ga = gs.inv * (T)is0, gb = Scalar<T>::fma(-gs.lo * gs.inv, (T)is0, (T)nb0);
         [[maybe_unused]] const T la = ls.inv * (T)is1, lb = Scalar<T>::fma(-ls.lo * ls.inv, (T)is1, (T)nb1);
         T prev[Q];
 #pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            const int at = base_at + (row0 - 1) * srow + (lane + 32 * q) * scol;
-            prev[q] = (row0 > 0) ? Ls[at] : T(0);
-        }
+        for (int q = 0; q < Q; ++q) prev[q] = (row0 > 0) ? Ls[src_at(row0 - 1, lane + 32 * q, 0)] : T(0);
 #pragma unroll 1
         for (int s = 0; s < STEPS; ++s) {
             const int orow = row0 + s;  // output row i'
+            float o[Q][3];
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
                 const int ocol = lane + 32 * q;  // output column j'
-                const int at = base_at + orow * srow + ocol * scol;
+                const int at = src_at(orow, ocol, 0);
                 const T c = Ls[at];
                 const T td = (orow > 0) ? c - prev[q] : T(0);
-                const T fd = (ocol > 0) ? c - Ls[at + db] : T(0);
+                const T fd = (ocol > 0) ? c - Ls[src_at(orow, ocol, 1)] : T(0);
                 prev[q] = c;
                 const T g = sqrt_fast(Scalar<T>::fma(td, td, fd * fd));
                 // ((g - lo) * inv) * (1/std) - mean/std, folded; a flat (or all-NaN) channel is exactly 0
                 // before the ImageNet step, whatever its pixels hold (preprocessor.py:157-163)
-                const float o0 = gs.ok ? (float)Scalar<T>::fma(g, ga, gb) : nb0;
-                float o1, o2;
+                o[q][0] = gs.ok ? (float)Scalar<T>::fma(g, ga, gb) : nb0;
                 if constexpr (kComplexBranch) {
                     T u = (c - T(-3.0)) * T(1.0 / 7.0);
                     u = u < T(0) ? T(0) : (u > T(1) ? T(1) : u);  // np.clip keeps NaN
-                    o1 = __fmaf_rn((float)u, is1, nb1);
-                    o2 = Ph[at];
+                    o[q][1] = __fmaf_rn((float)u, is1, nb1);
+                    o[q][2] = Ph[at];
                 } else {
-                    o1 = ls.ok ? (float)Scalar<T>::fma(c, la, lb) : nb1;
-                    o2 = nb2;
+                    o[q][1] = ls.ok ? (float)Scalar<T>::fma(c, la, lb) : nb1;
+                    o[q][2] = nb2;
                 }
-                wstage[ocol * 3 + 0] = o0;
-                wstage[ocol * 3 + 1] = o1;
-                wstage[ocol * 3 + 2] = o2;
             }
+            // the previous row's bulk copy has read the staging buffer
+            if (lane == 0) bulk_wait_read();
             __syncwarp();
-            float4* dst = reinterpret_cast<float4*>(out_img + (size_t)orow * kP * 3);
-            const float4* src = reinterpret_cast<const float4*>(wstage);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) dst[lane + 32 * k] = src[lane + 32 * k];
+            for (int q = 0; q < Q; ++q) {
+                const int ocol = lane + 32 * q;
+                wstage[ocol * 3 + 0] = o[q][0];
+                wstage[ocol * 3 + 1] = o[q][1];
+                wstage[ocol * 3 + 2] = o[q][2];
+            }
+            fence_async_shared();
+            __syncwarp();
+            if (lane == 0) bulk_store(out_img + (size_t)orow * kP * 3, wstage, 3 * kP * sizeof(float));
             if constexpr (rot >= 2) {  // label row = row of the transposed label tile (flipped for rot 3)
                 const unsigned char* lrow = FbT + ((rot == 2) ? orow : (kP - 1 - orow)) * FP;
                 reinterpret_cast<uint32_t*>(out_lab + (size_t)orow * kP)[lane] =
                     reinterpret_cast<const uint32_t*>(lrow)[lane];
             }
-            __syncwarp();
         }
     };
     emit(std::integral_constant<int, 0>{}, slot0, g0);
     emit(std::integral_constant<int, 1>{}, slot1, g1);
     emit(std::integral_constant<int, 2>{}, slot2, g0);
     emit(std::integral_constant<int, 3>{}, slot3, g3);
+    if (lane == 0) bulk_wait_read();  // shared memory must outlive the last copy's read
+}
+
+// canonical patch index of each rotation of tile (ti, tj) of waterfall w
+RFI_DEVINL void tile_slots(const PlanDev& p, const long long* __restrict__ dest_slot, long long tile,
+                           long long& slot0, long long& slot1, long long& slot2, long long& slot3) {
+    const int per = p.nh * p.nw;
+    const long long w = tile / per;
+    const int ti = (int)((tile % per) / p.nw), tj = (int)(tile % p.nw);
+    const int R = p.rotations;
+    const long long base = w * R * per;
+    slot0 = dest_slot[base + (long long)ti * p.nw + tj];
+    slot1 = slot2 = slot3 = -1;
+    if (R >= 2) slot1 = dest_slot[base + per + (long long)(p.nh - 1 - ti) * p.nw + tj];
+    if (R >= 4) {
+        slot2 = dest_slot[base + 2LL * per + (long long)tj * p.nh + ti];
+        slot3 = dest_slot[base + 3LL * per + (long long)(p.nw - 1 - tj) * p.nh + ti];
+    }
+}
+
+template <int DT, int NT, bool kComplexBranch>
+__global__ void __launch_bounds__(NT, (sizeof(typename In<DT>::T) == 4 && !kComplexBranch) ? 2 : 1)
+write_patches_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __restrict__ flags,
+                     const rfi_tile_stat_t* __restrict__ stats, const long long* __restrict__ dest_slot,
+                     float* __restrict__ images, uint8_t* __restrict__ labels,
+                     const float* __restrict__ mag_scratch) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const long long tile = blockIdx.x;
+    long long slot0, slot1, slot2, slot3;
+    tile_slots(p, dest_slot, tile, slot0, slot1, slot2, slot3);
+    if (slot0 < 0 && slot1 < 0 && slot2 < 0 && slot3 < 0) return;
+    const rfi_tile_stat_t st = stats[tile];
+    write_tile<DT, NT, kComplexBranch, false>(p, data, flags, st, tile, slot0, slot1, slot2, slot3, images, labels,
+                                              mag_scratch, smem_raw, false);
+}
+
+// ------------------------------------------------------------------------------------------
+// phase 1 + phase 2 in ONE launch (float32 arithmetic, real branch), for a caller that knows every
+// patch's destination slot before the statistics exist: inference_mode (no compaction, no shuffle)
+// or MAD flags with the slots of the all-kept case drawn ahead (the Python layer checks the flag
+// counts afterwards and falls back to the two-phase path if a tile turned out blank).  One CTA per
+// original tile, 2 CTAs / SM: while one CTA sits in the barrier-bound selection, the other streams
+// its 4 x 196 KB of patches out -- the issue-bound and the HBM-bound halves of the path overlap
+// inside every SM, the cube is read once (8 B / px) and nothing but the output is written: 60 B / px.
+constexpr size_t kFusedTileBytes = (size_t)kP * kP * 4;
+constexpr size_t kFusedAuxBytes = (size_t)(kMonoCap + kMonoNT) * 4;      // candidates + sample | transposed labels
+constexpr size_t kFusedStageBytes = (size_t)(kMonoNT / 32) * 3 * kP * 4;  // staging rows | phase 1's MonoShared
+constexpr size_t kFusedSmem = kFusedTileBytes + kFusedAuxBytes + kFusedStageBytes;
+static_assert(sizeof(MonoShared<uint32_t>) <= kFusedStageBytes, "MonoShared aliases the staging rows");
+static_assert((size_t)kP * Phase2Smem<float>::kFlagPitch <= kFusedAuxBytes, "transposed labels alias phase 1's lists");
+
+template <int DT>
+__global__ void __launch_bounds__(kMonoNT, 2)
+tile_fused_kernel(PlanDev p, const void* __restrict__ data, const uint8_t* __restrict__ flags,
+                  rfi_tile_stat_t* __restrict__ stats, const long long* __restrict__ dest_slot,
+                  float* __restrict__ images, uint8_t* __restrict__ labels) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ rfi_tile_stat_t st_sh;
+    MonoShared<uint32_t>& sh = *reinterpret_cast<MonoShared<uint32_t>*>(smem_raw + kFusedTileBytes + kFusedAuxBytes);
+    const long long tile = blockIdx.x;
+    const bool mono = mono_tile_stats<DT, kMonoNT, false, kMonoGS, true>(p, data, flags, stats, nullptr, smem_raw, sh, &st_sh);
+    __syncthreads();  // statistics visible (shared copy, or stats[tile] written by this CTA's thread 0)
+    long long slot0, slot1, slot2, slot3;
+    tile_slots(p, dest_slot, tile, slot0, slot1, slot2, slot3);
+    if (slot0 < 0 && slot1 < 0 && slot2 < 0 && slot3 < 0) return;
+    const rfi_tile_stat_t st = mono ? st_sh : stats[tile];
+    write_tile<DT, kMonoNT, false, true>(p, data, flags, st, tile, slot0, slot1, slot2, slot3, images, labels,
+                                         nullptr, smem_raw, mono);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -669,6 +794,39 @@ extern "C" int rfi_tile_stats(const rfi_plan_t* plan, const void* data, const ui
             default:      rc = launch_stats<RFI_C128, 512>(d, tiles, data, flags, stats, workspace, st); break;
         }
         if (rc) return rc;
+    }
+    RFI_CUDA_TRY(cudaGetLastError());
+    return RFI_OK;
+}
+
+// ---- single launch (see tile_fused_kernel) ---------------------------------------------------
+static bool plan_is_fusable(const rfi_plan_t* plan) {
+    if (!plan || plan->patch <= 0 || !plan_is_fast(plan)) return false;
+    const bool f32_real = plan->dtype == RFI_F32 || (plan->dtype == RFI_C64 && plan->magnitude);
+    return f32_real && (plan->flag_mode == RFI_FLAGS_MAD || plan->flag_mode == RFI_FLAGS_INFERENCE);
+}
+extern "C" int rfi_plan_fusable(const rfi_plan_t* plan) { return plan_is_fusable(plan) ? 1 : 0; }
+
+extern "C" int rfi_fused_patches(const rfi_plan_t* plan, const void* data, const uint8_t* flags,
+                                 rfi_tile_stat_t* stats, const int64_t* dest_slot, float* images,
+                                 uint8_t* labels, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!plan_is_fusable(plan)) { set_error("plan cannot take the single-launch path (rfi_plan_fusable)"); return RFI_E_UNSUPPORTED; }
+    PlanDev d;
+    int rc = make_plan(plan, d);
+    if (rc) return rc;
+    const long long tiles = rfi_plan_num_tiles(plan);
+    if (tiles == 0) return RFI_OK;
+    if (!data || !stats || !dest_slot) { set_error("data / stats / dest_slot is NULL"); return RFI_E_INVALID; }
+    const long long* dest = reinterpret_cast<const long long*>(dest_slot);
+    if (plan->dtype == RFI_F32) {
+        auto k = tile_fused_kernel<RFI_F32>;
+        RFI_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem));
+        k<<<(unsigned)tiles, kMonoNT, kFusedSmem, st>>>(d, data, flags, stats, dest, images, labels);
+    } else {
+        auto k = tile_fused_kernel<RFI_C64>;
+        RFI_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem));
+        k<<<(unsigned)tiles, kMonoNT, kFusedSmem, st>>>(d, data, flags, stats, dest, images, labels);
     }
     RFI_CUDA_TRY(cudaGetLastError());
     return RFI_OK;

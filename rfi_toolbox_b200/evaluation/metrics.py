@@ -118,10 +118,36 @@ class PendingMetrics:
         return _ratios(*self._counts.result())
 
 
-def confusion_counts_async(pred, true, group=None):
+_METRIC_STREAMS = {}
+
+
+def _metrics_stream(device):
+    s = _METRIC_STREAMS.get(device.index)
+    if s is None:
+        s = _METRIC_STREAMS[device.index] = torch.cuda.Stream(device=device)
+    return s
+
+
+def confusion_counts_async(pred, true, group=None, side_stream=False):
     """`confusion_counts` without the host synchronisation: -> `PendingCounts`.  With `group`, the
     sum over the ranks happens inside the counting kernel (NVLink peer memory); `RFI_NO_PEER=1`,
-    several hosts or missing CUDA IPC fall back to an NCCL all-reduce enqueued behind the kernel."""
+    several hosts or missing CUDA IPC fall back to an NCCL all-reduce enqueued behind the kernel.
+
+    `side_stream=True`: the counting kernel (HBM-bound, a few registers, no shared memory) and its
+    24-byte download run on a per-device side stream that waits for the work queued so far, so that
+    whatever the caller enqueues next on the current stream -- in a streaming loop the issue-bound
+    statistics kernel of the next `create_dataset_async` -- shares the SMs with it."""
+    if side_stream:
+        device = _pick_device(pred, true)
+        require_cuda(device)
+        cur, side = torch.cuda.current_stream(device), _metrics_stream(device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            out = confusion_counts_async(pred, true, group=group)
+        for x in (pred, true):
+            if isinstance(x, torch.Tensor) and x.is_cuda:
+                x.record_stream(side)
+        return out
     if group is not None:
         import os
 
@@ -173,11 +199,11 @@ def evaluate_segmentation(pred, true, group=None):
     return _ratios(*confusion_counts(pred, true, group=group))
 
 
-def evaluate_segmentation_async(pred, true, group=None):
+def evaluate_segmentation_async(pred, true, group=None, side_stream=False):
     """`evaluate_segmentation` for streaming callers: the counting kernel and the download of its
     three totals are enqueued, the ratios are formed in `result()`.  Reading the metrics of step k
     after step k + 1 has been enqueued keeps the GPU queue from draining between steps."""
-    return PendingMetrics(confusion_counts_async(pred, true, group=group))
+    return PendingMetrics(confusion_counts_async(pred, true, group=group, side_stream=side_stream))
 
 
 def compute_iou(pred, true):
@@ -211,7 +237,11 @@ def evaluate_segmentation_batch(pred, true):
     numel = pred.numel() if isinstance(pred, torch.Tensor) else np.asarray(pred).size
     seg = numel // n
     c = _counts_tensor(pred, true, n_seg=n, seg=seg).cpu().numpy()
-    tp, fp, fn = c[:, 0].astype(np.int64), c[:, 1].astype(np.int64), c[:, 2].astype(np.int64)
+    return _ratio_arrays(c[:, 0].astype(np.int64), c[:, 1].astype(np.int64), c[:, 2].astype(np.int64))
+
+
+def _ratio_arrays(tp, fp, fn):
+    """`_ratios` over int64 arrays of counts (same branches, same float64 operations)."""
     with np.errstate(divide="ignore", invalid="ignore"):
         union = tp + fp + fn
         iou = np.where(union == 0, 1.0, tp / union)

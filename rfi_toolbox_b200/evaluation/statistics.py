@@ -236,3 +236,70 @@ def compute_ffi_batch(data, flags, errors="raise"):
            "std_reduction": np.where(guard, 0.0, np.where(bad, np.nan, std_red)),
            "flagged_fraction": np.where(guard, 1.0, penalty)}
     return res
+
+
+_PAIR_DTYPE = np.dtype([("ffi", "f8"), ("mad_reduction", "f8"), ("std_reduction", "f8"), ("flagged_fraction", "f8"),
+                        ("tp", "u4"), ("fp", "u4"), ("fn", "u4"), ("status", "i4")])
+_PINNED_RESULTS = {}
+
+
+def _mask_u8(mask, device, what):
+    """bool / uint8 masks as they are; anything else through `!= 0` (astype(bool), metrics.py:36)."""
+    t = as_device_tensor(mask, device)
+    if t.dtype == torch.bool:
+        return t.contiguous().view(torch.uint8)
+    if t.dtype == torch.uint8:
+        return t.contiguous()
+    return (t != 0).contiguous().view(torch.uint8)
+
+
+def evaluate_pairs(data, pred, true, errors="raise"):
+    """BASELINE config 4 as ONE launch: for every pair i of a stack (N, ...) the results of
+    `compute_ffi(data[i], pred[i])` (statistics.py:59-97) and of `evaluate_segmentation(pred[i], true[i])`
+    (metrics.py:155-172), with data, pred and true each read once (`rfi_pair_sweep`).
+
+    data: float32 / complex64 (N, ...), at most 16384 samples per pair (other dtypes / sizes: use
+    `compute_ffi_batch` + `evaluate_segmentation_batch`).  `pred` must be boolean, as the reference's
+    `data[~flags]` demands.  Returns float64 arrays 'ffi', 'mad_reduction', 'std_reduction',
+    'flagged_fraction', 'iou', 'precision', 'recall', 'f1', 'dice' and int64 'tp', 'fp', 'fn'.
+    Constant data makes the reference raise ZeroDivisionError; so does this function, naming the first
+    such pair, unless `errors="nan"`."""
+    from .metrics import _ratio_arrays
+    lib = _native.load()
+    device = _device_of(data, pred, true)
+    require_cuda(device)
+    d = as_device_tensor(data, device)
+    if d.dtype not in (torch.float32, torch.complex64):
+        raise TypeError(f"evaluate_pairs: float32 / complex64 data (got {d.dtype})")
+    if d.ndim < 2:
+        raise ValueError("evaluate_pairs needs a leading pair axis: data.shape = (N, ...)")
+    n = d.shape[0]
+    seg = d.numel() // n if n else 0
+    f = _flags_tensor(pred, device)
+    t = _mask_u8(true, device, "true")
+    if tuple(f.shape) != tuple(d.shape) or t.numel() != d.numel():
+        raise IndexError("data, pred and true must have the same shape")
+    if n == 0 or seg == 0:
+        z = np.zeros(0)
+        return {k: z for k in ("ffi", "mad_reduction", "std_reduction", "flagged_fraction", "iou", "precision",
+                               "recall", "f1", "dice", "tp", "fp", "fn")}
+    with torch.cuda.device(device):
+        res = torch.empty((n, _PAIR_DTYPE.itemsize), dtype=torch.uint8, device=device)
+        rc = lib.rfi_pair_sweep(d.contiguous().data_ptr(), _DTYPE_CODE[d.dtype], f.contiguous().data_ptr(), t.data_ptr(),
+                                n, seg, None, res.data_ptr(), current_stream_ptr(device))
+        _native.check(rc, "rfi_pair_sweep")
+        # results come down through a pinned buffer kept per device (48 B per pair)
+        key = device.index
+        host = _PINNED_RESULTS.get(key)
+        if host is None or host.shape[0] < n:
+            host = _PINNED_RESULTS[key] = torch.empty((n, _PAIR_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True)
+        host[:n].copy_(res, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+        r = host[:n].numpy().view(_PAIR_DTYPE).reshape(n).copy()
+    zero = r["status"] == 2
+    if zero.any() and errors == "raise":
+        raise ZeroDivisionError(f"float division by zero (pair {int(np.flatnonzero(zero)[0])}: constant data)")
+    out = {k: r[k].astype(np.float64) for k in ("ffi", "mad_reduction", "std_reduction", "flagged_fraction")}
+    tp, fp, fn = (r[k].astype(np.int64) for k in ("tp", "fp", "fn"))
+    out.update(_ratio_arrays(tp, fp, fn))
+    return out

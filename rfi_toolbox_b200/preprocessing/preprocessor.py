@@ -27,7 +27,7 @@ import torch
 
 from .. import _native
 from ..datasets.batched_dataset import TorchDataset
-from ..utils.device import as_device_tensor, as_host_tensor, copy_stream, current_stream_ptr, phase1_stream, require_cuda
+from ..utils.device import as_device_tensor, as_host_tensor, copy_stream, current_stream_ptr, require_cuda
 
 logger = logging.getLogger(__name__)
 
@@ -105,6 +105,13 @@ class _HostBuffers:
 _HOST_POOL = {}
 _HOST_POOL_LOCK = threading.Lock()
 
+# ---- single-launch path: bookkeeping of the speculative shuffle draws (see `Preprocessor.speculate`)
+_SPEC_LOCK = threading.Lock()
+_SPEC_INFLIGHT = []      # contexts of speculative calls whose result() has not run yet, in submission order
+_SPEC_COOLDOWN = {}      # call signature -> submissions left before speculation is tried again
+_SPEC_BACKOFF = {}       # call signature -> length of its last cool-down (doubles per failure)
+_ZERO_COUNT = np.zeros(1, dtype=np.int32)
+
 
 def _acquire_host_buffers(device, n_groups, n_patches):
     """Pinned memory is expensive to allocate (more than the whole host phase), so the staging
@@ -157,6 +164,18 @@ class PendingDataset:
             self._ctx = None
         return self._dataset
 
+    def __del__(self):
+        # a handle dropped without result(): its staging buffers go back to the pool and it no longer
+        # counts as a speculative call in flight (its shuffle draw stays consumed, like a discarded dataset's)
+        ctx = getattr(self, "_ctx", None)
+        if ctx is not None:
+            try:
+                with _SPEC_LOCK:
+                    _SPEC_INFLIGHT[:] = [c for c in _SPEC_INFLIGHT if c is not ctx]
+                _release_host_buffers(ctx["hb"])
+            except Exception:
+                pass
+
 
 class Preprocessor:
     """Preprocess waterfall data into training patches (preprocessor.py:139-196)."""
@@ -164,15 +183,26 @@ class Preprocessor:
     #: host (pinned) input is uploaded in this many baseline chunks, overlapped with phase 1
     upload_chunks = 8
 
-    #: "side": `create_dataset_async` enqueues phase 1 (and the download of the flag counts) on a
-    #: per-device side stream, so that the statistics kernel of call k + 1 can share the SMs with the
-    #: writer of call k (one is issue-bound, the other HBM-bound).  The side stream waits for the
-    #: work already queued on the current stream unless the call is told `input_ready=True`.
-    phase1_stream = None
-
     #: when True, CUDA events bracket the two kernels of every call (read by bench.py):
-    #: `self.events = {"stats": (start, stop), "write": (start, stop)}` on the current stream.
+    #: `self.events = {"stats": (start, stop), "write": (start, stop)}` on the current stream
+    #: (`{"fused": (start, stop)}` when the call took the single-launch path).
     profile = False
+
+    #: Single-launch path (`rfi_fused_patches`: statistics and patches of a tile in ONE kernel, no host
+    #: round trip between the phases), OFF by default: measured on B200 it moves fewer bytes (60 instead of
+    #: 68 B / px) but takes 3.85 ms where the two launches take 2.87 ms on the bench cube -- a CTA that holds
+    #: both halves runs them one after the other, and statistics and writer CTAs side by side on one SM
+    #: evict each other's instructions.  It remains for callers that cannot synchronise with
+    #: the host between the phases (stream capture, `inference_mode` services).
+    #: The kernel needs every patch's destination slot before the statistics exist.  `inference_mode` has
+    #: them by definition.  With MAD flags the call SPECULATES that no patch is blank: it draws
+    #: `np.random.permutation(N0)` at submission, launches, and checks the flag counts in `result()`.  If a
+    #: tile did turn out blank (while others were not), the global generator is put back to where it stood
+    #: before the draw and the call completes through the two-phase path with the statistics the launch
+    #: left -- results and RNG consumption are the reference's either way.  Calls submitted after a
+    #: mis-speculated one and before its `result()` are re-drawn in order; a call signature that
+    #: mis-speculated is not tried again for a while.
+    speculate = False
 
     def __init__(self, data, flags=None, *, magnitude=False, device=None, pin=False):
         ndim = data.ndim
@@ -189,6 +219,7 @@ class Preprocessor:
         self._device = device
         self._pin = pin
         self.last_tile_stats = None
+        self.last_launch = None   # "single" / "two-phase" / ... : which launches the last fast-path call made
 
     # ------------------------------------------------------------------------------ helpers
     @staticmethod
@@ -247,10 +278,9 @@ class Preprocessor:
         """Same arguments as `create_dataset`; enqueues phase 1 and returns a `PendingDataset` whose
         `result()` is the dataset.  `create_dataset(...)` == `create_dataset_async(...).result()`.
         Streaming callers (one Preprocessor per sample / baseline chunk, the reference's own unit of
-        work, synthetic_generator.py:55-107) keep one or two calls in flight so that the host phase
-        of each hides behind the statistics kernel of the next (`iter_dataset_chunks(lookahead=)`).
-        `input_ready=True` (only read when `phase1_stream == "side"`): the caller guarantees that the
-        input tensors are complete, so phase 1 need not wait for work queued on the current stream."""
+        work, synthetic_generator.py:55-107) keep calls in flight so that the host phase of each hides
+        behind the statistics kernel of the next (`iter_dataset_chunks(lookahead=)`).
+        `input_ready` is accepted for compatibility and ignored."""
         lib = _native.load()
         device = self._resolve_device()
         if stretch and stretch not in ("SQRT", "LOG10"):
@@ -336,22 +366,72 @@ class Preprocessor:
                 images, labels, order, patch_size, stretch, flag_sigma, normalize_before_stretch,
                 normalize_after_stretch, augmentation_rotations))
 
-        side1 = None
-        if self.phase1_stream == "side" and host is None:
-            side1 = phase1_stream(device)
-            if not input_ready:
-                side1.wait_stream(torch.cuda.current_stream(device))
-        with torch.cuda.device(device), torch.cuda.stream(side1 if side1 is not None else torch.cuda.current_stream(device)):
+        # ---- single launch?  (inference_mode, or MAD flags with the all-kept shuffle drawn ahead)
+        sig = (P, stretch, float(flag_sigma), bool(normalize_before_stretch), bool(normalize_after_stretch), R)
+        fused = bool(self.speculate) and n_tiles > 0 and bool(lib.rfi_plan_fusable(C.byref(plan)))
+        if fused and not inference_mode:
+            with _SPEC_LOCK:
+                left = _SPEC_COOLDOWN.get(sig, 0)
+                if left > 0:
+                    _SPEC_COOLDOWN[sig] = left - 1
+                    fused = False
+                elif any(c.get("stale") for c in _SPEC_INFLIGHT):
+                    fused = False  # a re-draw is pending: later calls must draw after it, i.e. in result()
+
+        with torch.cuda.device(device):
+            stats = torch.empty((max(n_tiles, 1), _native.TILE_STAT_BYTES), dtype=torch.uint8, device=device)
+            hb = _acquire_host_buffers(device, max(n_tiles, 1), max(n0, 1))
+            fast = lib.rfi_plan_path(C.byref(plan)) == _native.RFI_PATH_FAST
+        ctx = dict(pre=self, lib=lib, device=device, plan=plan, host=host, data=data, flags=flags, stats=stats, work=None, hb=hb,
+                   ev=[torch.cuda.Event(enable_timing=True) for _ in range(4)] if self.profile else None,
+                   n_tiles=n_tiles, n0=n0, P=P, C_=C_, T_=T_, B=B, npol=npol, R=R, ws_bytes=ws_bytes, fast=fast,
+                   skip_patchify=skip_patchify, inference_mode=inference_mode, num_patches=num_patches,
+                   keep_work=not (fast and not (is_complex and self.magnitude)), fused=fused, sig=sig,
+                   spec=None, stale=False,
+                   meta=(patch_size, stretch, flag_sigma, normalize_before_stretch, normalize_after_stretch,
+                         augmentation_rotations))
+        self._launch_phase1(ctx)
+        return PendingDataset(self, ctx=ctx)
+
+    def _launch_phase1(self, ctx):
+        """Enqueue phase 1 of `ctx` (the single launch when `ctx["fused"]`), then the download of its flag counts."""
+        lib, device, plan, hb, ev = ctx["lib"], ctx["device"], ctx["plan"], ctx["hb"], ctx["ev"]
+        host, data, flags, stats = ctx["host"], ctx["data"], ctx["flags"], ctx["stats"]
+        n_tiles, n0, P, R, B, npol = ctx["n_tiles"], ctx["n0"], ctx["P"], ctx["R"], ctx["B"], ctx["npol"]
+        C_, T_, ws_bytes, fast, fused = ctx["C_"], ctx["T_"], ctx["ws_bytes"], ctx["fast"], ctx["fused"]
+        inference_mode, num_patches = ctx["inference_mode"], ctx["num_patches"]
+        with torch.cuda.device(device):
             stream = current_stream_ptr(device)
             fptr = flags.data_ptr() if flags is not None else None
-            # ---- phase 1: statistics + flag counts per original tile
-            stats = torch.empty((max(n_tiles, 1), _native.TILE_STAT_BYTES), dtype=torch.uint8, device=device)
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if self.profile else None
+            if fused:
+                # destination slots of the all-kept case (every group "unflagged" = nothing dropped,
+                # preprocessor.py:752-756), the call's ONE draw from the global legacy generator
+                rng_before = None if inference_mode else np.random.get_state()
+                n_out = _native.plan_slots(plan, None if inference_mode else np.broadcast_to(_ZERO_COUNT, (n_tiles,)),
+                                           not inference_mode, num_patches, hb.order_np, hb.dest_np)
+                dest_dev = torch.empty(max(n0, 1), dtype=torch.int64, device=device)
+                dest_dev.copy_(hb.dest[:max(n0, 1)], non_blocking=True)
+                hb.copied.record()
+                images = torch.empty((n_out, P, P, 3), dtype=torch.float32, device=device)
+                labels = torch.empty((n_out, P, P), dtype=torch.uint8, device=device)
+                ctx["spec"] = dict(rng_before=rng_before, n_out=n_out, images=images, labels=labels,
+                                   order=hb.order_np[:n_out].copy(), sig=ctx["sig"])
+                ws_bytes = 0
             if ev:
                 ev[0].record()
+            # ---- phase 1: statistics + flag counts per original tile (single launch: and the patches)
             work = torch.empty(ws_bytes, dtype=torch.uint8, device=device) if ws_bytes else None
             wptr = work.data_ptr() if work is not None else None
-            fast = lib.rfi_plan_path(C.byref(plan)) == _native.RFI_PATH_FAST
+
+            def launch(pl, dptr, fp, sptr, wp, slot_off):
+                if fused:
+                    rc = lib.rfi_fused_patches(C.byref(pl), dptr, fp, sptr, dest_dev.data_ptr() + 8 * slot_off,
+                                               images.data_ptr(), labels.data_ptr(), stream)
+                    _native.check(rc, "rfi_fused_patches")
+                else:
+                    rc = lib.rfi_tile_stats(C.byref(pl), dptr, fp, sptr, wp, stream)
+                    _native.check(rc, "rfi_tile_stats")
+
             pipelined = host is not None and host.is_pinned() and fast and B > 1 and n_tiles > 0
             if host is not None and not pipelined:
                 data = host.to(device, non_blocking=True)
@@ -360,7 +440,7 @@ class Preprocessor:
                 data = torch.empty(host.shape, dtype=host.dtype, device=device)
                 main, side = torch.cuda.current_stream(device), copy_stream(device)
                 side.wait_stream(main)  # the fresh buffer may still be in use by work queued on `main`
-                bounds = np.linspace(0, B, min(B, self.upload_chunks) + 1).astype(np.int64)
+                bounds = np.linspace(0, B, min(B, ctx["pre"].upload_chunks) + 1).astype(np.int64)
                 per_bl_tiles = n_tiles // B
                 for b0, b1 in zip(bounds[:-1], bounds[1:]):
                     b0, b1 = int(b0), int(b1)
@@ -372,56 +452,70 @@ class Preprocessor:
                     sub = _native.RfiPlan.from_buffer_copy(plan)
                     sub.n_waterfalls = (b1 - b0) * npol
                     off = b0 * npol * C_ * T_
-                    rc = lib.rfi_tile_stats(C.byref(sub), data.data_ptr() + off * data.element_size(),
-                                            fptr + off if fptr is not None else None,
-                                            stats.data_ptr() + b0 * per_bl_tiles * _native.TILE_STAT_BYTES,
-                                            wptr + b0 * per_bl_tiles * (ws_bytes // n_tiles) if wptr else None,
-                                            stream)
-                    _native.check(rc, "rfi_tile_stats")
+                    launch(sub, data.data_ptr() + off * data.element_size(), fptr + off if fptr is not None else None,
+                           stats.data_ptr() + b0 * per_bl_tiles * _native.TILE_STAT_BYTES,
+                           wptr + b0 * per_bl_tiles * (ws_bytes // n_tiles) if wptr else None,
+                           b0 * per_bl_tiles * R)
                 data.record_stream(side)
             else:
-                rc = lib.rfi_tile_stats(C.byref(plan), data.data_ptr(), fptr, stats.data_ptr(), wptr, stream)
-                _native.check(rc, "rfi_tile_stats")
+                launch(plan, data.data_ptr(), fptr, stats.data_ptr(), wptr, 0)
             if ev:
                 ev[1].record()
-            self.last_tile_stats = stats
-            if fast and not (is_complex and self.magnitude):
-                # real input: the fast path's scratch serves phase 1 only -- hand its block back
-                # before the outputs are allocated (stream-ordered reuse).  Complex input through
-                # the real branch keeps it: phase 2 reads the exact magnitudes phase 1 left there.
-                work, wptr = None, None
-
+            ctx["pre"].last_tile_stats = stats
+            # real input: the fast path's scratch serves phase 1 only -- its block goes back before the
+            # outputs are allocated (stream-ordered reuse).  Complex input through the real branch keeps it:
+            # phase 2 reads the exact magnitudes phase 1 left there.
+            ctx["data"], ctx["work"] = data, (work if ctx["keep_work"] else None)
             # ---- flag counts down to pinned memory; the host phase (`_complete`) waits for them
-            hb = _acquire_host_buffers(device, max(n_tiles, 1), max(n0, 1))
             if not inference_mode:
                 hb.nflag[:n_tiles].copy_(stats[:n_tiles].view(torch.int32)[:, 16], non_blocking=True)
                 hb.event.record()
-            done1 = None
-            if side1 is not None:
-                done1 = torch.cuda.Event()
-                done1.record()
-        ctx = dict(side1=side1, done1=done1, lib=lib, device=device, plan=plan, data=data, flags=flags, stats=stats, work=work, hb=hb, ev=ev,
-                   n_tiles=n_tiles, n0=n0, P=P, C_=C_, T_=T_, skip_patchify=skip_patchify,
-                   inference_mode=inference_mode, num_patches=num_patches,
-                   meta=(patch_size, stretch, flag_sigma, normalize_before_stretch, normalize_after_stretch,
-                         augmentation_rotations))
-        return PendingDataset(self, ctx=ctx)
+        if ctx["spec"] is not None and not inference_mode:
+            with _SPEC_LOCK:
+                _SPEC_INFLIGHT.append(ctx)
 
     def _complete(self, ctx):
-        """Host phase + phase 2 of a call whose phase 1 is enqueued (see `PendingDataset`)."""
+        """Host phase + phase 2 of a call whose phase 1 is enqueued (see `PendingDataset`); for a call
+        on the single-launch path: the check of the speculation, and the two-phase completion if it failed."""
         lib, device, plan, hb, ev = ctx["lib"], ctx["device"], ctx["plan"], ctx["hb"], ctx["ev"]
-        data, flags, stats, work = ctx["data"], ctx["flags"], ctx["stats"], ctx["work"]
         n_tiles, n0, P, C_, T_ = ctx["n_tiles"], ctx["n0"], ctx["P"], ctx["C_"], ctx["T_"]
         skip_patchify, inference_mode, num_patches = ctx["skip_patchify"], ctx["inference_mode"], ctx["num_patches"]
+        data, flags, stats, work = ctx["data"], ctx["flags"], ctx["stats"], ctx["work"]
+        spec = ctx["spec"]
+        if spec is not None:
+            good = True
+            nflag = None
+            if not inference_mode:
+                hb.event.synchronize()
+                nflag = hb.nflag_np[:n_tiles]
+                any_flag = nflag > 0
+                n_any = int(np.count_nonzero(any_flag))
+                with _SPEC_LOCK:
+                    _SPEC_INFLIGHT[:] = [c for c in _SPEC_INFLIGHT if c is not ctx]
+                    if ctx["stale"]:
+                        good = False   # an earlier call was re-drawn: this call's draw comes now, in order
+                    elif n_any not in (0, n_tiles):
+                        good = False   # a blank tile among flagged ones: the drawn permutation is too long
+                        np.random.set_state(spec["rng_before"])
+                        for c in _SPEC_INFLIGHT:
+                            c["stale"] = True
+                        # not tried again for a while, longer after every failure
+                        _SPEC_COOLDOWN[spec["sig"]] = _SPEC_BACKOFF[spec["sig"]] = min(4096, 2 * _SPEC_BACKOFF.get(spec["sig"], 32))
+                        logger.info("single-launch path: %d of %d tiles blank, completing through two phases",
+                                    n_tiles - n_any, n_tiles)
+            self.last_launch = "single" if good else "single, then phase 2 again (speculation failed)"
+            if good:
+                if ev:
+                    self.events = {"fused": (ev[0], ev[1])}
+                if nflag is not None and n_any == 0:
+                    logger.warning("No flagged patches found - keeping all patches")
+                _release_host_buffers(hb)
+                return self._finish(spec["images"], spec["labels"], spec["order"], *ctx["meta"])
+            spec["images"] = spec["labels"] = None  # released before the right-sized outputs are allocated
+        else:
+            self.last_launch = "two-phase"
         with torch.cuda.device(device):
             stream = current_stream_ptr(device)
-            if ctx["side1"] is not None:
-                # phase 1 ran on the side stream: phase 2 (this stream) starts after it and keeps its buffers
-                cur = torch.cuda.current_stream(device)
-                cur.wait_event(ctx["done1"])
-                for t in (stats, work):
-                    if t is not None:
-                        t.record_stream(cur)
             fptr = flags.data_ptr() if flags is not None else None
             wptr = work.data_ptr() if work is not None else None
             # ---- host: blank-patch compaction + shuffle -> destination slot of every patch

@@ -74,18 +74,6 @@ def copy_stream(device: torch.device) -> torch.cuda.Stream:
     return s
 
 
-_PHASE1_STREAMS = {}
-
-
-def phase1_stream(device: torch.device) -> torch.cuda.Stream:
-    """One low-priority side stream per device for phase 1 of `create_dataset_async` calls in flight
-    (the writer of the previous call, on the caller's stream, gets the SMs first)."""
-    s = _PHASE1_STREAMS.get(device.index)
-    if s is None:
-        s = _PHASE1_STREAMS[device.index] = torch.cuda.Stream(device=device, priority=0)
-    return s
-
-
 def bind_host_to_device(device) -> list | None:
     """Pin the calling process to the CPU cores (hence, by first touch, the host memory node)
     closest to `device`, as NVML reports them.  With one process per GPU this keeps every rank's
