@@ -229,6 +229,36 @@ size_t rfi_statistics_workspace_bytes(void);
 int rfi_statistics(const void* data, int dtype, const uint8_t* flags, int64_t n,
                    rfi_stats_t* out, void* workspace, void* stream);
 
+/* Both sets of compute_ffi in one call -- replaces compute_statistics(data) AND compute_statistics(data,
+ * flags) (statistics.py:16-56, called back to back by compute_ffi, :73-74): out[0] = all samples, out[1] =
+ * the samples whose flag byte is zero (== out[0] when flags is NULL).  RFI_F32 / RFI_C64: three passes over
+ * the data (cube -> 4 B / px key scratch; median brackets; MAD brackets) instead of forty, exact order
+ * statistics from sampled brackets; a missed bracket (probability ~1e-5) is reported as out[0].count = -1
+ * and the caller repeats the call through rfi_statistics.  RFI_F64 / RFI_C128: rfi_statistics twice.
+ *   data       device, 16-byte aligned;  flags  device uint8[n] (4-byte aligned) or NULL
+ *   workspace  device, rfi_statistics2_workspace_bytes(dtype, n) bytes (~4.6 B per sample) */
+size_t rfi_statistics2_workspace_bytes(int dtype, int64_t n);
+int rfi_statistics2(const void* data, int dtype, const uint8_t* flags, int64_t n, rfi_stats_t* out,
+                    void* workspace, void* stream);
+
+/* The same two sets of statistics over a cube that is SHARDED over ranks by baseline ("f64 {n,
+ * sum x, sum x^2} plus radix histograms for a global FFI"): the caller (torch.distributed in the Python layer)
+ * sums what these two entry points leave between the calls.  RFI_F32 / RFI_C64 only.
+ *   rfi_statistics_shard_begin   pass A over the rank's shard (keys -> workspace scratch); state = device
+ *       double[8] {n, n_flagged, n_nan[0], n_nan[1], sum[0], sum[1], maxkey[0], maxkey[1]} (set 0 = all samples,
+ *       set 1 = unflagged; [0..5] are summed over the ranks, [6..7] maximised)
+ *   rfi_statistics_shard_count   one pass over the rank's key scratch.  mode 0: counts[s * 16 + t] = number of
+ *       keys of set s below prefix[s] | (t + 1) << shift, t = 0 .. 14 (MSB-first radix select, 4 bits per pass;
+ *       all-reduce SUM); mode 1: counts[s * 16] = keys <= prefix[s] (SUM), counts[s * 16 + 1] = smallest key
+ *       above it (MIN).  dev_mode 1: the key of a sample is |x - centre[s]| (the MAD).  sumsq (or NULL): device
+ *       double[2], sum of (x - mean[s])^2 over the rank's samples of each set.
+ *   centre / mean / prefix are HOST arrays of 2; counts device uint64[32]; workspace as for rfi_statistics2. */
+int rfi_statistics_shard_begin(const void* data, int dtype, const uint8_t* flags, int64_t n,
+                               void* workspace, double* state, void* stream);
+int rfi_statistics_shard_count(const uint8_t* flags, int64_t n, void* workspace, int mode, int dev_mode,
+                               const float* centre, const float* mean, const uint32_t* prefix, int shift,
+                               unsigned long long* counts, double* sumsq, void* stream);
+
 /* Per-pair sweep (BASELINE config 4): the same statistics for every consecutive segment of `seg`
  * samples (seg <= 16384, e.g. one 128 x 128 patch) in one launch, one CTA per segment.
  *   out  device rfi_stats_t[n_seg][2]: [i][0] over all samples of segment i (statistics.py:73),
@@ -250,6 +280,7 @@ int rfi_statistics_segmented(const void* data, int dtype, const uint8_t* flags, 
  * before flagging: the reference raises ZeroDivisionError; the fields hold NaN). */
 typedef struct rfi_pair_result {
     double ffi, mad_reduction, std_reduction, flagged_fraction;   /* statistics.py:80-97, float64 like Python floats */
+    double iou, precision, recall, f1, dice;                      /* metrics.py:25-152 from the counts, float64 */
     uint32_t tp, fp, fn;                                          /* pred & true, pred & ~true, ~pred & true */
     int32_t status;
 } rfi_pair_result_t;
@@ -341,6 +372,24 @@ int rfi_rotate_pad(const void* in, void* out, int elem_bytes, int64_t n_waterfal
 /* Self test (used by tests/): counts the inputs t in [1, 2] (all 2^23 + 1 float32 values) for
  * which the range-restricted square root of the magnitude kernel differs from sqrt.rn.f32.
  *   mismatches_dev  device uint64, ACCUMULATED into (caller zeroes); must end up 0 */
+/* Preprocessor.patches -- the side-effect attribute of preprocessor.py:194, 272-311, 345-359: the PROCESSED
+ * patches (normalised / stretched / inf-filled samples in the data's precision on the real branch, the raw
+ * complex samples on the complex branch) in the dataset's final order.  The hot path never materialises
+ * them; this rebuilds them on demand from the cube and the statistics rfi_tile_stats left.
+ *   stats  device, as written by rfi_tile_stats / rfi_fused_patches for this plan
+ *   order  device int64[n_out], canonical patch index of every output patch (rfi_plan_slots' `order`)
+ *   out    device, n_out x P x P samples of T (real branch) or of the input's complex type
+ * Only for plans on RFI_PATH_FAST / RFI_PATH_BIG (dims multiples of the patch size). */
+int rfi_processed_patches(const rfi_plan_t* plan, const void* data, const rfi_tile_stat_t* stats,
+                          const int64_t* order, int64_t n_out, void* out, void* stream);
+
+/* Ingestion of the reference loaders' complex128 / float64 cubes (io/ms_loader.py:202-238,
+ * data_generation/synthetic_generator.py:648) as complex64 / float32: every component rounded once to
+ * nearest-even (= ndarray.astype(np.complex64)).  Opt-in (Preprocessor(..., compute_dtype="float32")): the
+ * reference itself computes such input in float64 up to preprocessor.py:376.
+ *   in   device, n samples of RFI_F64 / RFI_C128 (16-byte aligned);  out  device, n samples of RFI_F32 / RFI_C64 */
+int rfi_downcast(const void* in, void* out, int dtype_in, int64_t n, void* stream);
+
 int rfi_selftest_sqrt_unit(unsigned long long* mismatches_dev, void* stream);
 
 const char* rfi_last_error_string(void);

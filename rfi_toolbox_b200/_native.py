@@ -51,7 +51,8 @@ class RfiStats(C.Structure):
 class RfiPairResult(C.Structure):
     _fields_ = [
         ("ffi", C.c_double), ("mad_reduction", C.c_double), ("std_reduction", C.c_double),
-        ("flagged_fraction", C.c_double), ("tp", C.c_uint32), ("fp", C.c_uint32), ("fn", C.c_uint32),
+        ("flagged_fraction", C.c_double), ("iou", C.c_double), ("precision", C.c_double), ("recall", C.c_double),
+        ("f1", C.c_double), ("dice", C.c_double), ("tp", C.c_uint32), ("fp", C.c_uint32), ("fn", C.c_uint32),
         ("status", C.c_int32),
     ]
 
@@ -87,6 +88,10 @@ SYMBOLS = {
     "rfi_confusion_counts_segmented": (_I, [_VP, _I, _I, _VP, _I, _I, _I64, _I64, _VP, _VP]),
     "rfi_statistics_workspace_bytes": (C.c_size_t, []),
     "rfi_statistics": (_I, [_VP, _I, _VP, _I64, _VP, _VP, _VP]),
+    "rfi_statistics2_workspace_bytes": (C.c_size_t, [_I, _I64]),
+    "rfi_statistics2": (_I, [_VP, _I, _VP, _I64, _VP, _VP, _VP]),
+    "rfi_statistics_shard_begin": (_I, [_VP, _I, _VP, _I64, _VP, _VP, _VP]),
+    "rfi_statistics_shard_count": (_I, [_VP, _I64, _VP, _I, _I, _VP, _VP, _VP, _I, _VP, _VP, _VP]),
     "rfi_statistics_segmented": (_I, [_VP, _I, _VP, _I64, _I64, _VP, _VP]),
     "rfi_pair_sweep": (_I, [_VP, _I, _VP, _VP, _I64, _I64, _VP, _VP, _VP]),
     "rfi_legacy_permutation": (_I, [_VP, C.POINTER(C.c_int32), _I64, _VP]),
@@ -97,6 +102,8 @@ SYMBOLS = {
     "rfi_raw_tile_counts": (_I, [_VP, _I, _VP, _I64, _I64, _I64, C.c_int32, _VP, _VP]),
     "rfi_raw_gather": (_I, [_VP, _I, _VP, _I64, _I64, _I64, C.c_int32, _VP, _VP, _VP, _VP]),
     "rfi_rotate_pad": (_I, [_VP, _VP, _I, _I64, _I64, _I64, _I64, _I64, _I, _VP]),
+    "rfi_processed_patches": (_I, [C.POINTER(RfiPlan), _VP, _VP, _VP, _I64, _VP, _VP]),
+    "rfi_downcast": (_I, [_VP, _VP, _I, _I64, _VP]),
     "rfi_selftest_sqrt_unit": (_I, [_VP, _VP]),
     "rfi_last_error_string": (C.c_char_p, []),
     "rfi_abi_version": (_I, []),

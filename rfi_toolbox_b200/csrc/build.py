@@ -16,7 +16,7 @@ HERE = Path(__file__).resolve().parent
 PKG = HERE.parent
 LIB = PKG / "_lib" / "librfi_b200.so"
 OBJ = HERE / "build"
-SOURCES = ["rfi_error.cu", "rfi_tiles.cu", "rfi_generic.cu", "rfi_bigtile.cu", "rfi_metrics.cu", "rfi_stats.cu", "rfi_pairs.cu", "rfi_synth.cu", "rfi_raw.cu", "rfi_host.cpp"]
+SOURCES = ["rfi_error.cu", "rfi_tiles.cu", "rfi_generic.cu", "rfi_bigtile.cu", "rfi_metrics.cu", "rfi_stats.cu", "rfi_gstats.cu", "rfi_pairs.cu", "rfi_synth.cu", "rfi_raw.cu", "rfi_ingest.cu", "rfi_host.cpp"]
 HEADERS = sorted(HERE.glob("*.cuh")) + [PKG.parent / "include" / "rfi_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

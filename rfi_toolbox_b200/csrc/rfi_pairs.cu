@@ -35,7 +35,8 @@ struct PairShared {
     double rd[4];         // block totals
     uint32_t ru[8];
     uint32_t cnt[4][16];  // radix-select counters, rotating (see RoundCounter)
-    uint32_t nxt[2];      // count(key <= prefix), min(key > prefix)
+    uint32_t nxt[2];      // count(key <= prefix), min(key > prefix); the two maxima of the load pass
+    uint32_t ext[2];      // the two minima of the load pass
 };
 
 RFI_DEVINL uint4 pair_keys(const PK* skeys, int g) {
@@ -410,10 +411,19 @@ pair_sweep_kernel(const void* __restrict__ data, const uint8_t* __restrict__ fla
                      (!flags || (reinterpret_cast<uintptr_t>(flags) + (size_t)base) % 4 == 0) &&
                      (!truth || (reinterpret_cast<uintptr_t>(truth) + (size_t)base) % 4 == 0);
 
+    // shift for the moment sums: the pair's first sample (a typical value unless it is an outlier, in
+    // which case the conditioning check below sends the pair through the two-pass formula)
+    float K = 0.f;
+    if (seg > 0) {
+        if constexpr (DT == RFI_C64) { const float2 z = __ldg(static_cast<const float2*>(data) + base); K = cabs_np<float>(z.x, z.y); }
+        else K = __ldg(static_cast<const float*>(data) + base);
+        if (!(fabsf(K) < 3.0e38f)) K = 0.f;   // NaN / inf
+    }
     // ---- load
     uint32_t fmask = 0;     // bit e: element e of this thread is flagged
-    double s_all = 0.0, s_cln = 0.0;
+    double s_all = 0.0, s_cln = 0.0, ss_all = 0.0, ss_cln = 0.0;
     uint32_t nflag = 0, tp = 0, fp = 0, fn = 0, nan_all = 0, nan_cln = 0, mx_all = 0, mx_cln = 0;
+    uint32_t mn_all = kPExcl, mn_cln = kPExcl;
 #pragma unroll 2
     for (int g = 0; g < G; ++g) {
         const long long i0 = ((long long)g * NT + tid) * 4;
@@ -449,7 +459,7 @@ pair_sweep_kernel(const void* __restrict__ data, const uint8_t* __restrict__ fla
         const uint32_t fb = ((pz >> 7) & 1u) | ((pz >> 14) & 2u) | ((pz >> 21) & 4u) | ((pz >> 28) & 8u);
         fmask |= fb << (4 * g);
         PK k4[4];
-        float sa = 0.f, sc = 0.f;
+        float sa = 0.f, sc = 0.f, qa = 0.f, qc = 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const bool in = j < nin, fl = (fb >> j) & 1u;
@@ -462,28 +472,53 @@ pair_sweep_kernel(const void* __restrict__ data, const uint8_t* __restrict__ fla
             mx_all = km > mx_all ? km : mx_all;
             const PK kc = fl ? PK(0) : km;
             mx_cln = kc > mx_cln ? kc : mx_cln;
-            sa += in ? q[j] : 0.f;
-            sc += (in && !fl) ? q[j] : 0.f;
+            mn_all = k4[j] < mn_all ? k4[j] : mn_all;
+            const PK kd = fl ? kPExcl : k4[j];
+            mn_cln = kd < mn_cln ? kd : mn_cln;
+            const float d = q[j] - K;
+            const float x = in ? d : 0.f, xc = (in && !fl) ? d : 0.f;
+            sa += x; sc += xc;
+            qa += x * x; qc += xc * xc;
         }
-        s_all += (double)sa;
-        s_cln += (double)sc;
+        s_all += (double)sa; s_cln += (double)sc;
+        ss_all += (double)qa; ss_cln += (double)qc;
         *reinterpret_cast<uint4*>(skeys + ((size_t)g * NT + tid) * 4) = make_uint4(k4[0], k4[1], k4[2], k4[3]);
     }
     mx_all = warp_max(mx_all);
     mx_cln = warp_max(mx_cln);
-    if (tid == 0) { sh.nxt[0] = 0; sh.nxt[1] = 0; }
+    mn_all = warp_min(mn_all);
+    mn_cln = warp_min(mn_cln);
+    if (tid == 0) { sh.nxt[0] = 0; sh.nxt[1] = 0; sh.ext[0] = kPExcl; sh.ext[1] = kPExcl; }
     __syncthreads();
-    if ((tid & 31) == 0) { atomicMax(&sh.nxt[0], mx_all); atomicMax(&sh.nxt[1], mx_cln); }
-    double d2[2] = {s_all, s_cln};
+    if ((tid & 31) == 0) {
+        atomicMax(&sh.nxt[0], mx_all); atomicMax(&sh.nxt[1], mx_cln);
+        atomicMin(&sh.ext[0], mn_all); atomicMin(&sh.ext[1], mn_cln);
+    }
+    double d2[4] = {s_all, s_cln, ss_all, ss_cln};
     uint32_t u6[6] = {nflag, tp, fp, fn, nan_all, nan_cln};
-    pair_totals<2, 6>(d2, u6, sh);   // (its barriers also publish the two maxima)
+    pair_totals<4, 6>(d2, u6, sh);   // (its barriers also publish the extremes)
     mx_all = sh.nxt[0]; mx_cln = sh.nxt[1];
+    mn_all = sh.ext[0]; mn_cln = sh.ext[1];
     nflag = u6[0]; tp = u6[1]; fp = u6[2]; fn = u6[3]; nan_all = u6[4]; nan_cln = u6[5];
     const uint32_t n_cln = n_all - nflag;
-    const float mean_all = n_all ? (float)(d2[0] / (double)n_all) : 0.f;
-    const float mean_cln = n_cln ? (float)(d2[1] / (double)n_cln) : 0.f;
+    // the load pass summed d = x - K: sum x = sum d + n K
+    const float mean_all = n_all ? (float)((d2[0] + (double)n_all * (double)K) / (double)n_all) : 0.f;
+    const float mean_cln = n_cln ? (float)((d2[1] + (double)n_cln * (double)K) / (double)n_cln) : 0.f;
 
-    // ---- squared deviations from the T-rounded means (np.std: abs(x - mean) ** 2 in T, then summed)
+    // ---- sum of squared deviations from the T-rounded mean m (np.std: abs(x - m) ** 2, summed), with
+    //      e = m - K:  sum (x - m)^2 = sum d^2 - 2 e sum d + n e^2, from the float64 sums of the load pass.
+    //      The squares were rounded to float32 (~1e-9 of sum d^2 after averaging), so the result is good to
+    //      1e-7 as long as it is not a small difference: it must exceed 1 % of sum d^2 (K within a few sigma
+    //      of the mean); otherwise the data is swept again with the differences formed one by one
+    double dq[2];
+    bool resweep = false;
+    {
+        const double ea = (double)mean_all - (double)K, ec = (double)mean_cln - (double)K;
+        dq[0] = d2[2] - 2.0 * ea * d2[0] + (double)n_all * ea * ea;
+        dq[1] = d2[3] - 2.0 * ec * d2[1] + (double)n_cln * ec * ec;
+        resweep = !(dq[0] > 0.01 * d2[2]) || (n_cln && !(dq[1] > 0.01 * d2[3]));   // also true for NaN / inf sums
+    }
+    if (resweep) {
     double q_all = 0.0, q_cln = 0.0;
 #pragma unroll 2
     for (int g = 0; g < G; ++g) {
@@ -502,9 +537,10 @@ pair_sweep_kernel(const void* __restrict__ data, const uint8_t* __restrict__ fla
         q_all += (double)qa;
         q_cln += (double)qc;
     }
-    double dq[2] = {q_all, q_cln};
+    dq[0] = q_all; dq[1] = q_cln;
     uint32_t u0[1] = {0};
     pair_totals<2, 1>(dq, u0, sh);
+    }
 
     const double kNaN = __longlong_as_double(0x7ff8000000000000LL);
     rfi_stats_t oa, oc;
@@ -526,37 +562,25 @@ pair_sweep_kernel(const void* __restrict__ data, const uint8_t* __restrict__ fla
     // ---- order statistics: all samples, then the unflagged ones
     constexpr PK kInfHi = to_key_const_inf<float>(false), kInfLo = to_key_const_inf<float>(true);
     if (n_all && nan_all == 0) {
-        // +-inf present?  (the minimum is not tracked: ask the maximum and one cheap sweep only then)
-        bool any_inf = mx_all >= kInfHi;
-        if (!any_inf) {
-            uint32_t ninf = 0;
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                const uint4 kq = pair_keys(skeys, g);
-                ninf += (kq.x <= kInfLo) + (kq.y <= kInfLo) + (kq.z <= kInfLo) + (kq.w <= kInfLo);
-            }
-            any_inf = __syncthreads_or(ninf != 0);
-        }
+        const bool any_inf = mx_all >= kInfHi || mn_all <= kInfLo;   // +-inf present: radix route
         float med, mad;
         pair_median_mad(skeys, cand, samp, sh, n_all, any_inf, med, mad);
         oa.median = (double)med; oa.mad = (double)mad;
         if (nflag == 0) { oc.median = oa.median; oc.mad = oa.mad; }
     }
     if (nflag != 0 && n_cln && nan_cln == 0) {
-        uint32_t ninf = 0;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            PK* kp = skeys + ((size_t)g * NT + tid) * 4;
-            const uint4 kq = *reinterpret_cast<const uint4*>(kp);
-            PK k4[4] = {kq.x, kq.y, kq.z, kq.w};
+            const uint32_t fb = (fmask >> (4 * g)) & 15u;
+            if (fb) {
+                PK* kp = skeys + ((size_t)g * NT + tid) * 4;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if ((fmask >> (4 * g + j)) & 1u) k4[j] = kPExcl;
-                ninf += (k4[j] <= kInfLo || k4[j] == kInfHi) ? 1u : 0u;
+                for (int j = 0; j < 4; ++j)
+                    if ((fb >> j) & 1u) kp[j] = kPExcl;
             }
-            *reinterpret_cast<uint4*>(kp) = make_uint4(k4[0], k4[1], k4[2], k4[3]);
         }
-        const bool any_inf = __syncthreads_or(ninf != 0);
+        __syncthreads();
+        const bool any_inf = mx_cln >= kInfHi || mn_cln <= kInfLo;
         float med, mad;
         pair_median_mad(skeys, cand, samp, sh, n_cln, any_inf, med, mad);
         oc.median = (double)med; oc.mad = (double)mad;
@@ -570,6 +594,17 @@ pair_sweep_kernel(const void* __restrict__ data, const uint8_t* __restrict__ fla
             // statistics.py:73-97 on Python floats: float64, one IEEE operation per source operation
             rfi_pair_result_t r;
             r.tp = tp; r.fp = fp; r.fn = fn;
+            {   // metrics.py:39-45, 66-79, 98-104, 120-126, 145-152 on the integer counts, in float64
+                const double dtp = (double)tp, dfp = (double)fp, dfn = (double)fn;
+                const uint32_t uni = tp + fp + fn;
+                r.iou = uni == 0 ? 1.0 : dtp / (double)uni;
+                r.precision = (tp + fp == 0) ? (fn == 0 ? 1.0 : 0.0) : dtp / (double)(tp + fp);
+                r.recall = (tp + fn == 0) ? 1.0 : dtp / (double)(tp + fn);
+                const double pr = r.precision + r.recall;
+                r.f1 = pr == 0.0 ? 0.0 : 2.0 * (r.precision * r.recall) / pr;
+                r.dice = (2 * tp + fp + fn == 0) ? 1.0 : (double)(2 * tp) / (double)(2 * tp + fp + fn);
+                (void)dfp; (void)dfn;
+            }
             const double frac = n_all ? (double)nflag / (double)n_all : kNaN;   // np.sum(flags) / flags.size
             const bool guard = n_cln == 0 || oc.mad != oc.mad || oc.std != oc.std;  // :77-78
             if (guard) {

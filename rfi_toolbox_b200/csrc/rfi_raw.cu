@@ -7,7 +7,7 @@
 // 2 x (element + 1) bytes of HBM traffic per kept sample.
 #include <string.h>
 
-#include "rfi_common.cuh"
+#include "rfi_tiles.cuh"
 
 namespace rfi {
 
@@ -203,6 +203,97 @@ extern "C" int rfi_rotate_pad(const void* in, void* out, int elem_bytes, int64_t
         case 8: rotate_pad_kernel<float2><<<grid, 256, 0, st>>>(static_cast<const float2*>(in), static_cast<float2*>(out), channels, times, out_rows, out_cols, rotation); break;
         case 16: rotate_pad_kernel<double2><<<grid, 256, 0, st>>>(static_cast<const double2*>(in), static_cast<double2*>(out), channels, times, out_rows, out_cols, rotation); break;
         default: set_error("element size %d not supported", elem_bytes); return RFI_E_INVALID;
+    }
+    RFI_CUDA_TRY(cudaGetLastError());
+    return RFI_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Preprocessor.patches (preprocessor.py:194, 272-311, 345-359): the PROCESSED patches in the dataset's
+// final order -- normalised / stretched / inf-filled samples of the real branch, the raw complex samples
+// of the complex branch.  The hot path never materialises them (phase 2 goes from the cube to the image
+// channels); this kernel rebuilds them on demand from the cube, the tile statistics of phase 1 and the
+// canonical index of every output patch, with the very operations of phase 1 (process_sample).
+namespace rfi {
+
+template <int DT, bool kComplexBranch>
+__global__ void __launch_bounds__(256)
+processed_patches_kernel(PlanDev p, int P, const void* __restrict__ data, const rfi_tile_stat_t* __restrict__ stats,
+                         const long long* __restrict__ order, void* __restrict__ out) {
+    using T = typename In<DT>::T;
+    const long long k = blockIdx.x;
+    const long long q = order[k];
+    const int R = p.rotations, per = p.nh * p.nw;
+    const long long w = q / ((long long)R * per);
+    const int rem = (int)(q % ((long long)R * per)), r = rem / per, t = rem % per;
+    int ti, tj;
+    if (r == 0) { ti = t / p.nw; tj = t % p.nw; }
+    else if (r == 1) { ti = p.nh - 1 - t / p.nw; tj = t % p.nw; }
+    else if (r == 2) { tj = t / p.nh; ti = t % p.nh; }
+    else { tj = p.nw - 1 - t / p.nh; ti = t % p.nh; }
+    const size_t origin = ((size_t)w * p.channels + (size_t)ti * P) * p.times + (size_t)tj * P;
+    const rfi_tile_stat_t st = stats[w * per + (long long)ti * p.nw + tj];
+    const T mb = (T)st.median_before, fill = (T)st.inf_fill, ma = (T)st.median_after;
+    const long long total = (long long)P * P;
+    for (long long e = (long long)blockIdx.y * 256 + threadIdx.x; e < total; e += (long long)gridDim.y * 256) {
+        const int orow = (int)(e / P), ocol = (int)(e % P);
+        int sr, sc;
+        if (r == 0) { sr = orow; sc = ocol; }
+        else if (r == 1) { sr = P - 1 - orow; sc = ocol; }
+        else if (r == 2) { sr = ocol; sc = orow; }
+        else { sr = ocol; sc = P - 1 - orow; }
+        const size_t idx = origin + (size_t)sr * p.times + sc;
+        if constexpr (kComplexBranch) {
+            using Z = typename std::conditional<sizeof(T) == 4, float2, double2>::type;
+            static_cast<Z*>(out)[k * total + e] = static_cast<const Z*>(data)[idx];
+        } else {
+            T a, ph;
+            load1<DT, false>(data, idx, a, ph);
+            static_cast<T*>(out)[k * total + e] = process_sample<T>(a, p, mb, fill, ma);
+        }
+    }
+}
+
+}  // namespace rfi
+
+extern "C" int rfi_processed_patches(const rfi_plan_t* plan, const void* data, const rfi_tile_stat_t* stats,
+                                     const int64_t* order, int64_t n_out, void* out, void* stream) {
+    using namespace rfi;
+    if (!plan || plan->patch <= 0) { set_error("plan is NULL"); return RFI_E_INVALID; }
+    if (rfi_plan_path(plan) == RFI_PATH_GENERIC) {
+        set_error("rfi_processed_patches: only for geometries whose dims are multiples of the patch size (on-chip paths)");
+        return RFI_E_UNSUPPORTED;
+    }
+    if (n_out < 0 || (n_out > 0 && (!data || !stats || !order || !out))) { set_error("bad arguments to rfi_processed_patches"); return RFI_E_INVALID; }
+    if (n_out == 0) return RFI_OK;
+    const int P = plan->patch;
+    PlanDev d;
+    d.n_waterfalls = plan->n_waterfalls; d.channels = plan->channels; d.times = plan->times;
+    d.nh = (int)(plan->channels / P); d.nw = (int)(plan->times / P);
+    d.rotations = plan->rotations; d.stretch = plan->stretch; d.norm_before = plan->norm_before;
+    d.norm_after = plan->norm_after; d.flag_mode = plan->flag_mode; d.magnitude = plan->magnitude; d.sigma = plan->sigma;
+    const bool cb = plan->dtype >= RFI_C64 && !plan->magnitude;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long* ord = reinterpret_cast<const long long*>(order);
+    const unsigned gy = (unsigned)((P * P + 256 * 16 - 1) / (256 * 16));
+    for (long long k0 = 0; k0 < n_out; k0 += 0x7fffffffLL) {   // grid.x limit
+        const long long nk = n_out - k0 < 0x7fffffffLL ? n_out - k0 : 0x7fffffffLL;
+        const dim3 grid((unsigned)nk, gy);
+        const size_t esz = (plan->dtype == RFI_F32 ? 4 : plan->dtype == RFI_F64 ? 8 : plan->dtype == RFI_C64 ? 8 : 16);
+        const size_t osz = cb ? esz : (plan->dtype == RFI_F32 || plan->dtype == RFI_C64 ? 4 : 8);
+        void* o = static_cast<char*>(out) + (size_t)k0 * P * P * osz;
+        switch (plan->dtype) {
+            case RFI_F32:  processed_patches_kernel<RFI_F32, false><<<grid, 256, 0, st>>>(d, P, data, stats, ord + k0, o); break;
+            case RFI_F64:  processed_patches_kernel<RFI_F64, false><<<grid, 256, 0, st>>>(d, P, data, stats, ord + k0, o); break;
+            case RFI_C64:
+                if (cb) processed_patches_kernel<RFI_C64, true><<<grid, 256, 0, st>>>(d, P, data, stats, ord + k0, o);
+                else processed_patches_kernel<RFI_C64, false><<<grid, 256, 0, st>>>(d, P, data, stats, ord + k0, o);
+                break;
+            default:
+                if (cb) processed_patches_kernel<RFI_C128, true><<<grid, 256, 0, st>>>(d, P, data, stats, ord + k0, o);
+                else processed_patches_kernel<RFI_C128, false><<<grid, 256, 0, st>>>(d, P, data, stats, ord + k0, o);
+                break;
+        }
     }
     RFI_CUDA_TRY(cudaGetLastError());
     return RFI_OK;

@@ -62,9 +62,139 @@ def _run(data, flags):
     return st, d.numel()
 
 
+def _run_both(data, flags):
+    """(stats of all samples, stats of the unflagged samples, n) from ONE call (`rfi_statistics2`: the cube is
+    read once, two more passes over a 4 B / px scratch); flags None -> the second equals the first."""
+    lib = _native.load()
+    device = _device_of(data, flags)
+    require_cuda(device)
+    d = as_device_tensor(data, device)
+    if d.dtype not in _DTYPE_CODE:
+        raise TypeError(f"unsupported data dtype {d.dtype} (float32/64, complex64/128)")
+    f = None
+    if flags is not None:
+        f = _flags_tensor(flags, device)
+        if f.numel() != d.numel():
+            raise IndexError("flags and data must have the same shape")
+    code = _DTYPE_CODE[d.dtype]
+    with torch.cuda.device(device):
+        ws = torch.empty(int(lib.rfi_statistics2_workspace_bytes(code, d.numel())), dtype=torch.uint8, device=device)
+        out = torch.empty(2 * C.sizeof(_native.RfiStats), dtype=torch.uint8, device=device)
+        rc = lib.rfi_statistics2(d.data_ptr(), code, f.data_ptr() if f is not None else None, d.numel(),
+                                 out.data_ptr(), ws.data_ptr(), current_stream_ptr(device))
+        _native.check(rc, "rfi_statistics2")
+        host = out.cpu().numpy().tobytes()
+    n = C.sizeof(_native.RfiStats)
+    before, after = _native.RfiStats.from_buffer_copy(host[:n]), _native.RfiStats.from_buffer_copy(host[n:])
+    if before.count < 0:   # a sampled bracket missed its rank: the exact radix passes instead
+        before, _ = _run(d, None)
+        after = _run(d, flags)[0] if flags is not None else before
+    return before, after, d.numel()
+
+
+class _Stats:
+    """Field-compatible with `_native.RfiStats` (host-side result of the sharded path)."""
+    __slots__ = ("mean", "median", "std", "mad", "count", "n_flagged", "n_nan", "max")
+
+
+def _key_to_f32(k):
+    """Order-preserving key (csrc/rfi_common.cuh to_key / from_key) -> np.float32."""
+    k = int(k) & 0xffffffff
+    bits = (k ^ 0x80000000) if (k & 0x80000000) else (~k & 0xffffffff)
+    return np.array([bits], dtype=np.uint32).view(np.float32)[0]
+
+
+def _run_both_sharded(data, flags, group):
+    """`_run_both` over the UNION of the ranks' shards (baseline-sharded cube): pass A per rank,
+    moments summed over `group`, order statistics by an MSB-first radix select on the ranks' key scratches
+    whose per-pass counts are all-reduced (`rfi_statistics_shard_begin / _count`).  float32 / complex64."""
+    import torch.distributed as dist
+    lib = _native.load()
+    device = _device_of(data, flags)
+    require_cuda(device)
+    d = as_device_tensor(data, device)
+    if d.dtype not in (torch.float32, torch.complex64):
+        raise TypeError(f"sharded statistics: float32 / complex64 data (got {d.dtype})")
+    f = None
+    if flags is not None:
+        f = _flags_tensor(flags, device)
+        if f.numel() != d.numel():
+            raise IndexError("flags and data must have the same shape")
+    g = None if group is True else group
+    code, n_loc = _DTYPE_CODE[d.dtype], d.numel()
+    fptr = f.data_ptr() if f is not None else None
+    with torch.cuda.device(device):
+        stream = current_stream_ptr(device)
+        ws = torch.empty(int(lib.rfi_statistics2_workspace_bytes(code, n_loc)), dtype=torch.uint8, device=device)
+        state = torch.zeros(8, dtype=torch.float64, device=device)
+        _native.check(lib.rfi_statistics_shard_begin(d.data_ptr() if n_loc else None, code, fptr, n_loc, ws.data_ptr(),
+                                                     state.data_ptr(), stream), "rfi_statistics_shard_begin")
+        dist.all_reduce(state[:6], op=dist.ReduceOp.SUM, group=g)
+        dist.all_reduce(state[6:], op=dist.ReduceOp.MAX, group=g)
+        st = state.cpu().numpy()
+        n_all, n_flag = int(st[0]), int(st[1])
+        n = [n_all, n_all - n_flag]
+        n_nan = [int(st[2]), int(st[3])]
+        mean = [np.float32(st[4 + s] / n[s]) if n[s] else np.float32(0) for s in range(2)]
+        n_valid = [n[s] - n_nan[s] for s in range(2)]
+        k1 = [(n_valid[s] - 1) >> 1 if n_valid[s] else 0 for s in range(2)]
+        k2 = [n_valid[s] >> 1 for s in range(2)]
+        counts = torch.zeros(32, dtype=torch.int64, device=device)
+        sumsq = torch.zeros(2, dtype=torch.float64, device=device)
+        F2, U2 = C.c_float * 2, C.c_uint32 * 2
+
+        def select(dev_mode, centre, want_moments):
+            prefix = [0, 0]
+            for p, shift in enumerate(range(28, -1, -4)):
+                _native.check(lib.rfi_statistics_shard_count(
+                    fptr, n_loc, ws.data_ptr(), 0, dev_mode, F2(*centre), F2(*mean), U2(*prefix), shift, counts.data_ptr(),
+                    sumsq.data_ptr() if (want_moments and p == 0) else None, stream), "rfi_statistics_shard_count")
+                dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=g)
+                c = counts.cpu().numpy()
+                for s in range(2):
+                    prefix[s] |= int(np.count_nonzero(c[s * 16:s * 16 + 15] <= k1[s])) << shift
+            _native.check(lib.rfi_statistics_shard_count(fptr, n_loc, ws.data_ptr(), 1, dev_mode, F2(*centre), F2(*mean),
+                                                         U2(*prefix), 0, counts.data_ptr(), None, stream),
+                          "rfi_statistics_shard_count")
+            cle, nxt = counts[[0, 16]].clone(), counts[[1, 17]].clone()
+            dist.all_reduce(cle, op=dist.ReduceOp.SUM, group=g)
+            dist.all_reduce(nxt, op=dist.ReduceOp.MIN, group=g)   # int64 view of the uint64 keys: keys < 2^32
+            cle, nxt = cle.cpu().numpy(), nxt.cpu().numpy()
+            out = []
+            for s in range(2):
+                if n_valid[s] == 0:
+                    out.append(np.float32(np.nan))
+                    continue
+                a = _key_to_f32(prefix[s])
+                b = a if (k2[s] == k1[s] or k2[s] < int(cle[s])) else _key_to_f32(int(nxt[s]))
+                out.append(a if (n_valid[s] & 1) else np.float32(np.float32(a + b) * np.float32(0.5)))
+            return out
+
+        with np.errstate(invalid="ignore", over="ignore"):
+            med = select(0, [0.0, 0.0], True)
+            dist.all_reduce(sumsq, op=dist.ReduceOp.SUM, group=g)
+            ssq = sumsq.cpu().numpy()
+            centre = [float(m) if np.isfinite(m) else 0.0 for m in med]
+            mad = select(1, centre, False)
+    res = []
+    for s in range(2):
+        o = _Stats()
+        o.count, o.n_flagged, o.n_nan = n[s], (n_flag if s == 1 else 0), n_nan[s]
+        o.mean = o.median = o.std = o.mad = o.max = float("nan")
+        if n[s]:
+            o.mean = float(mean[s])
+            o.std = float(np.sqrt(np.float32(ssq[s] / n[s])))
+            o.max = float(_key_to_f32(int(st[6 + s])))
+            if n_nan[s] == 0:
+                o.median = float(med[s])
+                o.mad = float(mad[s]) if np.isfinite(med[s]) else float("nan")
+        res.append(o)
+    return res[0], res[1], n_all
+
+
 def compute_mad(data):
     """statistics.py:10-13 (median absolute deviation, scale 1.0)."""
-    st, _ = _run(data, None)
+    st, _, _ = _run_both(data, None)
     return _scalar(st.mad, data)
 
 
@@ -72,10 +202,15 @@ def _scalar(v, data):
     return v
 
 
-def compute_statistics(data, flags=None):
-    """statistics.py:16-56."""
-    st, n = _run(data, flags)
-    if flags is not None:
+def compute_statistics(data, flags=None, group=None):
+    """statistics.py:16-56.  `group` (extension; `True` = the default process group): `data` / `flags` are this
+    rank's baseline shard and the statistics are those of the whole cube -- every rank gets the same dict."""
+    before, after, n = _run_both(data, flags) if group is None else _run_both_sharded(data, flags, group)
+    return _stats_dict(after if flags is not None else before, n, flags is not None)
+
+
+def _stats_dict(st, n, flagged):
+    if flagged:
         flagged_fraction = st.n_flagged / n if n else float("nan")
     else:
         flagged_fraction = 0.0
@@ -88,10 +223,11 @@ def compute_statistics(data, flags=None):
     }
 
 
-def compute_ffi(data, flags):
-    """statistics.py:59-97."""
-    before = compute_statistics(data, flags=None)
-    after = compute_statistics(data, flags=flags)
+def compute_ffi(data, flags, group=None):
+    """statistics.py:59-97 (both compute_statistics calls of :73-74 from one pass over the cube).  `group`: as
+    for `compute_statistics` -- the FFI of a cube sharded over the ranks by baseline."""
+    b, a, n = _run_both(data, flags) if group is None else _run_both_sharded(data, flags, group)
+    before, after = _stats_dict(b, n, False), _stats_dict(a, n, flags is not None)
     if np.isnan(after["mad"]) or np.isnan(after["std"]):
         return {"ffi": 0.0, "mad_reduction": 0.0, "std_reduction": 0.0, "flagged_fraction": 1.0}
     mad_reduction = 1.0 - (after["mad"] / before["mad"])
@@ -106,13 +242,13 @@ def compute_calcquality(data, flags, reference_data=None):
     """statistics.py:100-193 (lower is better): sensitivity, mean shift, std shift and
     over-flagging penalty from the statistics before / after flagging; the reductions
     (moments, max) run on the GPU, the formulas are the reference's Python-float ones."""
+    b, a, n = _run_both(data, flags)
+    flag_stats = _stats_dict(a, n, flags is not None)
     if reference_data is not None:
-        ref_st, _ = _run(reference_data, None)
-        ref_stats = compute_statistics(reference_data, flags=None)
+        ref_st, _, nr = _run_both(reference_data, None)
+        ref_stats = _stats_dict(ref_st, nr, False)
     else:
-        ref_st, _ = _run(data, None)
-        ref_stats = compute_statistics(data, flags=None)
-    flag_stats = compute_statistics(data, flags=flags)
+        ref_st, ref_stats = b, _stats_dict(b, n, False)
     rmean, rstd = ref_stats["mean"], ref_stats["std"]
     fmean, fstd = flag_stats["mean"], flag_stats["std"]
     pflag = flag_stats["flagged_fraction"] * 100
@@ -138,8 +274,8 @@ def compute_calcquality(data, flags, reference_data=None):
 
 def print_statistics_comparison(data, flags):
     """statistics.py:196-229 -- same text, same number formats."""
-    b = compute_statistics(data, flags=None)
-    a = compute_statistics(data, flags=flags)
+    sb, sa, n = _run_both(data, flags)
+    b, a = _stats_dict(sb, n, False), _stats_dict(sa, n, flags is not None)
     f = compute_ffi(data, flags)
     print("\n" + "=" * 60)
     print("Statistics Comparison (Before/After Flagging)")
@@ -186,6 +322,17 @@ def _run_batch(data, flags):
             raise IndexError("flags and data must have the same shape")
     if n_seg == 0:
         return np.zeros((0, 2), dtype=_STATS_DTYPE), seg
+    if seg > 16384:
+        # pairs larger than one CTA's shared memory: the whole-cube routine per pair (three passes each)
+        host = np.zeros((n_seg, 2), dtype=_STATS_DTYPE)
+        dd, ff = d.reshape(n_seg, -1), (f.reshape(n_seg, -1).view(torch.bool) if f is not None else None)
+        for i in range(n_seg):
+            b, a, _ = _run_both(dd[i], ff[i] if ff is not None else None)
+            for col, st in ((0, b), (1, a)):
+                for k in _STATS_DTYPE.names:
+                    host[i, col][k] = getattr(st, k)
+            host[i, 0]["n_flagged"] = 0
+        return host, seg
     with torch.cuda.device(device):
         out = torch.empty((n_seg, 2, _STATS_DTYPE.itemsize), dtype=torch.uint8, device=device)
         rc = lib.rfi_statistics_segmented(d.data_ptr(), _DTYPE_CODE[d.dtype], f.data_ptr() if f is not None else None,
@@ -239,6 +386,7 @@ def compute_ffi_batch(data, flags, errors="raise"):
 
 
 _PAIR_DTYPE = np.dtype([("ffi", "f8"), ("mad_reduction", "f8"), ("std_reduction", "f8"), ("flagged_fraction", "f8"),
+                        ("iou", "f8"), ("precision", "f8"), ("recall", "f8"), ("f1", "f8"), ("dice", "f8"),
                         ("tp", "u4"), ("fp", "u4"), ("fn", "u4"), ("status", "i4")])
 _PINNED_RESULTS = {}
 
@@ -264,7 +412,6 @@ def evaluate_pairs(data, pred, true, errors="raise"):
     'flagged_fraction', 'iou', 'precision', 'recall', 'f1', 'dice' and int64 'tp', 'fp', 'fn'.
     Constant data makes the reference raise ZeroDivisionError; so does this function, naming the first
     such pair, unless `errors="nan"`."""
-    from .metrics import _ratio_arrays
     lib = _native.load()
     device = _device_of(data, pred, true)
     require_cuda(device)
@@ -295,11 +442,14 @@ def evaluate_pairs(data, pred, true, errors="raise"):
             host = _PINNED_RESULTS[key] = torch.empty((n, _PAIR_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True)
         host[:n].copy_(res, non_blocking=True)
         torch.cuda.current_stream(device).synchronize()
-        r = host[:n].numpy().view(_PAIR_DTYPE).reshape(n).copy()
-    zero = r["status"] == 2
-    if zero.any() and errors == "raise":
-        raise ZeroDivisionError(f"float division by zero (pair {int(np.flatnonzero(zero)[0])}: constant data)")
-    out = {k: r[k].astype(np.float64) for k in ("ffi", "mad_reduction", "std_reduction", "flagged_fraction")}
-    tp, fp, fn = (r[k].astype(np.int64) for k in ("tp", "fp", "fn"))
-    out.update(_ratio_arrays(tp, fp, fn))
+        r = host[:n].numpy().view(_PAIR_DTYPE).reshape(n)
+        if errors == "raise":
+            zero = r["status"] == 2
+            if zero.any():
+                raise ZeroDivisionError(f"float division by zero (pair {int(np.flatnonzero(zero)[0])}: constant data)")
+        # the ratios were formed on the device with the reference's float64 operations (metrics.py:25-152)
+        out = {k: np.ascontiguousarray(r[k]) for k in ("ffi", "mad_reduction", "std_reduction", "flagged_fraction",
+                                                       "iou", "precision", "recall", "f1", "dice")}
+        for k in ("tp", "fp", "fn"):
+            out[k] = r[k].astype(np.int64)
     return out

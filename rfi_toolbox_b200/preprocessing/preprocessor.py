@@ -14,7 +14,9 @@ order.  What changes is where the work happens:
 
 Extensions, all keyword-only and off by default: `magnitude=True` treats complex input as
 the reference treats `np.abs(data)` (the real branch, with |z| fused into the load);
-`device=`; `pin=` for the host->device copy of NumPy input.
+`device=`; `pin=` for the host->device copy of NumPy input; `compute_dtype="float32"` takes
+complex128 / float64 input (what the reference's loaders emit, io/ms_loader.py:202-238) in as
+complex64 / float32 instead of following it in float64 as the reference does (preprocessor.py:376).
 """
 from __future__ import annotations
 
@@ -204,7 +206,7 @@ class Preprocessor:
     #: mis-speculated is not tried again for a while.
     speculate = False
 
-    def __init__(self, data, flags=None, *, magnitude=False, device=None, pin=False):
+    def __init__(self, data, flags=None, *, magnitude=False, device=None, pin=False, compute_dtype=None):
         ndim = data.ndim
         if ndim == 3:
             data = data[None, ...]  # :187-189 -- flags are NOT reshaped (reference quirk Q7)
@@ -212,12 +214,15 @@ class Preprocessor:
             raise ValueError(f"Data must be 3D or 4D, got shape {tuple(data.shape)}")
         self.data = data
         self.flags = flags
-        self.patches = None
+        self._patches, self._patch_src = None, None
         self.patch_flags = None
         self.dataset = None
         self.magnitude = bool(magnitude)
         self._device = device
         self._pin = pin
+        if compute_dtype not in (None, "float32", "float64"):
+            raise ValueError("compute_dtype must be None (follow the input, as the reference does), 'float32' or 'float64'")
+        self._compute_dtype = compute_dtype
         self.last_tile_stats = None
         self.last_launch = None   # "single" / "two-phase" / ... : which launches the last fast-path call made
 
@@ -228,6 +233,53 @@ class Preprocessor:
         if not enable_augmentation or augmentation_rotations <= 1:
             return 1
         return 4 if augmentation_rotations >= 4 else 2
+
+    def _ingest_float32(self, lib, device, data):
+        """complex128 -> complex64 / float64 -> float32 on the device, one baseline at a time, so that at
+        most one baseline of the wide type is resident beside the narrow cube."""
+        narrow = torch.complex64 if data.is_complex() else torch.float32
+        with torch.cuda.device(device):
+            out = torch.empty(data.shape, dtype=narrow, device=device)
+            stream = current_stream_ptr(device)
+            code = _DTYPE_CODE[data.dtype]
+            for b in range(data.shape[0]):
+                wide = data[b]
+                if wide.device != device:
+                    wide = wide.to(device, non_blocking=True)
+                wide = wide.contiguous()
+                _native.check(lib.rfi_downcast(wide.data_ptr(), out[b].data_ptr(), code, wide.numel(), stream), "rfi_downcast")
+        return out
+
+    @property
+    def patches(self):
+        """preprocessor.py:194, 272-311, 345-359: the processed patches of the last `create_dataset` call in
+        the dataset's order -- `(N, P, P)` in the data's precision on the real branch (normalised, stretched,
+        inf-filled), the raw complex samples on the complex branch.  The hot path goes from the cube straight
+        to the image channels, so the array is built on first access (`rfi_processed_patches`) from the
+        input, the tile statistics and the patch order the call left, and cached.  None before the first call."""
+        if self._patches is None and self._patch_src is not None:
+            lib = _native.load()
+            plan, stats, order, device = self._patch_src
+            if lib.rfi_plan_path(C.byref(plan)) == _native.RFI_PATH_GENERIC:
+                raise NotImplementedError("Preprocessor.patches is rebuilt only for waterfalls whose dims are multiples of "
+                                          "the patch size (P = 128 / 256 / 512 / 1024)")
+            data = as_device_tensor(self.data, device)
+            if self._compute_dtype == "float32" and data.dtype in (torch.float64, torch.complex128):
+                data = self._ingest_float32(lib, device, data)
+            cb = data.is_complex() and not self.magnitude
+            real_t = torch.float32 if data.dtype in (torch.float32, torch.complex64) else torch.float64
+            with torch.cuda.device(device):
+                out = torch.empty((len(order), plan.patch, plan.patch), dtype=data.dtype if cb else real_t, device=device)
+                od = torch.from_numpy(np.ascontiguousarray(order, dtype=np.int64)).to(device)
+                _native.check(lib.rfi_processed_patches(C.byref(plan), data.data_ptr(), stats.data_ptr(), od.data_ptr(),
+                                                        len(order), out.data_ptr(), current_stream_ptr(device)),
+                              "rfi_processed_patches")
+            self._patches = out
+        return self._patches
+
+    @patches.setter
+    def patches(self, value):
+        self._patches = value
 
     def _resolve_device(self):
         for x in (self.data, self.flags):
@@ -292,6 +344,10 @@ class Preprocessor:
         data = host if host is not None else as_device_tensor(self.data, device, pin=self._pin)
         if data.dtype not in _DTYPE_CODE:
             raise TypeError(f"unsupported data dtype {data.dtype}: float32/64 or complex64/128")
+        if self._compute_dtype == "float32" and data.dtype in (torch.float64, torch.complex128):
+            # loader-shaped complex128 / float64 input (io/ms_loader.py:202-238) taken in as complex64 /
+            # float32: uploaded (if on the host) and rounded baseline by baseline (`rfi_downcast`)
+            data, host = self._ingest_float32(lib, device, data), None
         B, npol, C_, T_ = data.shape
         is_complex = data.is_complex()
         complex_branch = is_complex and not self.magnitude
@@ -364,7 +420,7 @@ class Preprocessor:
                                                         inference_mode, num_patches)
             return PendingDataset(self, dataset=self._finish(
                 images, labels, order, patch_size, stretch, flag_sigma, normalize_before_stretch,
-                normalize_after_stretch, augmentation_rotations))
+                normalize_after_stretch, augmentation_rotations, patch_src=(plan, None, order, device)))
 
         # ---- single launch?  (inference_mode, or MAD flags with the all-kept shuffle drawn ahead)
         sig = (P, stretch, float(flag_sigma), bool(normalize_before_stretch), bool(normalize_after_stretch), R)
@@ -510,7 +566,8 @@ class Preprocessor:
                 if nflag is not None and n_any == 0:
                     logger.warning("No flagged patches found - keeping all patches")
                 _release_host_buffers(hb)
-                return self._finish(spec["images"], spec["labels"], spec["order"], *ctx["meta"])
+                return self._finish(spec["images"], spec["labels"], spec["order"], *ctx["meta"],
+                                    patch_src=(plan, ctx["stats"], spec["order"], device))
             spec["images"] = spec["labels"] = None  # released before the right-sized outputs are allocated
         else:
             self.last_launch = "two-phase"
@@ -548,7 +605,7 @@ class Preprocessor:
             order = hb.order_np[:n_out].copy()
             _release_host_buffers(hb)
 
-        return self._finish(images, labels, order, *ctx["meta"])
+        return self._finish(images, labels, order, *ctx["meta"], patch_src=(plan, stats, order, device))
 
     # ---------------------------------------------------------------- zero-padded geometries
     @staticmethod
@@ -631,10 +688,11 @@ class Preprocessor:
         return images, labels, order
 
     def _finish(self, images, labels, order, patch_size, stretch, flag_sigma, normalize_before_stretch,
-                normalize_after_stretch, augmentation_rotations):
+                normalize_after_stretch, augmentation_rotations, patch_src=None):
+        self._patch_src = patch_src
         self.order = order  # canonical index of every output patch (not in the reference)
         self.patch_flags = labels
-        self.patches = None  # processed patches are never materialised on this path
+        self._patches = None  # rebuilt on first access (see the `patches` property)
         metadata = {  # :394-402
             "patch_size": patch_size,
             "stretch": stretch,

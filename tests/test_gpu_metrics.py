@@ -140,8 +140,13 @@ def test_ffi_sweep_ragged_segment_and_errors(native_lib):
     assert np.isnan(compute_ffi_batch(const, np.zeros_like(const, dtype=bool), errors="nan")["ffi"]).all()
     with pytest.raises(IndexError):
         compute_ffi_batch(const, np.zeros_like(const, dtype=np.uint8))
-    with pytest.raises(NotImplementedError):
-        compute_ffi_batch(np.ones((1, 256, 256), dtype=np.float32), np.zeros((1, 256, 256), dtype=bool))
+    # pairs beyond 128 x 128 go through the whole-cube routine, pair by pair
+    big, _, bpred = _pairs(2, np.complex64, seed=6, shape=(256, 200))
+    got = compute_ffi_batch(big, bpred)
+    for i in range(2):
+        want = oracle.compute_ffi(big[i], bpred[i])
+        for k, v in want.items():
+            assert got[k][i] == pytest.approx(v, rel=1e-6, abs=1e-9)
 
 
 @pytest.mark.parametrize("dtype", [np.complex64, np.float32, np.float64])
@@ -167,3 +172,59 @@ def test_calcquality_and_print_comparison(native_lib, dtype, capsys):
     assert "Statistics Comparison (Before/After Flagging)" in out and "Flagging Fidelity Index (FFI):" in out
     st = oracle.compute_statistics(data, noisy)
     assert f"  Count:  {st['count']}" in out and f"({st['flagged_fraction']*100:.2f}% flagged)" in out
+
+
+@pytest.mark.parametrize("dtype", [np.complex64, np.float32])
+@pytest.mark.parametrize("n", [1, 5, 4099, 300_001, 5_000_003])
+def test_whole_cube_statistics_three_pass_exact(native_lib, dtype, n):
+    """`rfi_statistics2` (sampled brackets, one to three list levels depending on n): medians and MADs are
+    exact order statistics of all samples and of the unflagged ones -- bit-identical to NumPy's -- for
+    sizes below, at and far above one CTA's final list, odd and even counts, ragged tails."""
+    import oracle
+    from rfi_toolbox_b200 import compute_ffi, compute_statistics
+    rng = np.random.default_rng(n)
+    data = rng.normal(0, 1, n) + 1j * rng.normal(0, 1, n)
+    flags = rng.random(n) < 0.1
+    data[flags] *= 50.0
+    flags ^= rng.random(n) < 0.01
+    data = (data if np.dtype(dtype).kind == "c" else np.abs(data) * np.where(rng.random(n) < 0.3, -1.0, 1.0)).astype(dtype)
+    for fl in (None, flags):
+        got, want = compute_statistics(data, fl), oracle.compute_statistics(data, fl)
+        for k in ("median", "mad"):
+            assert (np.isnan(got[k]) and np.isnan(want[k])) or np.float32(got[k]) == np.float32(want[k]), (k, got[k], want[k])
+        scale = float(np.mean(np.abs(data)))
+        for k in ("mean", "std"):
+            assert got[k] == pytest.approx(want[k], rel=1e-6, abs=2e-6 * scale, nan_ok=True), (k, got[k], want[k])
+        assert got["count"] == want["count"] and got["flagged_fraction"] == pytest.approx(want["flagged_fraction"])
+    if n > 5 and flags.any() and not flags.all():
+        got, want = compute_ffi(data, flags), oracle.compute_ffi(data, flags)
+        for k, v in want.items():
+            assert got[k] == pytest.approx(v, rel=1e-5, abs=1e-7), (k, got[k], v)
+
+
+def test_whole_cube_statistics_special_values(native_lib):
+    import oracle
+    from rfi_toolbox_b200 import compute_statistics
+    rng = np.random.default_rng(3)
+    base = np.abs(rng.normal(0, 1, 400_000)).astype(np.float32)
+    flags = rng.random(base.size) < 0.2
+    for name in ("nan_flagged", "nan_unflagged", "inf", "all_flagged", "duplicates"):
+        d, f = base.copy(), flags.copy()
+        if name == "nan_flagged":
+            d[7] = np.nan; f[7] = True
+        elif name == "nan_unflagged":
+            d[7] = np.nan; f[7] = False
+        elif name == "inf":
+            d[11] = np.inf; d[12] = -np.inf
+        elif name == "all_flagged":
+            f[:] = True
+        else:
+            d = np.round(d * 4) / 4
+        for fl in (None, f):
+            got, want = compute_statistics(d, fl), oracle.compute_statistics(d, fl)
+            for k in ("median", "mad", "mean", "std"):
+                a, b = got[k], want[k]
+                assert (np.isnan(a) and np.isnan(b)) or a == pytest.approx(b, rel=2e-6, abs=1e-6) or (np.isinf(a) and a == b), (name, k, a, b)
+            for k in ("median", "mad"):
+                a, b = got[k], want[k]
+                assert (np.isnan(a) and np.isnan(b)) or np.float32(a) == np.float32(b), (name, k, a, b)

@@ -103,3 +103,82 @@ def test_partial_peer_failure_falls_back_everywhere(native_lib):
     for rank, want, got, none_ctx in results:
         assert none_ctx == [True], "a rank kept the peer path although rank 1 failed"
         assert all(g == want for g in got)
+
+
+def _worker_sharded_ffi(rank, world, port, q):
+    """compute_ffi / compute_statistics of a cube sharded by baseline == the unsharded oracle."""
+    import torch.distributed as dist
+
+    import oracle
+    from rfi_toolbox_b200 import compute_ffi, compute_statistics
+    from rfi_toolbox_b200.utils.sharding import baseline_shard
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    out = []
+    try:
+        for case, (n_bl, dtype) in enumerate([(5, np.complex64), (4, np.float32), (1, np.complex64)]):   # n_bl = 1: an empty shard
+            rng = np.random.default_rng(40 + case)
+            shape = (n_bl, 2, 96, 130)
+            data = rng.normal(0, 1, shape) + 1j * rng.normal(0, 1, shape)
+            flags = rng.random(shape) < 0.1
+            data[flags] *= 30.0
+            flags ^= rng.random(shape) < 0.01
+            data = (data if np.dtype(dtype).kind == "c" else np.abs(data)).astype(dtype)
+            sl = baseline_shard(n_bl, world, rank)
+            d, f = torch.from_numpy(data[sl]).to(dev), torch.from_numpy(flags[sl]).to(dev)
+            got_ffi = compute_ffi(d, f, group=True)
+            got_b = compute_statistics(d, None, group=True)
+            got_a = compute_statistics(d, f, group=True)
+            out.append((got_ffi, got_b, got_a, oracle.compute_ffi(data, flags), oracle.compute_statistics(data, None),
+                        oracle.compute_statistics(data, flags)))
+        q.put((rank, out))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def _check_sharded(out):
+    for got_ffi, got_b, got_a, want_ffi, want_b, want_a in out:
+        for got, want in ((got_b, want_b), (got_a, want_a)):
+            for k in ("median", "mad"):
+                assert np.float32(got[k]) == np.float32(want[k]), (k, got[k], want[k])
+            for k in ("mean", "std", "flagged_fraction"):
+                assert got[k] == pytest.approx(want[k], rel=1e-6, abs=1e-7), (k, got[k], want[k])
+            assert got["count"] == want["count"]
+        for k, v in want_ffi.items():
+            assert got_ffi[k] == pytest.approx(v, rel=1e-5, abs=1e-7), (k, got_ffi[k], v)
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_ffi_matches_unsharded_oracle(native_lib):
+    import torch.multiprocessing as mp
+    world, port = 2, 29641
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_sharded_ffi, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, out in results:
+        _check_sharded(out)
+    assert results[0][1][0][0] == results[1][1][0][0]     # every rank holds the same FFI
+
+
+@pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a GPU")
+def test_sharded_ffi_group_of_one(native_lib):
+    """The sharded code path (radix select with all-reduced counts) on a process group of ONE rank: runs on the
+    single-GPU box of the regular GPU suite."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_worker_sharded_ffi, args=(0, 1, 29643, q))
+    p.start()
+    rank, out = q.get(timeout=300)
+    p.join(timeout=120)
+    assert p.exitcode == 0
+    _check_sharded(out)

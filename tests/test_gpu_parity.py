@@ -399,3 +399,74 @@ def test_flat_and_all_nan_channels_are_zero(native_lib, patch):
     pre, ds = _run_gpu(data, flags, **kw)
     ods, inter = _run_oracle(data, flags, **kw)
     _compare(ds, ods, inter, pre, label=f"flat / all-NaN P{patch}")
+
+
+@pytest.mark.parametrize("case", ["real_sqrt", "real_log10_p256", "complex_custom", "c64_magnitude"])
+def test_patches_attribute_rebuilt_on_access(native_lib, case):
+    """`Preprocessor.patches` (preprocessor.py:194, 272-311, 345-359): the processed patches in the dataset's
+    order, rebuilt on first access by `rfi_processed_patches`.  Bit-exact for stretch None / SQRT (IEEE ops);
+    LOG10 within 2 ulp of NumPy's host-dependent log10."""
+    from rfi_toolbox_b200 import Preprocessor
+    if case == "real_sqrt":
+        data, mask = make_cube(dtype=np.float32, seed=3)
+        flags, mag, kw = None, False, dict(stretch="SQRT", flag_sigma=5, use_custom_flags=False)
+    elif case == "real_log10_p256":
+        data, mask = make_cube(n_bl=1, n_pol=2, channels=512, times=512, dtype=np.float32, seed=4)
+        flags, mag, kw = None, False, dict(patch_size=256, stretch="LOG10", flag_sigma=5, use_custom_flags=False)
+    elif case == "complex_custom":
+        data, mask = make_cube(dtype=np.complex64, seed=5)
+        flags, mag, kw = mask, False, dict(stretch=None, use_custom_flags=True)
+    else:
+        data, mask = make_cube(dtype=np.complex64, seed=6)
+        flags, mag, kw = None, True, dict(stretch=None, flag_sigma=5, use_custom_flags=False, normalize_after_stretch=True)
+    np.random.seed(3)
+    pre = Preprocessor(data, flags, magnitude=mag)
+    assert pre.patches is None
+    ds = pre.create_dataset(**kw)
+    got = pre.patches
+    assert got is pre.patches                      # cached
+    np.random.seed(3)
+    ods, inter = _run_oracle(data, flags, magnitude=mag, seed=3, **kw)
+    want = inter["processed"][inter["order"]]
+    assert got.shape == want.shape and len(got) == len(ds)
+    g = got.cpu().numpy()
+    assert g.dtype == want.dtype
+    if kw.get("stretch") == "LOG10":
+        fin = np.isfinite(want)
+        assert np.array_equal(np.isfinite(g), fin)
+        assert np.allclose(g[fin], want[fin], rtol=4e-7, atol=1e-7)
+    else:
+        assert np.array_equal(g, want, equal_nan=True)
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.float64])
+@pytest.mark.parametrize("where", ["host", "device"])
+def test_loader_shaped_wide_input_taken_in_as_float32(native_lib, dtype, where):
+    """MSLoader / the generator emit complex128 (io/ms_loader.py:202-238).  With
+    compute_dtype="float32" the cube is rounded once per component on the device (`rfi_downcast`) and the
+    call equals the one on `data.astype(complex64 / float32)` bit for bit; without it the dtype is followed
+    (float64 arithmetic), as in the reference."""
+    from rfi_toolbox_b200 import Preprocessor
+    data, mask = make_cube(n_bl=2, n_pol=2, dtype=dtype, seed=12)
+    narrow = data.astype(np.complex64 if np.dtype(dtype).kind == "c" else np.float32)
+    mag = np.dtype(dtype).kind == "c"
+    kw = dict(stretch="SQRT", flag_sigma=5, use_custom_flags=False)
+    src = torch.from_numpy(data).cuda() if where == "device" else data
+    np.random.seed(6)
+    pre = Preprocessor(src, None, magnitude=mag, compute_dtype="float32")
+    ds = pre.create_dataset(**kw)
+    np.random.seed(6)
+    pre2 = Preprocessor(narrow, None, magnitude=mag)
+    ds2 = pre2.create_dataset(**kw)
+    assert np.array_equal(pre.order, pre2.order)
+    assert torch.equal(ds.labels, ds2.labels) and torch.equal(ds.images, ds2.images)
+    assert pre.patches.dtype == torch.float32 and torch.equal(pre.patches, pre2.patches)
+    # the custom-flag complex branch too
+    np.random.seed(6)
+    if mag:
+        a = Preprocessor(src, mask, compute_dtype="float32").create_dataset(use_custom_flags=True)
+        np.random.seed(6)
+        b = Preprocessor(narrow, mask).create_dataset(use_custom_flags=True)
+        assert torch.equal(a.labels, b.labels) and torch.equal(a.images, b.images)
+    with pytest.raises(ValueError):
+        Preprocessor(data, None, compute_dtype="float16")
