@@ -509,15 +509,36 @@ constexpr int kBigFP = kP + 4;   // pitch of the transposed label tile (bytes)
 // Pass A of a sub-tile: log-amplitude tile, halo rows / columns from the neighbouring sub-tiles of
 // the same group, labels.  kWrite: label rows of rotations 0 / 1 go straight to global memory and
 // the transposed label tile is kept for rotations 2 / 3; else only the flagged samples are counted.
-template <bool kFast, bool kWrite>
-RFI_DEVINL void big_pass_a(const BigGeom& g, const BigTile& t, const BigMath& bm, const float* __restrict__ src,
+// kCplx (complex branch, preprocessor.py:562-606): `src` is the complex64 cube itself, L = log10(|z| + 1e-10) with no
+// normalisation or stretch, and the phase channel ((angle + pi) / (2 pi), ImageNet-normalised) goes to the tile `Ph`.
+template <bool kCplx> struct BigSrc { using type = float; };
+template <> struct BigSrc<true> { using type = float2; };
+
+template <bool kFast, bool kCplx>
+RFI_DEVINL float big_sample_L(const typename BigSrc<kCplx>::type& v, const PlanDev& p, const BigMath& bm, unsigned char& fm, float& ph) {
+    if constexpr (kCplx) {
+        fm = 0;
+        const float a = cabs_fast(v.x, v.y);
+        const float c2 = (atan2f(v.y, v.x) + 3.141592653589793f) * (float)(1.0 / 6.283185307179586);
+        ph = __fmaf_rn(c2, 1.0f / 0.225f, (0.0f - 0.406f) / 0.225f);
+        return log10_img(a + 1e-10f);
+    } else {
+        ph = 0.f;
+        return big_eval<kFast>(v, p, bm, fm);
+    }
+}
+
+template <bool kFast, bool kWrite, bool kCplx = false>
+RFI_DEVINL void big_pass_a(const BigGeom& g, const BigTile& t, const BigMath& bm, const void* __restrict__ src_v,
                            const uint8_t* __restrict__ flags, float* Ls, float* halo, unsigned char* FbT,
-                           uint8_t* lab0, uint8_t* lab1, uint32_t& nflag) {
+                           uint8_t* lab0, uint8_t* lab1, uint32_t& nflag, float* Ph = nullptr) {
+    using S = typename BigSrc<kCplx>::type;
+    const S* __restrict__ src = static_cast<const S*>(src_v);
     constexpr int RS = kBigNT / 32, STEPS = kP / RS, Q = kP / 32;
     const PlanDev& p = g.p;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const size_t T_ = (size_t)p.times;
-    float cur[Q], nxt[Q];
+    S cur[Q], nxt[Q];
 #pragma unroll
     for (int q = 0; q < Q; ++q) cur[q] = __ldg(src + t.origin + (size_t)warp * T_ + lane + 32 * q);
     uint32_t nf = 0;
@@ -538,9 +559,11 @@ RFI_DEVINL void big_pass_a(const BigGeom& g, const BigTile& t, const BigMath& bm
         for (int q = 0; q < Q; ++q) {
             const int col = lane + 32 * q;
             unsigned char fm;
-            const float L = big_eval<kFast>(cur[q], p, bm, fm);
+            float ph;
+            const float L = big_sample_L<kFast, kCplx>(cur[q], p, bm, fm, ph);
             const unsigned char f = (p.flag_mode == RFI_FLAGS_MAD) ? fm : fl[q];
             Ls[row * kBigLP + col] = L;
+            if constexpr (kCplx && kWrite) Ph[row * kBigLP + col] = ph;
             if constexpr (kWrite) {
                 FbT[col * kBigFP + row] = f;
                 if (lab0) lab0[(size_t)row * g.P + col] = f;
@@ -561,7 +584,8 @@ RFI_DEVINL void big_pass_a(const BigGeom& g, const BigTile& t, const BigMath& bm
             const size_t at = side == 0 ? t.origin - T_ + k : side == 1 ? t.origin + (size_t)kP * T_ + k
                             : side == 2 ? t.origin + (size_t)k * T_ - 1 : t.origin + (size_t)k * T_ + kP;
             unsigned char fm;
-            L = big_eval<kFast>(__ldg(src + at), p, bm, fm);
+            float ph;
+            L = big_sample_L<kFast, kCplx>(__ldg(src + at), p, bm, fm, ph);
         }
         halo[side * kP + k] = L;
     }
@@ -606,8 +630,9 @@ RFI_DEVINL void big_pass_b(const BigTile& t, int R, const float* Ls, const float
 
 // ------------------------------------------------------------------------------------------
 // sub-tile: flag count + min / max of L and of the squared-gradient variants -> group accumulators
+template <bool kCplx>
 __global__ void __launch_bounds__(kBigNT, 2)
-big_range_kernel(BigGeom g, const float* __restrict__ src, const uint8_t* __restrict__ flags,
+big_range_kernel(BigGeom g, const void* __restrict__ src, const uint8_t* __restrict__ flags,
                  rfi_tile_stat_t* __restrict__ stats, BigGroup* __restrict__ groups,
                  const int* __restrict__ list, int count_flags) {
     constexpr int LP = kBigLP;
@@ -623,7 +648,8 @@ big_range_kernel(BigGeom g, const float* __restrict__ src, const uint8_t* __rest
     const rfi_tile_stat_t st = stats[t.grp];
     const BigMath bm = big_math(p, st);
     uint32_t nf = 0;
-    if (bm.fast) big_pass_a<true, false>(g, t, bm, src, flags, Ls, halo, nullptr, nullptr, nullptr, nf);
+    if constexpr (kCplx) big_pass_a<false, false, true>(g, t, bm, src, flags, Ls, halo, nullptr, nullptr, nullptr, nf);
+    else if (bm.fast) big_pass_a<true, false>(g, t, bm, src, flags, Ls, halo, nullptr, nullptr, nullptr, nf);
     else big_pass_a<false, false>(g, t, bm, src, flags, Ls, halo, nullptr, nullptr, nullptr, nf);
     __syncthreads();
     float lo4[4], hi4[4];
@@ -696,9 +722,9 @@ RFI_DEVINL ChanScale<float> big_scale(uint32_t kmin, uint32_t kmax, bool take_sq
 // own sub-tile after pass A and the group's ranges are combined through distributed shared memory
 // (one cluster barrier pair), so no separate range launch reads the magnitudes again.  Otherwise
 // the ranges come from big_range_kernel's accumulators.
-template <bool kCluster>
-__global__ void __launch_bounds__(kBigNT, 2)
-big_write_kernel(BigGeom g, const float* __restrict__ src, const uint8_t* __restrict__ flags,
+template <bool kCluster, bool kCplx = false>
+__global__ void __launch_bounds__(kBigNT, kCplx ? 1 : 2)
+big_write_kernel(BigGeom g, const void* __restrict__ src, const uint8_t* __restrict__ flags,
                  const rfi_tile_stat_t* __restrict__ stats, const BigGroup* __restrict__ groups,
                  const long long* __restrict__ dest_slot, float* __restrict__ images,
                  uint8_t* __restrict__ labels) {
@@ -708,6 +734,7 @@ big_write_kernel(BigGeom g, const float* __restrict__ src, const uint8_t* __rest
     float* halo = Ls + (size_t)kP * LP;                                   // [4][kP]
     unsigned char* FbT = reinterpret_cast<unsigned char*>(halo + 4 * kP); // [kP][FP]
     float* stage = reinterpret_cast<float*>(FbT + (size_t)kP * FP);       // [warps][3 * kP]
+    [[maybe_unused]] float* Ph = stage + (size_t)(NT / 32) * 3 * kP;      // [kP][LP] phase channel (complex branch)
 
     const BigTile t = big_tile(g, blockIdx.x);
     const PlanDev& p = g.p;
@@ -732,7 +759,8 @@ big_write_kernel(BigGeom g, const float* __restrict__ src, const uint8_t* __rest
         return sl < 0 ? nullptr : labels + (size_t)sl * PP + (size_t)br[r] * kP * P + (size_t)bc[r] * kP;
     };
     uint32_t nf_unused = 0;
-    if (bm.fast) big_pass_a<true, true>(g, t, bm, src, flags, Ls, halo, FbT, lab_at(slot0, 0), lab_at(slot1, 1), nf_unused);
+    if constexpr (kCplx) big_pass_a<false, true, true>(g, t, bm, src, flags, Ls, halo, FbT, lab_at(slot0, 0), lab_at(slot1, 1), nf_unused, Ph);
+    else if (bm.fast) big_pass_a<true, true>(g, t, bm, src, flags, Ls, halo, FbT, lab_at(slot0, 0), lab_at(slot1, 1), nf_unused);
     else big_pass_a<false, true>(g, t, bm, src, flags, Ls, halo, FbT, lab_at(slot0, 0), lab_at(slot1, 1), nf_unused);
     __syncthreads();
 
@@ -815,8 +843,15 @@ big_write_kernel(BigGeom g, const float* __restrict__ src, const uint8_t* __rest
                 prev[q] = c;
                 const float gr = sqrt_fast(__fmaf_rn(td, td, fd * fd));
                 wstage[ocol * 3 + 0] = gs.ok ? __fmaf_rn(gr, ga, gb) : nb0;   // flat / all-NaN channel: exactly 0 before ImageNet
-                wstage[ocol * 3 + 1] = ls.ok ? __fmaf_rn(c, la, lb) : nb1;
-                wstage[ocol * 3 + 2] = nb2;
+                if constexpr (kCplx) {   // fixed scale clip((L + 3) / 7, 0, 1) and the phase (preprocessor.py:588-604)
+                    float u = (c - (-3.0f)) * (float)(1.0 / 7.0);
+                    u = u < 0.f ? 0.f : (u > 1.f ? 1.f : u);  // np.clip keeps NaN
+                    wstage[ocol * 3 + 1] = __fmaf_rn(u, is1, nb1);
+                    wstage[ocol * 3 + 2] = Ph[at];
+                } else {
+                    wstage[ocol * 3 + 1] = ls.ok ? __fmaf_rn(c, la, lb) : nb1;
+                    wstage[ocol * 3 + 2] = nb2;
+                }
             }
             __syncwarp();
             float4* dst = reinterpret_cast<float4*>(out_img + (size_t)orow * P * 3);
@@ -843,9 +878,11 @@ bool plan_is_big(const rfi_plan_t* plan) {
     const int P = plan->patch;
     if (P != 256 && P != 512 && P != 1024) return false;
     if (plan->channels % P || plan->times % P || plan->channels < P || plan->times < P) return false;
-    if (plan->channels <= P && plan->times <= P) return false;  // patchify skipped (preprocessor.py:261)
+    // (a waterfall of exactly P x P is not patchified by the reference, preprocessor.py:261 -- the "patches" are
+    //  then the R rotated waterfalls, which is what one tile per waterfall gives)
     if (plan->dtype != RFI_F32 && plan->dtype != RFI_C64) return false;
-    if (plan->dtype == RFI_C64 && !plan->magnitude) return false;  // complex branch: generic path
+    // complex branch (no normalisation, no stretch): with the caller's flags or none; MAD flags of |z| stay generic
+    if (plan->dtype == RFI_C64 && !plan->magnitude && plan->flag_mode == RFI_FLAGS_MAD) return false;
     const bool need_median = plan->norm_before || plan->norm_after || plan->flag_mode == RFI_FLAGS_MAD;
     if (!need_median && plan->stretch != RFI_STRETCH_NONE) return false;  // inf fill without a median pass
     if (plan->rotations != 1 && plan->rotations != 2 && plan->rotations != 4) return false;
@@ -894,7 +931,7 @@ static BigWs big_ws(const rfi_plan_t* plan, const BigGeom& g, void* ws) {
     w.samples = reinterpret_cast<uint32_t*>(b + off); off += up256((size_t)g.n_groups * kBigS * sizeof(uint32_t));
     w.cand = reinterpret_cast<uint32_t*>(b + off); off += up256((size_t)g.n_groups * g.cap * sizeof(uint32_t));
     w.mag = reinterpret_cast<float*>(b + off);
-    if (plan->dtype == RFI_C64) off += up256((size_t)plan->n_waterfalls * plan->channels * plan->times * sizeof(float));
+    if (plan->dtype == RFI_C64 && plan->magnitude) off += up256((size_t)plan->n_waterfalls * plan->channels * plan->times * sizeof(float));
     w.bytes = off;
     return w;
 }
@@ -913,8 +950,20 @@ static bool big_use_cluster(const BigGeom& g) {
 }
 
 static size_t big_range_smem() { return ((size_t)kP * kBigLP + 4 * kP + kBigNT / 32 * 8) * sizeof(float); }
-static size_t big_write_smem() {
-    return ((size_t)kP * kBigLP + 4 * kP) * sizeof(float) + (size_t)kP * kBigFP + (size_t)(kBigNT / 32) * 3 * kP * sizeof(float);
+static size_t big_write_smem(bool cplx = false) {
+    return ((size_t)kP * kBigLP + 4 * kP) * sizeof(float) + (size_t)kP * kBigFP + (size_t)(kBigNT / 32) * 3 * kP * sizeof(float) +
+           (cplx ? (size_t)kP * kBigLP * sizeof(float) : 0);
+}
+
+// complex branch: nothing is measured on the data; the statistics entry only carries the flag count
+__global__ void big_neutral_stats_kernel(BigGeom g, rfi_tile_stat_t* __restrict__ stats) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n_groups) return;
+    rfi_tile_stat_t st;
+    st.median_before = st.inf_fill = st.median_after = 0.0;
+    st.centre = st.mad = st.thr_lo = st.thr_hi = 0.0;
+    st.n_valid = g.P * g.P; st.n_inf = 0; st.n_flagged = 0; st.route = 0; st.raw_lo = st.raw_hi = 0.0;
+    stats[i] = st;
 }
 
 int big_tile_stats(const rfi_plan_t* plan, const void* data, const uint8_t* flags,
@@ -926,6 +975,22 @@ int big_tile_stats(const rfi_plan_t* plan, const void* data, const uint8_t* flag
     if (!workspace) { set_error("patch sizes above 128 need the workspace rfi_plan_workspace_bytes() reports"); return RFI_E_INVALID; }
     if (g.p.flag_mode == RFI_FLAGS_CUSTOM && !flags) { set_error("custom flag mode needs flags"); return RFI_E_INVALID; }
     const BigWs w = big_ws(plan, g, workspace);
+    if (plan->dtype == RFI_C64 && !plan->magnitude) {
+        // complex branch (preprocessor.py:285-292: no normalisation, no stretch): flag counts per patch, and --
+        // unless the writer's cluster finds them itself -- the per-patch ranges of the gradient variants
+        const unsigned subs_c = (unsigned)(g.n_groups * g.n2), groups_c = (unsigned)g.n_groups;
+        const int count = g.p.flag_mode == RFI_FLAGS_CUSTOM ? 1 : 0;
+        big_init_kernel<<<(groups_c + 255) / 256, 256, 0, st>>>(g, w.groups, w.fail_count);
+        big_neutral_stats_kernel<<<(groups_c + 255) / 256, 256, 0, st>>>(g, stats);
+        if (big_use_cluster(g)) {
+            if (count) big_count_kernel<<<subs_c, kBigNT, 0, st>>>(g, nullptr, flags, stats, w.groups);
+        } else {
+            RFI_CUDA_TRY(cudaFuncSetAttribute(big_range_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_range_smem()));
+            big_range_kernel<true><<<subs_c, kBigNT, big_range_smem(), st>>>(g, data, flags, stats, w.groups, nullptr, count);
+        }
+        RFI_CUDA_TRY(cudaGetLastError());
+        return RFI_OK;
+    }
     const bool cplx = plan->dtype == RFI_C64;
     const bool need_median = g.p.norm_before || g.p.norm_after || g.p.flag_mode == RFI_FLAGS_MAD;
     const float* src = cplx ? w.mag : static_cast<const float*>(data);
@@ -955,7 +1020,7 @@ int big_tile_stats(const rfi_plan_t* plan, const void* data, const uint8_t* flag
         // through the same subset entry point with the identity list
         n_fail = -1;
     }
-    RFI_CUDA_TRY(cudaFuncSetAttribute(big_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_range_smem()));
+    RFI_CUDA_TRY(cudaFuncSetAttribute(big_range_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_range_smem()));
     if (n_fail != 0) {
         if (n_fail < 0) {
             // identity list
@@ -970,12 +1035,12 @@ int big_tile_stats(const rfi_plan_t* plan, const void* data, const uint8_t* flag
         if (!cluster) {
             big_rearm_kernel<<<(n_fail + 255) / 256, 256, 0, st>>>(w.groups, w.fail_list, n_fail);
             // ranges of the listed groups (their flag counts come from the generic path)
-            big_range_kernel<<<(unsigned)n_fail * g.n2, kBigNT, big_range_smem(), st>>>(g, src, flags, stats, w.groups, w.fail_list, 0);
+            big_range_kernel<false><<<(unsigned)n_fail * g.n2, kBigNT, big_range_smem(), st>>>(g, src, flags, stats, w.groups, w.fail_list, 0);
         }
     }
     if (need_median) {
         const int count = g.p.flag_mode != RFI_FLAGS_INFERENCE ? 1 : 0;
-        if (!cluster) big_range_kernel<<<subs, kBigNT, big_range_smem(), st>>>(g, src, flags, stats, w.groups, nullptr, count);
+        if (!cluster) big_range_kernel<false><<<subs, kBigNT, big_range_smem(), st>>>(g, src, flags, stats, w.groups, nullptr, count);
         else if (count) big_count_kernel<<<subs, kBigNT, 0, st>>>(g, src, flags, stats, w.groups);
     }
     RFI_CUDA_TRY(cudaGetLastError());
@@ -992,13 +1057,14 @@ int big_write_patches(const rfi_plan_t* plan, const void* data, const uint8_t* f
     if (!workspace) { set_error("patch sizes above 128 need the workspace rfi_tile_stats was given"); return RFI_E_INVALID; }
     if (g.p.flag_mode == RFI_FLAGS_CUSTOM && !flags) { set_error("custom flag mode needs flags"); return RFI_E_INVALID; }
     const BigWs w = big_ws(plan, g, workspace);
-    const float* src = plan->dtype == RFI_C64 ? w.mag : static_cast<const float*>(data);
+    const bool cb = plan->dtype == RFI_C64 && !plan->magnitude;
+    const void* src = cb ? data : (plan->dtype == RFI_C64 ? static_cast<const void*>(w.mag) : data);
     const unsigned subs = (unsigned)(g.n_groups * g.n2);
     if (big_use_cluster(g)) {
-        auto kern = big_write_kernel<true>;
-        RFI_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_write_smem()));
+        auto kern = cb ? big_write_kernel<true, true> : big_write_kernel<true, false>;
+        RFI_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_write_smem(cb)));
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(subs); cfg.blockDim = dim3(kBigNT); cfg.dynamicSmemBytes = big_write_smem(); cfg.stream = st;
+        cfg.gridDim = dim3(subs); cfg.blockDim = dim3(kBigNT); cfg.dynamicSmemBytes = big_write_smem(cb); cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = (unsigned)g.n2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -1006,9 +1072,9 @@ int big_write_patches(const rfi_plan_t* plan, const void* data, const uint8_t* f
         const BigGroup* groups = w.groups;
         RFI_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, g, src, flags, stats, groups, dest_slot, images, labels));
     } else {
-        auto kern = big_write_kernel<false>;
-        RFI_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_write_smem()));
-        kern<<<subs, kBigNT, big_write_smem(), st>>>(g, src, flags, stats, w.groups, dest_slot, images, labels);
+        auto kern = cb ? big_write_kernel<false, true> : big_write_kernel<false, false>;
+        RFI_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_write_smem(cb)));
+        kern<<<subs, kBigNT, big_write_smem(cb), st>>>(g, src, flags, stats, w.groups, dest_slot, images, labels);
     }
     RFI_CUDA_TRY(cudaGetLastError());
     return RFI_OK;

@@ -652,7 +652,7 @@ extern "C" int rfi_statistics_shard_count(const uint8_t* flags, int64_t n, void*
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     RFI_CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * 32, st));
     if (mode == 1) {
-        const unsigned long long ones = ~0ull;
+        const unsigned long long ones = (unsigned long long)kGExcl;   // "no key above" (stays positive as int64 for the MIN all-reduce)
         RFI_CUDA_TRY(cudaMemcpyAsync(counts + 1, &ones, sizeof(ones), cudaMemcpyHostToDevice, st));
         RFI_CUDA_TRY(cudaMemcpyAsync(counts + 17, &ones, sizeof(ones), cudaMemcpyHostToDevice, st));
     }

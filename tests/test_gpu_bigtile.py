@@ -153,3 +153,44 @@ def test_p256_padded_views(native_lib, rot):
     ods, inter = _run_oracle(data, None, magnitude=True, **kw)
     _compare(ds, ods, inter, pre)
     assert (_routes(pre)["route"] & 3).all()
+
+
+@pytest.mark.parametrize("patch,shape", [(256, (512, 768)), (512, (1024, 512)), (1024, (1024, 1024))])
+@pytest.mark.parametrize("rot", [1, 4])
+def test_complex_branch_on_chip(native_lib, patch, shape, rot):
+    """Complex input + custom flags at P >= 256 (gradient / log-amplitude / phase channels,
+    preprocessor.py:562-606) through the big-tile kernels.  The last case is the reference's own production
+    call: 1024 x 1024 complex waterfalls at patch_size = 1024 (configs/data_generation/synthetic_train_4k.yaml:50,
+    synthetic_generator.py:93-105), where patchify is skipped (:261) and the patches are the rotated waterfalls."""
+    from rfi_toolbox_b200 import _native
+    data, mask = make_cube(n_bl=1, n_pol=2, channels=shape[0], times=shape[1], dtype=np.complex64, seed=81)
+    kw = dict(patch_size=patch, use_custom_flags=True, augmentation_rotations=rot, enable_augmentation=rot > 1)
+    pre, ds = _run_gpu(data, mask, **kw)
+    ods, inter = _run_oracle(data, mask, **kw)
+    _compare(ds, ods, inter, pre, label=f"complex branch P={patch} R={rot}")
+    import ctypes as C
+    from rfi_toolbox_b200.preprocessing.preprocessor import _DTYPE_CODE  # noqa: F401
+    plan = _native.RfiPlan(dtype=_native.RFI_C64, magnitude=0, n_waterfalls=2, channels=shape[0], times=shape[1], patch=patch,
+                           rotations=rot, stretch=0, norm_before=0, norm_after=0, flag_mode=_native.RFI_FLAGS_CUSTOM, sigma=5.0)
+    assert native_lib.rfi_plan_path(C.byref(plan)) == _native.RFI_PATH_BIG
+
+
+def test_complex_branch_on_chip_inference_and_patches(native_lib):
+    data, mask = make_cube(n_bl=1, n_pol=2, channels=512, times=512, dtype=np.complex64, seed=82)
+    kw = dict(patch_size=256, inference_mode=True)
+    pre, ds = _run_gpu(data, mask, **kw)
+    ods, inter = _run_oracle(data, mask, **kw)
+    _compare(ds, ods, inter, pre, label="complex branch P=256 inference")
+    assert np.array_equal(pre.patches.cpu().numpy(), inter["processed"][inter["order"]])
+
+
+@pytest.mark.parametrize("patch", [256, 512])
+def test_skipped_patchify_square_waterfall_on_chip(native_lib, patch):
+    """Real branch, waterfall of exactly P x P: the reference skips patchify (preprocessor.py:261); one tile
+    per waterfall through the big-tile kernels gives the same R rotated patches."""
+    data, _ = make_cube(n_bl=2, n_pol=2, channels=patch, times=patch, dtype=np.float32, seed=83)
+    kw = dict(patch_size=patch, stretch="SQRT", flag_sigma=4, use_custom_flags=False)
+    pre, ds = _run_gpu(data, None, **kw)
+    ods, inter = _run_oracle(data, None, **kw)
+    _compare(ds, ods, inter, pre, label=f"skipped patchify P={patch}")
+    assert ds.metadata["original_shapes"] is None
