@@ -503,6 +503,14 @@ RFI_DEVINL float big_eval(float a, const PlanDev& p, const BigMath& b, unsigned 
     }
 }
 
+// bulk asynchronous copy shared -> global (cp.async.bulk, SASS UBLKCP), as in the P = 128 writer (rfi_tiles.cu)
+RFI_DEVINL void big_bulk_store(void* dst_global, const void* src_shared, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\tcp.async.bulk.commit_group;"
+                 :: "l"(dst_global), "r"((uint32_t)__cvta_generic_to_shared(src_shared)), "r"(bytes) : "memory");
+}
+RFI_DEVINL void big_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+RFI_DEVINL void big_fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 constexpr int kBigLP = kP + 1;   // pitch of the log-amplitude tile: conflict-free rows AND columns
 constexpr int kBigFP = kP + 4;   // pitch of the transposed label tile (bytes)
 
@@ -833,6 +841,7 @@ big_write_kernel(BigGeom g, const void* __restrict__ src, const uint8_t* __restr
         for (int s = 0; s < STEPS; ++s) {
             const int orow = row0 + s;
             const float left0 = hleft[(rot == 1 || rot == 3) ? (kP - 1 - orow) : orow];
+            float o[Q][3];
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
                 const int ocol = lane + 32 * q;
@@ -842,33 +851,42 @@ big_write_kernel(BigGeom g, const void* __restrict__ src, const uint8_t* __restr
                 const float fd = (ocol > 0) ? c - Ls[at + db] : (has_left ? c - left0 : 0.f);
                 prev[q] = c;
                 const float gr = sqrt_fast(__fmaf_rn(td, td, fd * fd));
-                wstage[ocol * 3 + 0] = gs.ok ? __fmaf_rn(gr, ga, gb) : nb0;   // flat / all-NaN channel: exactly 0 before ImageNet
+                o[q][0] = gs.ok ? __fmaf_rn(gr, ga, gb) : nb0;   // flat / all-NaN channel: exactly 0 before ImageNet
                 if constexpr (kCplx) {   // fixed scale clip((L + 3) / 7, 0, 1) and the phase (preprocessor.py:588-604)
                     float u = (c - (-3.0f)) * (float)(1.0 / 7.0);
                     u = u < 0.f ? 0.f : (u > 1.f ? 1.f : u);  // np.clip keeps NaN
-                    wstage[ocol * 3 + 1] = __fmaf_rn(u, is1, nb1);
-                    wstage[ocol * 3 + 2] = Ph[at];
+                    o[q][1] = __fmaf_rn(u, is1, nb1);
+                    o[q][2] = Ph[at];
                 } else {
-                    wstage[ocol * 3 + 1] = ls.ok ? __fmaf_rn(c, la, lb) : nb1;
-                    wstage[ocol * 3 + 2] = nb2;
+                    o[q][1] = ls.ok ? __fmaf_rn(c, la, lb) : nb1;
+                    o[q][2] = nb2;
                 }
             }
+            // the staged row (1536 contiguous bytes of the output row) leaves as one bulk asynchronous copy;
+            // the previous row's copy has read the staging buffer by the time this row's values exist
+            if (lane == 0) big_bulk_wait_read();
             __syncwarp();
-            float4* dst = reinterpret_cast<float4*>(out_img + (size_t)orow * P * 3);
-            const float4* sv4 = reinterpret_cast<const float4*>(wstage);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) dst[lane + 32 * k] = sv4[lane + 32 * k];
+            for (int q = 0; q < Q; ++q) {
+                const int ocol = lane + 32 * q;
+                wstage[ocol * 3 + 0] = o[q][0];
+                wstage[ocol * 3 + 1] = o[q][1];
+                wstage[ocol * 3 + 2] = o[q][2];
+            }
+            big_fence_async_shared();
+            __syncwarp();
+            if (lane == 0) big_bulk_store(out_img + (size_t)orow * P * 3, wstage, 3 * kP * sizeof(float));
             if constexpr (rot >= 2) {
                 const unsigned char* lrow = FbT + ((rot == 2) ? orow : (kP - 1 - orow)) * FP;
                 reinterpret_cast<uint32_t*>(out_lab + (size_t)orow * P)[lane] = reinterpret_cast<const uint32_t*>(lrow)[lane];
             }
-            __syncwarp();
         }
     };
     emit(std::integral_constant<int, 0>{}, slot0, g0);
     emit(std::integral_constant<int, 1>{}, slot1, g1);
     emit(std::integral_constant<int, 2>{}, slot2, g0);
     emit(std::integral_constant<int, 3>{}, slot3, g3);
+    if (lane == 0) big_bulk_wait_read();  // shared memory must outlive the last copy's read
 }
 
 // ------------------------------------------------------------------------------------------

@@ -20,23 +20,20 @@
 //            select over the same shared-memory keys -- results are exact order statistics either way
 //   result   the FFI arithmetic of statistics.py:77-97 in float64, operation by operation (the
 //            build forbids FMA contraction), so the values equal the reference's Python floats
-#include "rfi_stats_mono.cuh"
+#include "rfi_select_keys.cuh"
 
 namespace rfi {
 
-constexpr int kPairNT = 512, kPairE = 32, kPairG = kPairE / 4, kPairSeg = kPairNT * kPairE;
-using PK = uint32_t;
-constexpr PK kPExcl = ~PK(0);
+constexpr int kPairNT = kSelNT, kPairE = 32, kPairG = kPairE / 4, kPairSeg = kPairNT * kPairE;
+constexpr PK kPExcl = kSelExcl;
 
 struct PairShared {
-    MonoShared<PK> ms;
+    SelShared sel;
     double pd[4][16];     // per-warp partials
     uint32_t pu[8][16];
     double rd[4];         // block totals
     uint32_t ru[8];
-    uint32_t cnt[4][16];  // radix-select counters, rotating (see RoundCounter)
-    uint32_t nxt[2];      // count(key <= prefix), min(key > prefix); the two maxima of the load pass
-    uint32_t ext[2];      // the two minima of the load pass
+    uint32_t ext[4];      // the two maxima and the two minima of the load pass
 };
 
 RFI_DEVINL uint4 pair_keys(const PK* skeys, int g) {
@@ -84,311 +81,25 @@ RFI_DEVINL void pair_totals(double (&d)[ND], uint32_t (&u)[NU], PairShared& sh) 
     for (int i = 0; i < NU; ++i) u[i] = sh.ru[i];
 }
 
-// ---- exact fallback: MSB-first radix select over the shared-memory keys, 4 bits per pass, 15
-// register counters per thread (no histogram atomics).  DEV: the key of a sample is its absolute
-// deviation from `centre`.  Returns the keys of ranks k1 <= k2 <= k1 + 1 among the valid keys.
-template <bool DEV>
-__device__ __noinline__ void pair_radix_select(const PK* __restrict__ skeys, uint32_t k1, uint32_t k2, float centre,
-                                               PK& o1, PK& o2, PairShared& sh) {
-    const int tid = threadIdx.x, lane = tid & 31;
-    auto key_of = [&](PK x) -> PK {
-        if (!DEV) return x;
-        return x == kPExcl ? kPExcl : to_key<float>(fabsf(from_key<float>(x) - centre));
-    };
-    if (tid < 64) sh.cnt[tid >> 4][tid & 15] = 0;
-    __syncthreads();
-    PK prefix = 0;
-    int round = 0;
-#pragma unroll 1
-    for (int shift = 28; shift >= 0; shift -= 4, ++round) {
-        uint32_t c[15];
-#pragma unroll
-        for (int t = 0; t < 15; ++t) c[t] = 0;
-#pragma unroll 2
-        for (int g = 0; g < kPairG; ++g) {
-            const uint4 q = pair_keys(skeys, g);
-            const PK k4[4] = {key_of(q.x), key_of(q.y), key_of(q.z), key_of(q.w)};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-#pragma unroll
-                for (int t = 0; t < 15; ++t) c[t] += (k4[i] < (prefix | ((PK)(t + 1) << shift))) ? 1u : 0u;
-            }
-        }
-        uint32_t* slot = sh.cnt[round & 3];
-#pragma unroll
-        for (int t = 0; t < 15; ++t) {
-            const uint32_t v = __reduce_add_sync(0xffffffffu, c[t]);
-            if (lane == 0 && v) atomicAdd(&slot[t], v);
-        }
-        __syncthreads();
-        int d = 0;
-#pragma unroll
-        for (int t = 0; t < 15; ++t) d += (slot[t] <= k1) ? 1 : 0;
-        prefix |= (PK)d << shift;
-        if (tid < 16) sh.cnt[(round + 2) & 3][tid] = 0;  // last read before the previous barrier
-    }
-    o1 = o2 = prefix;
-    if (k2 != k1) {  // rank k1 + 1: the same key if duplicates reach it, else the smallest key above
-        uint32_t cle = 0;
-        PK nxt = kPExcl;
-#pragma unroll 2
-        for (int g = 0; g < kPairG; ++g) {
-            const uint4 q = pair_keys(skeys, g);
-            const PK k4[4] = {key_of(q.x), key_of(q.y), key_of(q.z), key_of(q.w)};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                cle += (k4[i] <= prefix) ? 1u : 0u;
-                const PK y = k4[i] > prefix ? k4[i] : kPExcl;
-                nxt = y < nxt ? y : nxt;
-            }
-        }
-        cle = __reduce_add_sync(0xffffffffu, cle);
-        nxt = warp_min(nxt);
-        __syncthreads();
-        if (tid == 0) { sh.nxt[0] = 0; sh.nxt[1] = kPExcl; }
-        __syncthreads();
-        if (lane == 0) { atomicAdd(&sh.nxt[0], cle); atomicMin(&sh.nxt[1], nxt); }
-        __syncthreads();
-        if (k2 >= sh.nxt[0]) o2 = sh.nxt[1];
-    }
-    __syncthreads();
-}
-
-// ---- sorted 512-sample of the valid keys (one element per thread, stratified like phase 1's):
-// four warps sort 128 keys each in registers, every thread ranks one key in the other three runs.
-// `runs` is scratch (the candidate list).  Returns the number of valid samples (sorted first).
-RFI_DEVINL int pair_sort_sample(const PK* __restrict__ skeys, PK* runs, PK* samp) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int e_s = (((lane + warp * 3) & 7) << 2) | (((lane >> 3) + warp) & 3);
-    PK x = skeys[((size_t)(e_s >> 2) * kPairNT + tid) * 4 + (e_s & 3)];
-    runs[tid] = x;
-    const int nvalid = __syncthreads_count(x != kPExcl);
-    if (warp < 4) {
-        PK v[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) v[r] = runs[warp * 128 + r * 32 + lane];
-        warp_sort_regs<PK, 4>(v, lane);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) runs[warp * 128 + r * 32 + lane] = v[r];
-    }
-    __syncthreads();
-    const int run_id = tid >> 7;
-    x = runs[tid];
-    uint32_t rank = tid & 127;
-#pragma unroll
-    for (int o = 0; o < 4; ++o) {
-        if (o == run_id) continue;  // warp-uniform
-        const PK* run = runs + o * 128;
-        const bool incl = o < run_id;  // earlier runs win ties
-        uint32_t pos = 0;
-#pragma unroll
-        for (int step = 64; step > 0; step >>= 1) {
-            const PK y = run[pos + step - 1];
-            pos += (incl ? (y <= x) : (y < x)) ? step : 0;
-        }
-        const PK y = run[127];
-        pos += (pos == 127 && (incl ? (y <= x) : (y < x))) ? 1u : 0u;
-        rank += pos;
-    }
-    samp[rank] = x;
-    __syncthreads();
-    return nvalid;
-}
-
-// ---- two middle order statistics of the nv valid keys by a sampled bracket (one directional retry).
-// false = bracket missed / too many candidates: the caller runs the radix select.
-__device__ __noinline__ bool pair_sampled_median(const PK* __restrict__ skeys, PK* cand, const PK* samp,
-                                                 PairShared& shp, uint32_t nv, int sv, PK& v1k, PK& v2k) {
-    MonoShared<PK>& sh = shp.ms;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const uint32_t k1 = (nv - 1) >> 1, k2 = nv >> 1;
-    const int delta = (int)(kMonoSigma * 0.5f * sqrtf((float)sv)) + 2;
-    const int rho = (int)(((float)(2 * k1 + 1) * (float)sv) / (float)(2 * nv));
-    const int ilo = rho - delta, ihi = rho + delta + 1;
-    PK lo = ilo < 0 ? PK(0) : samp[ilo];
-    PK hi = ihi >= sv ? kPExcl - 1 : samp[ihi];
-    if (tid == 0) { sh.cursor = 0; sh.below = 0; }
-    __syncthreads();
-    uint32_t M = 0, B = 0;
-#pragma unroll 1
-    for (int attempt = 0;; ++attempt) {
-        const PK span = hi - lo;
-        uint32_t below = 0, mine = 0;
-#pragma unroll
-        for (int g = 0; g < kPairG; ++g) {
-            const uint4 q = pair_keys(skeys, g);
-            const PK k4[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                below += (k4[i] < lo) ? 1u : 0u;
-                mine += ((PK)(k4[i] - lo) <= span) ? 1u : 0u;
-            }
-        }
-        uint32_t incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        uint32_t base = 0;
-        const uint32_t wb = __reduce_add_sync(0xffffffffu, below);
-        if (lane == 31) { base = atomicAdd(&sh.cursor, incl); atomicAdd(&sh.below, wb); }
-        base = __shfl_sync(0xffffffffu, base, 31);
-        uint32_t at = base + incl - mine;
-        __syncthreads();
-        M = sh.cursor; B = sh.below;
-        const bool low = B > k1, high = k2 >= B + M;   // the target rank lies below / above the bracket
-        if (M > (uint32_t)kMonoCap || low || high) {
-            const bool dead = attempt == 1 || M > (uint32_t)kMonoCap || (low && lo == 0) || (high && hi >= kPExcl - 1);
-            __syncthreads();  // every thread has read the totals
-            if (dead) return false;
-            if (low) {
-                const int j = ilo - 2 * delta;
-                hi = lo - 1;
-                lo = j < 0 ? PK(0) : samp[j];
-            } else {
-                const int j = ihi + 2 * delta;
-                lo = hi + 1;
-                hi = j >= sv ? kPExcl - 1 : samp[j];
-            }
-            if (tid == 0) { sh.cursor = 0; sh.below = 0; }
-            __syncthreads();
-            continue;
-        }
-#pragma unroll
-        for (int g = 0; g < kPairG; ++g) {
-            const uint4 q = pair_keys(skeys, g);
-            const PK k4[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if ((PK)(k4[i] - lo) <= span) cand[at++] = k4[i];
-        }
-        break;
-    }
-    __syncthreads();
-    mono_resolve<PK, kPairNT>(cand, M, k1 - B, k2 - B, v1k, v2k, sh);
-    return true;
-}
-
-// ---- two middle order statistics of |x - c| over the valid keys: |x - c| is V-shaped in x, so the
-// r smallest deviations are a contiguous window of the sorted sample around c; an inner and an outer
-// window prove bounds for everything strictly inside / outside, only the candidates in between get
-// their exact deviation, and the answer is accepted only inside what was proven.
-__device__ __noinline__ bool pair_sampled_mad(const PK* __restrict__ skeys, PK* cand, const PK* samp,
-                                              PairShared& shp, uint32_t nv, int sv, float c, PK& r1k, PK& r2k) {
-    MonoShared<PK>& sh = shp.ms;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const uint32_t k1 = (nv - 1) >> 1, k2 = nv >> 1;
-    const int delta = (int)(kMonoSigma * 0.5f * sqrtf((float)sv)) + 2;
-    PK* dsamp = cand;  // [NT], free until the candidates are compacted
-    bool below_c = false;
-    if (tid < sv) {
-        const float ps = from_key<float>(samp[tid]);
-        below_c = ps < c;
-        dsamp[tid] = to_key<float>(fabsf(ps - c));
-    }
-    if (tid == 0) { sh.win[0] = sh.win[1] = sh.win[2] = sh.win[3] = -1; sh.acc[3] = 0; sh.cursor = 0; sh.below = 0; }
-    __syncthreads();
-    {
-        const uint32_t nb = __popc(__ballot_sync(0xffffffffu, below_c));
-        if (lane == 0 && nb) atomicAdd(&sh.acc[3], nb);
-    }
-    __syncthreads();
-    const int ju = (int)sh.acc[3];  // first sample on the upper arm (value >= c)
-    const int rho = (int)(((float)(2 * k1 + 1) * (float)sv) / (float)(2 * nv));
-    const int r_in = rho - delta, r_out = rho + delta + 2;  // samples inside the inner / outer window
-    if (r_in < 1 || r_out > sv - 1) { __syncthreads(); return false; }
-    for (int which = 0; which < 2; ++which) {
-        const int r = which == 0 ? r_in : r_out;
-        const int i = tid;
-        if (i + r <= sv) {
-            auto pred = [&](int s) {
-                if (s + r >= sv) return true;
-                return dsamp[s] <= dsamp[s + r] && (s + r) >= ju;
-            };
-            if (pred(i) && (i == 0 || !pred(i - 1))) { sh.win[which * 2] = i; sh.win[which * 2 + 1] = i + r - 1; }
-        }
-    }
-    __syncthreads();
-    int il = sh.win[0], iu = sh.win[1], il2 = sh.win[2], iu2 = sh.win[3];
-    if (il < 0 || il2 < 0) { __syncthreads(); return false; }
-    il2 = il2 < il ? il2 : il;
-    iu2 = iu2 > iu ? iu2 : iu;
-    if (!(il2 <= il && il < ju && ju <= iu && iu <= iu2 && il2 < ju)) { __syncthreads(); return false; }
-    const PK L1 = samp[il], U1 = samp[iu];
-    const PK L2 = il2 > 0 ? samp[il2 - 1] : PK(0);
-    const PK U2 = iu2 + 1 < sv ? samp[iu2 + 1] : kPExcl - 1;
-    const PK d_in = dsamp[il] > dsamp[iu] ? dsamp[il] : dsamp[iu];       // interior deviations <= this
-    const PK d_lo2 = il2 > 0 ? dsamp[il2 - 1] : kPExcl, d_up2 = iu2 + 1 < sv ? dsamp[iu2 + 1] : kPExcl;
-    const PK d_out = d_lo2 < d_up2 ? d_lo2 : d_up2;                      // exterior deviations >= this
-    __syncthreads();  // dsamp (= cand) is overwritten below
-    const PK span_all = U2 - L2;
-    const PK w_in = U1 > L1 ? U1 - L1 - 1 : PK(0);
-    uint32_t inside = 0, mine = 0;
-#pragma unroll
-    for (int g = 0; g < kPairG; ++g) {
-        const uint4 q = pair_keys(skeys, g);
-        const PK k4[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const bool in_all = (PK)(k4[i] - L2) <= span_all;
-            const bool interior = (PK)(k4[i] - L1 - 1) < w_in;
-            inside += interior ? 1u : 0u;
-            mine += (in_all && !interior) ? 1u : 0u;
-        }
-    }
-    uint32_t incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    uint32_t base = 0;
-    const uint32_t wb = __reduce_add_sync(0xffffffffu, inside);
-    if (lane == 31) { base = atomicAdd(&sh.cursor, incl); atomicAdd(&sh.below, wb); }
-    base = __shfl_sync(0xffffffffu, base, 31);
-    uint32_t at = base + incl - mine;
-    __syncthreads();
-    const uint32_t M = sh.cursor, B = sh.below;
-    if (M > (uint32_t)kMonoCap || B > k1 || k2 >= B + M) { __syncthreads(); return false; }
-#pragma unroll
-    for (int g = 0; g < kPairG; ++g) {
-        const uint4 q = pair_keys(skeys, g);
-        const PK k4[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const bool in_all = (PK)(k4[i] - L2) <= span_all;
-            const bool interior = (PK)(k4[i] - L1 - 1) < w_in;
-            if (in_all && !interior) cand[at++] = k4[i];
-        }
-    }
-    __syncthreads();
-    for (uint32_t i = tid; i < M; i += kPairNT) cand[i] = to_key<float>(fabsf(from_key<float>(cand[i]) - c));
-    __syncthreads();
-    mono_resolve<PK, kPairNT>(cand, M, k1 - B, k2 - B, r1k, r2k, sh);
-    return !(r1k < d_in || r2k > d_out);  // the answers must lie inside what the windows prove
-}
+struct PairKeys {   // all eight groups in shared memory, [g][thread][4]
+    const PK* skeys;
+    RFI_DEVINL uint4 load(int g) const { return *reinterpret_cast<const uint4*>(skeys + ((size_t)g * kPairNT + threadIdx.x) * 4); }
+    RFI_DEVINL PK load1(int g, int i) const { return skeys[((size_t)g * kPairNT + threadIdx.x) * 4 + i]; }
+};
 
 // median and MAD of the nv valid keys (nv >= 1, no NaN among them)
 __device__ __noinline__ void pair_median_mad(const PK* __restrict__ skeys, PK* cand, PK* samp, PairShared& sh,
                                              uint32_t nv, bool any_inf, float& med, float& mad) {
-    const uint32_t k1 = (nv - 1) >> 1, k2 = nv >> 1;
-    bool sampled = nv >= 64 && !any_inf;
-    int sv = 0;
-    if (sampled) {
-        sv = pair_sort_sample(skeys, cand, samp);
-        sampled = sv >= 64;
-    }
+    const PairKeys ka{skeys};
     PK a = 0, b = 0;
-    if (!(sampled && pair_sampled_median(skeys, cand, samp, sh, nv, sv, a, b)))
-        pair_radix_select<false>(skeys, k1, k2, 0.f, a, b, sh);
+    int sv = 0;
+    sel_median(ka, cand, samp, sh.sel, nv, !any_inf, a, b, sv);
     med = median_of_pair<float>(from_key<float>(a), from_key<float>(b), nv);
     if (is_inf(med) || is_nan(med)) {  // some |x - med| is inf - inf = NaN: np.median propagates it
         mad = Scalar<float>::nan();
         return;
     }
-    if (!(sampled && pair_sampled_mad(skeys, cand, samp, sh, nv, sv, med, a, b)))
-        pair_radix_select<true>(skeys, k1, k2, med, a, b, sh);
+    sel_mad(ka, cand, samp, sh.sel, nv, sv, med, a, b);
     mad = median_of_pair<float>(from_key<float>(a), from_key<float>(b), nv);
 }
 
@@ -488,17 +199,17 @@ pair_sweep_kernel(const void* __restrict__ data, const uint8_t* __restrict__ fla
     mx_cln = warp_max(mx_cln);
     mn_all = warp_min(mn_all);
     mn_cln = warp_min(mn_cln);
-    if (tid == 0) { sh.nxt[0] = 0; sh.nxt[1] = 0; sh.ext[0] = kPExcl; sh.ext[1] = kPExcl; }
+    if (tid == 0) { sh.ext[0] = 0; sh.ext[1] = 0; sh.ext[2] = kPExcl; sh.ext[3] = kPExcl; }
     __syncthreads();
     if ((tid & 31) == 0) {
-        atomicMax(&sh.nxt[0], mx_all); atomicMax(&sh.nxt[1], mx_cln);
-        atomicMin(&sh.ext[0], mn_all); atomicMin(&sh.ext[1], mn_cln);
+        atomicMax(&sh.ext[0], mx_all); atomicMax(&sh.ext[1], mx_cln);
+        atomicMin(&sh.ext[2], mn_all); atomicMin(&sh.ext[3], mn_cln);
     }
     double d2[4] = {s_all, s_cln, ss_all, ss_cln};
     uint32_t u6[6] = {nflag, tp, fp, fn, nan_all, nan_cln};
     pair_totals<4, 6>(d2, u6, sh);   // (its barriers also publish the extremes)
-    mx_all = sh.nxt[0]; mx_cln = sh.nxt[1];
-    mn_all = sh.ext[0]; mn_cln = sh.ext[1];
+    mx_all = sh.ext[0]; mx_cln = sh.ext[1];
+    mn_all = sh.ext[2]; mn_cln = sh.ext[3];
     nflag = u6[0]; tp = u6[1]; fp = u6[2]; fn = u6[3]; nan_all = u6[4]; nan_cln = u6[5];
     const uint32_t n_cln = n_all - nflag;
     // the load pass summed d = x - K: sum x = sum d + n K
