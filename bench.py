@@ -539,9 +539,14 @@ def run_ours(args):
     # DRAM bytes of one launch from the committed `ncu --set full` capture of this very workload
     # (profiles/traffic.json, written by scripts/ncu_summary.py); null for any other workload
     def committed_traffic(kname):
-        tj = ROOT / "profiles" / "traffic.json"
-        if tj.exists() and not args.baselines and args.workload in ("c2", "c5"):
-            return json.loads(tj.read_text()).get(kname, {}).get("dram_bytes_per_launch")
+        if args.baselines or args.workload not in ("c2", "c5"):
+            return None
+        for name in ("r02_traffic.json", "traffic.json"):   # the newest committed capture that holds this kernel
+            tj = ROOT / "profiles" / name
+            if tj.exists():
+                v = json.loads(tj.read_text()).get(kname, {}).get("dram_bytes_per_launch")
+                if v is not None:
+                    return v
         return None
     if km["fused"]:
         # single launch per step (tile_fused_kernel): the cube is read once (8 B / px), every kept patch

@@ -28,7 +28,7 @@ struct SelShared {
 // register counters per thread (no histogram atomics).  DEV: the key of a sample is its absolute
 // deviation from `centre`.  Returns the keys of ranks k1 <= k2 <= k1 + 1 among the valid keys.
 template <bool DEV, typename KA>
-__device__ __noinline__ void sel_radix(const KA& ka, uint32_t k1, uint32_t k2, float centre,
+__device__ __noinline__ void sel_radix(const KA ka, uint32_t k1, uint32_t k2, float centre,
                                                PK& o1, PK& o2, SelShared& sh) {
     const int tid = threadIdx.x, lane = tid & 31;
     auto key_of = [&](PK x) -> PK {
@@ -98,7 +98,7 @@ __device__ __noinline__ void sel_radix(const KA& ka, uint32_t k1, uint32_t k2, f
 // four warps sort 128 keys each in registers, every thread ranks one key in the other three runs.
 // `runs` is scratch (the candidate list).  Returns the number of valid samples (sorted first).
 template <typename KA>
-RFI_DEVINL int sel_sort_sample(const KA& ka, PK* runs, PK* samp) {
+RFI_DEVINL int sel_sort_sample(const KA ka, PK* runs, PK* samp) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int e_s = (((lane + warp * 3) & 7) << 2) | (((lane >> 3) + warp) & 3);
     PK x = ka.load1(e_s >> 2, e_s & 3);
@@ -139,7 +139,7 @@ RFI_DEVINL int sel_sort_sample(const KA& ka, PK* runs, PK* samp) {
 // ---- two middle order statistics of the nv valid keys by a sampled bracket (one directional retry).
 // false = bracket missed / too many candidates: the caller runs the radix select.
 template <typename KA>
-__device__ __noinline__ bool sel_sampled_median(const KA& ka, PK* cand, const PK* samp,
+__device__ __noinline__ bool sel_sampled_median(const KA ka, PK* cand, const PK* samp,
                                                  SelShared& shp, uint32_t nv, int sv, PK& v1k, PK& v2k) {
     MonoShared<PK>& sh = shp.ms;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -217,7 +217,7 @@ __device__ __noinline__ bool sel_sampled_median(const KA& ka, PK* cand, const PK
 // window prove bounds for everything strictly inside / outside, only the candidates in between get
 // their exact deviation, and the answer is accepted only inside what was proven.
 template <typename KA>
-__device__ __noinline__ bool sel_sampled_mad(const KA& ka, PK* cand, const PK* samp,
+__device__ __noinline__ bool sel_sampled_mad(const KA ka, PK* cand, const PK* samp,
                                               SelShared& shp, uint32_t nv, int sv, float c, PK& r1k, PK& r2k) {
     MonoShared<PK>& sh = shp.ms;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -315,7 +315,7 @@ __device__ __noinline__ bool sel_sampled_mad(const KA& ka, PK* cand, const PK* s
 // two middle order statistics of the nv valid keys: sampled bracket, radix select if it misses.
 // `sv` (out): valid samples of the sorted sample left in `samp` (0 = no sample was drawn), for sel_mad.
 template <typename KA>
-__device__ __noinline__ void sel_median(const KA& ka, PK* cand, PK* samp, SelShared& sh, uint32_t nv, bool sample_ok,
+__device__ __noinline__ void sel_median(const KA ka, PK* cand, PK* samp, SelShared& sh, uint32_t nv, bool sample_ok,
                                         PK& a, PK& b, int& sv) {
     const uint32_t k1 = (nv - 1) >> 1, k2 = nv >> 1;
     bool sampled = sample_ok && nv >= 64;
@@ -331,7 +331,7 @@ __device__ __noinline__ void sel_median(const KA& ka, PK* cand, PK* samp, SelSha
 
 // two middle order statistics of |x - c| over the nv valid keys (`samp`, `sv` from sel_median on the SAME keys)
 template <typename KA>
-__device__ __noinline__ void sel_mad(const KA& ka, PK* cand, const PK* samp, SelShared& sh, uint32_t nv, int sv, float c,
+__device__ __noinline__ void sel_mad(const KA ka, PK* cand, const PK* samp, SelShared& sh, uint32_t nv, int sv, float c,
                                      PK& a, PK& b) {
     const uint32_t k1 = (nv - 1) >> 1, k2 = nv >> 1;
     if (!(sv >= 64 && sel_sampled_mad(ka, cand, samp, sh, nv, sv, c, a, b)))

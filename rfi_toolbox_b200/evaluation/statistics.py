@@ -3,8 +3,18 @@
 `compute_statistics(data, flags=None)` and `compute_ffi(data, flags)` keep the reference's
 signatures, dict keys, Python-float results and edge cases (all-flagged / NaN guard,
 bool-only flags, ZeroDivisionError on constant data).  The |z| pass, the boolean gather,
-the moments and the exact median / MAD selections run on the GPU (`rfi_statistics`,
-csrc/rfi_stats.cu); the final FFI arithmetic is the reference's Python-float formula.
+the moments and the exact median / MAD selections run on the GPU (`rfi_statistics2`,
+csrc/rfi_gstats.cu: three passes over the cube for both sets; float64 input: csrc/rfi_stats.cu);
+the final FFI arithmetic is the reference's Python-float formula.
+
+Where the values can differ from the reference's (tolerance class, tests/test_gpu_metrics.py):
+  * median / MAD / max: bit-identical (exact order statistics in the data's precision);
+  * mean / std: float64 accumulation rounded once to the data's precision, where NumPy sums
+    pairwise IN float32 for float32 data -- equal to ~1e-7 of mean(|x|), not to the last bit;
+  * `flags` must have `data`'s number of elements (the reference's `data[~flags]` also accepts
+    lower-rank boolean masks); integer data raises TypeError (the reference promotes it).
+Extensions: `group=` (cube sharded over ranks by baseline), `*_batch` / `evaluate_pairs`
+(per-pair sweeps in one launch).
 """
 from __future__ import annotations
 
