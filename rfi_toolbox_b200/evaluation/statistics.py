@@ -12,7 +12,7 @@ Where the values can differ from the reference's (tolerance class, tests/test_gp
   * mean / std: float64 accumulation rounded once to the data's precision, where NumPy sums
     pairwise IN float32 for float32 data -- equal to ~1e-7 of mean(|x|), not to the last bit;
   * `flags` must have `data`'s number of elements (the reference's `data[~flags]` also accepts
-    lower-rank boolean masks); integer data raises TypeError (the reference promotes it).
+    lower-rank boolean masks); integer data is promoted to float64 as NumPy promotes it.
 Extensions: `group=` (cube sharded over ranks by baseline), `*_batch` / `evaluate_pairs`
 (per-pair sweeps in one launch).
 """
@@ -79,8 +79,10 @@ def _run_both(data, flags):
     device = _device_of(data, flags)
     require_cuda(device)
     d = as_device_tensor(data, device)
+    if d.dtype in (torch.uint8, torch.int8, torch.int16, torch.int32, torch.int64):
+        d = d.to(torch.float64)   # np.mean / np.median / np.std of integer data are float64
     if d.dtype not in _DTYPE_CODE:
-        raise TypeError(f"unsupported data dtype {d.dtype} (float32/64, complex64/128)")
+        raise TypeError(f"unsupported data dtype {d.dtype} (float32/64, complex64/128 or an integer type)")
     f = None
     if flags is not None:
         f = _flags_tensor(flags, device)

@@ -37,6 +37,7 @@ _DTYPE_CODE = {
     torch.float32: _native.RFI_F32, torch.float64: _native.RFI_F64,
     torch.complex64: _native.RFI_C64, torch.complex128: _native.RFI_C128,
 }
+_INT_DTYPES = (torch.uint8, torch.int8, torch.int16, torch.int32, torch.int64, torch.bool)
 _STRETCH_CODE = {None: _native.RFI_STRETCH_NONE, "SQRT": _native.RFI_STRETCH_SQRT,
                  "LOG10": _native.RFI_STRETCH_LOG10}
 
@@ -342,8 +343,14 @@ class Preprocessor:
         # kernel starting as soon as its chunk has landed (fast path); else one plain H2D copy
         host = as_host_tensor(self.data, pin=self._pin)
         data = host if host is not None else as_device_tensor(self.data, device, pin=self._pin)
+        if data.dtype in _INT_DTYPES:
+            # integer samples: NumPy promotes them to float64 at the first division / sqrt / log10 of the
+            # reference chain, and every later step runs in float64 -- same results as float64 input
+            data = data.to(torch.float64)
+            if host is not None:
+                host = data
         if data.dtype not in _DTYPE_CODE:
-            raise TypeError(f"unsupported data dtype {data.dtype}: float32/64 or complex64/128")
+            raise TypeError(f"unsupported data dtype {data.dtype}: float32/64, complex64/128 or an integer type")
         if self._compute_dtype == "float32" and data.dtype in (torch.float64, torch.complex128):
             # loader-shaped complex128 / float64 input (io/ms_loader.py:202-238) taken in as complex64 /
             # float32: uploaded (if on the host) and rounded baseline by baseline (`rfi_downcast`)

@@ -470,3 +470,20 @@ def test_loader_shaped_wide_input_taken_in_as_float32(native_lib, dtype, where):
         assert torch.equal(a.labels, b.labels) and torch.equal(a.images, b.images)
     with pytest.raises(ValueError):
         Preprocessor(data, None, compute_dtype="float16")
+
+
+def test_integer_input_is_promoted_like_numpy(native_lib):
+    """Integer samples: the reference's chain runs in float64 from the first division on; the CUDA path
+    converts up front and equals the oracle on the integer array."""
+    from rfi_toolbox_b200 import compute_statistics
+    rng = np.random.default_rng(8)
+    data = rng.integers(1, 200, (1, 2, 256, 256)).astype(np.int32)
+    data[0, 0, 40:44, :] += 5000
+    kw = dict(stretch="SQRT", flag_sigma=4, use_custom_flags=False)
+    pre, ds = _run_gpu(data, None, **kw)
+    ods, inter = _run_oracle(data, None, **kw)
+    _compare(ds, ods, inter, pre, label="int32 input")
+    got, want = compute_statistics(data[0, 0]), oracle.compute_statistics(data[0, 0])
+    for k in ("median", "mad", "count"):
+        assert got[k] == want[k]
+    assert got["mean"] == pytest.approx(want["mean"], rel=1e-12) and got["std"] == pytest.approx(want["std"], rel=1e-12)

@@ -194,3 +194,19 @@ def test_batch_writer_files_match_reference_format(tmp_path):
     meta = json.loads((tmp_path / "out" / "metadata.json").read_text())
     assert meta["num_samples"] == 13 and meta["num_batches"] == 4 and meta["samples_per_batch"] == 5
     assert meta["image_shape"] == [8, 8, 3] and meta["mask_shape"] == [8, 8]
+
+
+def test_order_preserving_key_decode_matches_device_convention():
+    """`evaluation.statistics._key_to_f32` (host side of the sharded radix select) inverts the device's
+    order-preserving key map (csrc/rfi_common.cuh to_key): ascending float order == ascending key order."""
+    from rfi_toolbox_b200.evaluation.statistics import _key_to_f32
+    rng = np.random.default_rng(0)
+    vals = np.concatenate([rng.normal(0, 1e3, 500), [0.0, -0.0, np.inf, -np.inf, 1e-45, -1e-45, 3.4e38, -3.4e38]]).astype(np.float32)
+    bits = vals.view(np.uint32).astype(np.uint64)
+    keys = np.where(bits >> 31 == 1, (~bits) & 0xffffffff, bits | 0x80000000)          # to_key
+    order = np.argsort(keys, kind="stable")
+    assert np.all(np.diff(vals[order].astype(np.float64)) >= 0)                          # keys sort like the values
+    for k, v in zip(keys, vals):
+        back = _key_to_f32(int(k))
+        assert back == v and np.signbit(back) == np.signbit(v)
+    assert np.isnan(_key_to_f32(0xffffffff))                                             # the excluded key decodes to NaN
