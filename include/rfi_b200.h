@@ -103,6 +103,10 @@ typedef struct rfi_tile_stat {
 #define RFI_TILE_RAW_THRESHOLDS 1 /* all samples >= +0 and finite after the stretch: every stage is
                                      monotone, so thr_lo / thr_hi were mapped back EXACTLY to the raw
                                      domain (raw_lo / raw_hi) and phase 2 labels without normalising */
+#define RFI_TILE_RAW_FILL 8       /* with RFI_TILE_RAW_THRESHOLDS, LOG10 tiles whose smallest samples stretch to -inf
+                                   * (exact-zero bandpass rows): a sample <= raw_zero IS the fill value `inf_fill`
+                                   * (flagged iff inf_fill lies outside [thr_lo, thr_hi]); raw_zero travels in
+                                   * `median_after`, which such a tile does not use (no second normalisation) */
 #define RFI_TILE_GENERAL 2        /* measured by the general kernel (negative, infinite or inf-filled
                                      samples, or a sampled bracket that missed) */
 

@@ -37,6 +37,25 @@ namespace rfi {
 // serves the normalisation median AND the flag centre; only the MAD needs a second select.
 // The shortcut is dropped (general selects) as soon as a tile has a negative, infinite or
 // inf-filled sample.
+// smallest key in [0, kTop] at which a prefix-true predicate fails (kTop if none), found by the calling WARP:
+// 32-ary search, one ballot per step.
+template <typename K, typename Pre>
+RFI_DEVINL K first_false_key(Pre pre, K kTop, int lane) {
+    if (!pre(K(0))) return K(0);
+    if (pre(kTop - 1)) return kTop;
+    K a = 0, b = kTop - 1;  // pre(a), !pre(b)
+    while (b - a > 1) {
+        const K step = (b - a + 32) / 33;
+        const K t = a + (K)(lane + 1) * step;
+        const bool good = (t < b) && pre(t);
+        const int n = __popc(__ballot_sync(0xffffffffu, good));  // monotone: a prefix of the lanes
+        const K na = a + (K)n * step, nb = a + (K)(n + 1) * step;
+        a = na;
+        b = nb < b ? nb : b;
+    }
+    return b;
+}
+
 template <int DT, int NT>
 __device__ __noinline__ void tile_stats_general(const PlanDev& p, const void* __restrict__ data,
                                                 const uint8_t* __restrict__ flags,
@@ -107,6 +126,11 @@ __device__ __noinline__ void tile_stats_general(const PlanDev& p, const void* __
     const bool real_branch = !In<DT>::cplx || p.magnitude;
     bool shortcut = false;  // (v1, v2) are the two middle order statistics of the current tile
     T v1 = T(0), v2 = T(0);
+    // LOG10 tile whose only irregularity is that its smallest samples stretch to -inf (exact-zero bandpass rows):
+    // raw thresholds are found below so that phase 2 can take its fast route (RFI_TILE_RAW_FILL)
+    [[maybe_unused]] bool zero_fill = false;
+    [[maybe_unused]] T zf_m = T(0);
+    [[maybe_unused]] bool zf_divide = false;
 
     if (real_branch) {
         // ---- normalise by the median (preprocessor.py:646-670), then stretch; +-inf := MAD of
@@ -155,6 +179,8 @@ __device__ __noinline__ void tile_stats_general(const PlanDev& p, const void* __
                         for (int e = 0; e < E; ++e) a[e] = stash[e * NT + threadIdx.x];
                     }
                     if (threadIdx.x == 0) st.inf_fill = (double)fill;
+                    zero_fill = sizeof(T) == 4 && p.stretch == RFI_STRETCH_LOG10 && !p.norm_after && nodd == 0 && nfin > 0;
+                    zf_m = m; zf_divide = divide;
                     const K kfill = to_key<T>(fill);
 #pragma unroll
                     for (int e = 0; e < E; ++e) a[e] = (a[e] == kPosInf || a[e] == kNegInf) ? kfill : a[e];
@@ -209,6 +235,60 @@ __device__ __noinline__ void tile_stats_general(const PlanDev& p, const void* __
             st.centre = (double)c; st.mad = (double)d;
             st.thr_lo = (double)lo; st.thr_hi = (double)hi;
             st.n_flagged = (int)nf;
+        }
+        if constexpr (sizeof(T) == 4) {
+            if (zero_fill) {   // uniform
+                // The samples that stretch to -inf are a PREFIX of the raw order (a / m == 0) and everything above
+                // is monotone: exact raw thresholds by 32-ary searches that evaluate the chain itself, as in the
+                // monotone kernel.  Phase 2 then labels a pixel by
+                //     a <= raw_zero ? (fill outside [thr_lo, thr_hi]) : (a > raw_hi || a < raw_lo)
+                // and takes its float32 log-amplitude chain; raw_zero travels in median_after (unused: no second
+                // normalisation on such a tile).
+                using RK = uint32_t;
+                constexpr RK kTop = 0x7f800000u;   // first raw bit pattern that is not a finite value
+                const int pmode = (zf_divide ? kProcDivM : 0) | kProcLog10;
+                auto proc = [&](RK b) { return proc_mode<float>(__uint_as_float(b), pmode, (float)zf_m, 0.f); };
+                __shared__ RK zsh[3];
+                if (warp == 0) {
+                    const RK ff = first_false_key<RK>([&](RK b) { return proc(b) == -Scalar<float>::inf(); }, kTop, lane);
+                    if (lane == 0) zsh[0] = ff;
+                }
+                __syncthreads();
+                const RK zff = zsh[0];   // first raw key whose processed value is finite
+                if (zff > 0 && zff < kTop) {
+                    if (warp < 2) {
+                        const bool want_hi = warp == 0;
+                        const float thr = want_hi ? (float)hi : (float)lo;
+                        RK ff;
+                        if (!(thr == thr)) ff = want_hi ? kTop : zff;   // NaN: nothing above / below
+                        else ff = first_false_key<RK>([&](RK b) { if (b < zff) return true; const float v = proc(b);
+                                                                  return want_hi ? (v <= thr) : !(v >= thr); }, kTop, lane);
+                        if (lane == 0) zsh[want_hi ? 2 : 1] = ff;
+                    }
+                    __syncthreads();
+                    if (threadIdx.x == 0) {
+                        const RK klo = zsh[1], khi_ff = zsh[2];   // first key with proc >= thr_lo; first with proc > thr_hi
+                        st.route |= RFI_TILE_RAW_THRESHOLDS | RFI_TILE_RAW_FILL;
+                        st.raw_lo = (double)__uint_as_float(klo);                                   // kTop -> +inf: every finite-part sample
+                        st.raw_hi = (double)__uint_as_float((khi_ff <= zff ? zff : khi_ff) - 1);    // kTop - 1: nothing
+                        st.median_after = (double)__uint_as_float(zff - 1);                          // raw_zero
+                    }
+                    // complex input: the scratch (this algorithm's stash until here) gets the tile's exact magnitudes
+                    // back, row-major as the monotone kernel leaves them, so that phase 2 reads 4 B / px there
+                    if constexpr (In<DT>::cplx) {
+                        if (stash_override != nullptr) {
+#pragma unroll 2
+                            for (int g = 0; g < G; ++g) {
+                                const size_t idx = origin + (size_t)(g * RS + warp) * p.times + lane * 4;
+                                T q[4];
+                                load4_mag_fast<DT>(data, idx, q);
+                                *reinterpret_cast<uint4*>(stash_override + ((size_t)g * NT + threadIdx.x) * 4) =
+                                    make_uint4(__float_as_uint(q[0]), __float_as_uint(q[1]), __float_as_uint(q[2]), __float_as_uint(q[3]));
+                            }
+                        }
+                    }
+                }
+            }
         }
     } else if (p.flag_mode == RFI_FLAGS_CUSTOM) {
         uint32_t nf = 0;
@@ -372,7 +452,13 @@ RFI_DEVINL void write_tile(const PlanDev& p, const void* __restrict__ data, cons
         const size_t src_origin = kMag ? 0 : origin;
         const size_t src_pitch = kMag ? (size_t)kP : (size_t)p.times;
         [[maybe_unused]] const float raw_lo = (float)st.raw_lo, raw_hi = (float)st.raw_hi;
-        [[maybe_unused]] const FastChain chain = make_fast_chain(p, (float)med_before, (float)med_after);
+        // RFI_TILE_RAW_FILL (LOG10 tile whose smallest samples stretch to -inf): a sample <= raw_zero IS the fill
+        // value; raw_zero travels in median_after, which such a tile does not use (tile_stats_general)
+        [[maybe_unused]] const bool has_fill = (st.route & RFI_TILE_RAW_FILL) != 0;
+        [[maybe_unused]] const float raw_zero = has_fill ? (float)st.median_after : -1.0f;
+        [[maybe_unused]] const unsigned char fill_flag = (has_fill && (((float)inf_fill > (float)thr_hi) || ((float)inf_fill < (float)thr_lo))) ? 1 : 0;
+        [[maybe_unused]] const float L_fill = log10_img(fabsf((float)inf_fill) + 1e-10f);
+        [[maybe_unused]] const FastChain chain = make_fast_chain(p, (float)med_before, has_fill ? 0.0f : (float)med_after);
         Raw cur[Q], nxt[Q];
 #pragma unroll
         for (int q = 0; q < Q; ++q)
@@ -402,6 +488,7 @@ RFI_DEVINL void write_tile(const PlanDev& p, const void* __restrict__ data, cons
                     ph = T(0);
                     if (p.flag_mode == RFI_FLAGS_MAD) f = ((a > (T)raw_hi) || (a < (T)raw_lo)) ? 1 : 0;
                     L = (T)fast_log_amp((float)a, chain);
+                    if (a <= (T)raw_zero) { f = fill_flag; L = (T)L_fill; }   // raw_zero = -1: never (a >= 0 or NaN)
                 } else {
                     if constexpr (!kMag) raw_to_mag<DT, kComplexBranch>(cur[q], a, ph);
                     T x = a;
@@ -469,7 +556,11 @@ RFI_DEVINL void write_tile(const PlanDev& p, const void* __restrict__ data, cons
         if (keys_in_smem) { pass_a_inplace(); done = true; }
     }
     if constexpr (DT == RFI_C64 && !kComplexBranch && !FUSED) {
-        if (fast_route && mag_scratch != nullptr) { pass_a(std::true_type{}, std::true_type{}); done = true; }
+        // (a tile measured by the general algorithm had its scratch used as that algorithm's stash; it is only
+        //  rewritten with the magnitudes for RFI_TILE_RAW_FILL tiles)
+        if (fast_route && mag_scratch != nullptr && (!(st.route & RFI_TILE_GENERAL) || (st.route & RFI_TILE_RAW_FILL))) {
+            pass_a(std::true_type{}, std::true_type{}); done = true;
+        }
     }
     if (!done) {
         if (fast_route) pass_a(std::true_type{}, std::false_type{});

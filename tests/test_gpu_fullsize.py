@@ -137,9 +137,11 @@ def test_config3_half_shard_properties(native_lib):
     st, _ = _check_properties(pre, ds, 128, 4, 32, 16, 22 * 4)
     assert ds.images.numel() > 2**32
     route = st["route"].reshape(22 * 4, 32, 16)
-    # pol 0 carries the exact-zero bandpass edge rows (log10(0) = -inf -> MAD fill): general route there,
+    # pol 0 carries the exact-zero bandpass edge rows (log10(0) = -inf -> MAD fill): general algorithm there,
+    # which also finds the raw thresholds for phase 2's fast route (GENERAL | RAW_THRESHOLDS | RAW_FILL = 11);
     # raw thresholds in the interior
-    assert (route[0::4, 0] & 2).all() and (route[0::4, 31] & 2).all() and (route[:, 1:31] & 1).mean() > 0.95
+    assert ((route[0::4, 0] & 11) == 11).all() and ((route[0::4, 31] & 11) == 11).all()
+    assert (route[:, 1:31] & 1).mean() > 0.95
     del ds, pre
     # the headline configuration's literal call against the oracle: one baseline at 4096 x 2048
     _slice_parity(cube, 5, kw, 128, max_label_mismatch=1e-4, label="configs[2] baseline 5")

@@ -92,9 +92,19 @@ def test_single_launch_log10_zero_rows(native_lib):
     pre, ds, _ = _run(data, True, True, **kw)
     assert pre.last_launch == "single"
     pre2, ds2, _ = _run(data, False, True, **kw)
-    assert torch.equal(ds.labels, ds2.labels) and torch.equal(ds.images, ds2.images)
+    assert torch.equal(ds.labels, ds2.labels)
+    # the tiles with exact-zero rows go through the general algorithm on both sides, which also finds their raw
+    # thresholds (route GENERAL | RAW_THRESHOLDS | RAW_FILL = 11) so that phase 2 takes its fast route
+    from tests.test_gpu_bigtile import _routes
+    s1, s2 = _routes(pre), _routes(pre2)
+    fill = (s2["route"] & 8) != 0
+    assert fill.sum() >= 4 and ((s2["route"][fill] & 11) == 11).all(), s2["route"]
+    for k in ("median_before", "inf_fill", "centre", "mad", "thr_lo", "thr_hi", "n_valid", "n_inf", "n_flagged", "raw_lo", "raw_hi"):
+        assert np.array_equal(s1[k], s2[k]), (k, s1[k][fill], s2[k][fill])
+    assert torch.equal(ds.images, ds2.images)
     ods, inter = _run_oracle(data, None, magnitude=True, **kw)
     _compare(ds, ods, inter, pre, exact_labels=False, max_label_mismatch=1e-4, label="single-launch LOG10")
+    _compare(ds2, ods, inter, pre2, exact_labels=False, max_label_mismatch=1e-4, label="two-launch LOG10")
 
 
 def test_single_launch_inference_mode(native_lib):
