@@ -447,21 +447,26 @@ def evaluate_pairs(data, pred, true, errors="raise"):
         rc = lib.rfi_pair_sweep(d.contiguous().data_ptr(), _DTYPE_CODE[d.dtype], f.contiguous().data_ptr(), t.data_ptr(),
                                 n, seg, None, res.data_ptr(), current_stream_ptr(device))
         _native.check(rc, "rfi_pair_sweep")
-        # results come down through a pinned buffer kept per device (48 B per pair)
+        # 88 B per pair = 11 x 8 B: transposed on the device (plumbing), so that every result column arrives
+        # contiguous in a pinned buffer kept per device
+        cols = res.view(torch.float64).view(n, 11).t().contiguous()
         key = device.index
         host = _PINNED_RESULTS.get(key)
-        if host is None or host.shape[0] < n:
-            host = _PINNED_RESULTS[key] = torch.empty((n, _PAIR_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True)
-        host[:n].copy_(res, non_blocking=True)
+        if host is None or host.numel() < 11 * n:
+            host = _PINNED_RESULTS[key] = torch.empty(11 * n, dtype=torch.float64, pin_memory=True)
+        host[: 11 * n].view(11, n).copy_(cols, non_blocking=True)
         torch.cuda.current_stream(device).synchronize()
-        r = host[:n].numpy().view(_PAIR_DTYPE).reshape(n)
+        c = host.numpy()[: 11 * n].reshape(11, n)
+        tail = np.ascontiguousarray(c[9:11]).view(np.uint32).reshape(2, n, 2)   # (tp, fp), (fn, status)
+        status = tail[1, :, 1].view(np.int32)
         if errors == "raise":
-            zero = r["status"] == 2
+            zero = status == 2
             if zero.any():
                 raise ZeroDivisionError(f"float division by zero (pair {int(np.flatnonzero(zero)[0])}: constant data)")
         # the ratios were formed on the device with the reference's float64 operations (metrics.py:25-152)
-        out = {k: np.ascontiguousarray(r[k]) for k in ("ffi", "mad_reduction", "std_reduction", "flagged_fraction",
-                                                       "iou", "precision", "recall", "f1", "dice")}
-        for k in ("tp", "fp", "fn"):
-            out[k] = r[k].astype(np.int64)
+        names = ("ffi", "mad_reduction", "std_reduction", "flagged_fraction", "iou", "precision", "recall", "f1", "dice")
+        out = {k: c[i].copy() for i, k in enumerate(names)}
+        out["tp"] = tail[0, :, 0].astype(np.int64)
+        out["fp"] = tail[0, :, 1].astype(np.int64)
+        out["fn"] = tail[1, :, 0].astype(np.int64)
     return out

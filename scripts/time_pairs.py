@@ -14,7 +14,7 @@ true = torch.rand((n, 128, 128), generator=g, device=dev) < 0.10
 pred = true ^ (torch.rand((n, 128, 128), generator=g, device=dev) < 0.02)
 data = torch.view_as_complex(torch.randn((n, 128, 128, 2), generator=g, device=dev))
 data = (data * (1.0 + 99.0 * true)).contiguous()
-res = torch.empty((n, 48), dtype=torch.uint8, device=dev)
+res = torch.empty((n, 88), dtype=torch.uint8, device=dev)   # rfi_pair_result_t
 st = torch.cuda.current_stream().cuda_stream
 def kern():
     _native.check(lib.rfi_pair_sweep(data.data_ptr(), _native.RFI_C64, pred.view(torch.uint8).data_ptr(), true.view(torch.uint8).data_ptr(),
@@ -33,4 +33,4 @@ t0 = time.perf_counter()
 for _ in range(reps):
     r = evaluate_pairs(data, pred, true, errors="nan")
 torch.cuda.synchronize()
-print(f"evaluate_pairs: {(time.perf_counter() - t0) / reps * 1e3:.3f} ms per sweep; status counts", np.unique(np.frombuffer(res.cpu().numpy().tobytes(), dtype=np.dtype([('f','f8',4),('c','u4',3),('s','i4')]))['s'], return_counts=True))
+print(f"evaluate_pairs: {(time.perf_counter() - t0) / reps * 1e3:.3f} ms per sweep; status counts", np.unique(np.frombuffer(res.cpu().numpy().tobytes(), dtype=np.dtype([('f','f8',9),('c','u4',3),('s','i4')]))['s'], return_counts=True))
