@@ -395,6 +395,7 @@ int rfi_processed_patches(const rfi_plan_t* plan, const void* data, const rfi_ti
 int rfi_downcast(const void* in, void* out, int dtype_in, int64_t n, void* stream);
 
 int rfi_selftest_sqrt_unit(unsigned long long* mismatches_dev, void* stream);
+int rfi_selftest_cabs_fast(unsigned long long* mismatches_dev, void* stream);
 
 const char* rfi_last_error_string(void);
 int rfi_abi_version(void);

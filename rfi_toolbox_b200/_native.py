@@ -105,6 +105,7 @@ SYMBOLS = {
     "rfi_processed_patches": (_I, [C.POINTER(RfiPlan), _VP, _VP, _VP, _I64, _VP, _VP]),
     "rfi_downcast": (_I, [_VP, _VP, _I, _I64, _VP]),
     "rfi_selftest_sqrt_unit": (_I, [_VP, _VP]),
+    "rfi_selftest_cabs_fast": (_I, [_VP, _VP]),
     "rfi_last_error_string": (C.c_char_p, []),
     "rfi_abi_version": (_I, []),
 }

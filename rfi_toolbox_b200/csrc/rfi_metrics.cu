@@ -395,7 +395,50 @@ __global__ void sqrt_unit_check_kernel(unsigned long long* mismatches) {
     const float t = __uint_as_float(0x3f800000u + i);
     if (__float_as_uint(sqrt_rn_unit(t)) != __float_as_uint(__fsqrt_rn(t))) atomicAdd(mismatches, 1ull);
 }
+// cabs_fast (own quotient sequence, one range test) vs cabs_np (div.rn, sqrt.rn) on 2^32 operand pairs:
+// a third with arbitrary bit patterns (zeros, denormals, inf, NaN, any exponent gap), a third with both
+// operands inside a few binades of each other at an arbitrary exponent, a third around the edges of the
+// fast range; and the quotient itself against div.rn wherever cabs depends on it (quotient >= 2^-13).
+__global__ void cabs_fast_check_kernel(unsigned long long* mismatches) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t bad = 0;
+    for (uint32_t it = 0; it < 4096u; ++it) {
+        uint32_t x = t * 4096u + it, y;
+        x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;   // two hashed words
+        y = x + 0x9e3779b9u; y ^= y >> 16; y *= 0x85ebca6bu; y ^= y >> 13; y *= 0xc2b2ae35u; y ^= y >> 16;
+        uint32_t a = x, b = y;
+        const uint32_t kind = it % 3u;
+        if (kind == 1u) {          // close exponents
+            const uint32_t e = 1u + (x >> 24) % 253u, gap = (y >> 28) & 15u;
+            a = (x & 0x807fffffu) | (e << 23);
+            b = (y & 0x807fffffu) | ((e > gap ? e - gap : 1u) << 23);
+        } else if (kind == 2u) {   // edges of the fast range: 2^-64 and 2^64 (+-2 binades)
+            const uint32_t e = ((x >> 24) & 1u ? 63u : 191u) - 2u + ((x >> 25) & 3u), gap = (y >> 27) & 31u;
+            a = (x & 0x807fffffu) | (e << 23);
+            b = (y & 0x807fffffu) | ((e > gap ? e - gap : 0u) << 23);
+        }
+        if (x & 0x00800000u) { const uint32_t s = a; a = b; b = s; }
+        const float re = __uint_as_float(a), im = __uint_as_float(b);
+        const float f = cabs_fast(re, im), g = cabs_np<float>(re, im);
+        const bool same = (f != f && g != g) || __float_as_uint(f) == __float_as_uint(g);
+        bad += same ? 0u : 1u;
+        const uint32_t u = a & 0x7fffffffu, v = b & 0x7fffffffu;
+        const uint32_t hb = u > v ? u : v, lb = u > v ? v : u;
+        if (hb - kCabsLoBits < kCabsSpanBits) {
+            const float hi = __uint_as_float(hb), lo = __uint_as_float(lb);
+            const float q = __fdiv_rn(lo, hi);
+            if (q >= 0.0001220703125f && __float_as_uint(div_rn_unit(lo, hi)) != __float_as_uint(q)) ++bad;
+        }
+    }
+    if (bad) atomicAdd(mismatches, (unsigned long long)bad);
+}
 }  // namespace rfi
+extern "C" int rfi_selftest_cabs_fast(unsigned long long* mismatches_dev, void* stream) {
+    using namespace rfi;
+    cabs_fast_check_kernel<<<(1u << 20) / 256, 256, 0, (cudaStream_t)stream>>>(mismatches_dev);
+    RFI_CUDA_TRY(cudaGetLastError());
+    return RFI_OK;
+}
 extern "C" int rfi_selftest_sqrt_unit(unsigned long long* mismatches_dev, void* stream) {
     using namespace rfi;
     sqrt_unit_check_kernel<<<((1u << 23) + 256) / 256 + 1, 256, 0, (cudaStream_t)stream>>>(mismatches_dev);

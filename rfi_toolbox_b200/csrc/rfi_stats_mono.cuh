@@ -27,6 +27,7 @@
 // thread-private global scratch (57 KB of shared memory per CTA, 3 CTAs / SM; see the kernel);
 // float64 keys: all in shared memory, 1 CTA / SM.
 #pragma once
+#include <type_traits>
 #include "rfi_tiles.cuh"
 
 namespace rfi {
@@ -118,12 +119,17 @@ RFI_DEVINL int proc_mode_of(const PlanDev& p, T m, T m2) {
     return ((p.norm_before && m > T(0)) ? kProcDivM : 0) | (p.stretch == RFI_STRETCH_SQRT ? kProcSqrt : 0) |
            (p.stretch == RFI_STRETCH_LOG10 ? kProcLog10 : 0) | ((p.norm_after && m2 > T(0)) ? kProcDivM2 : 0);
 }
+// The optional steps are real branches (pin() keeps the compiler from evaluating a division that
+// is not asked for and selecting afterwards: with its divisor 0 -- a median that is not in use --
+// such a division takes div.rn's out-of-line path, ~45 instructions per call for nothing).
+RFI_DEVINL void pin(float& a) { asm volatile("" : "+f"(a)); }
+RFI_DEVINL void pin(double& a) { asm volatile("" : "+d"(a)); }
 template <typename T>
 __device__ __noinline__ T proc_mode(T a, int mode, T m, T m2) {
-    if (mode & kProcDivM) a = a / m;
+    if (mode & kProcDivM) { pin(a); a = a / m; }
     if (mode & kProcSqrt) a = Scalar<T>::sqrt_rn(fabs_(a));
     else if (mode & kProcLog10) a = Scalar<T>::log10_(fabs_(a));
-    if (mode & kProcDivM2) a = a / m2;
+    if (mode & kProcDivM2) { pin(a); a = a / m2; }
     return a;
 }
 template <typename T>
@@ -134,45 +140,60 @@ RFI_DEVINL T proc_nofill(T a, const PlanDev& p, T m, T m2) { return proc_mode<T>
 // key range, refined on the answer's bucket until that bucket holds <= 64 keys (ranked by one
 // warp) or a single key value (duplicates); rank q2 = q1 + 1 is then either the same key or the
 // smallest key above it.
+// bucket shift of the <= 512-bucket histogram over a key range of the given width
+template <typename K>
+RFI_DEVINL int mono_bucket_shift(K width) {
+    constexpr int kBitsK = (int)sizeof(K) * 8;
+    const int wbits = width == 0 ? 0 : kBitsK - (sizeof(K) == 8 ? __clzll((long long)width) : __clz((int)width));
+    return wbits > 9 ? wbits - 9 : 0;
+}
+// `prebuilt`: the caller knows a range [klo_in, khi_in] that holds every key of the list and has ALREADY
+// filled sh.hist over it (bucket (x - klo_in) >> mono_bucket_shift(khi_in - klo_in)) while it wrote the list,
+// behind a barrier -- the list is then neither scanned for its range nor for the first histogram.
 template <typename K, int NT>
 RFI_DEVINL void mono_resolve(const K* cand, uint32_t M, uint32_t q1, uint32_t q2, K& out1, K& out2,
-                             MonoShared<K>& sh) {
+                             MonoShared<K>& sh, bool prebuilt = false, K klo_in = 0, K khi_in = 0) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int kBitsK = (int)sizeof(K) * 8;
-    // ---- range of the list
-    K lo = ~K(0), hi = 0;
-    for (uint32_t i = tid; i < M; i += NT) {
-        const K x = cand[i];
-        lo = x < lo ? x : lo;
-        hi = x > hi ? x : hi;
-    }
-    lo = warp_min(lo);
-    hi = warp_max(hi);
-    if (tid == 0) { sh.kmin = ~K(0); sh.kmax = 0; }
-    __syncthreads();
-    if (lane == 0) {
-        if (sizeof(K) == 8) {
-            atomicMin(reinterpret_cast<unsigned long long*>(&sh.kmin), (unsigned long long)lo);
-            atomicMax(reinterpret_cast<unsigned long long*>(&sh.kmax), (unsigned long long)hi);
-        } else {
-            atomicMin(reinterpret_cast<unsigned int*>(&sh.kmin), (unsigned int)lo);
-            atomicMax(reinterpret_cast<unsigned int*>(&sh.kmax), (unsigned int)hi);
+    K klo = klo_in, khi = khi_in;
+    if (!prebuilt) {
+        // ---- range of the list
+        K lo = ~K(0), hi = 0;
+        for (uint32_t i = tid; i < M; i += NT) {
+            const K x = cand[i];
+            lo = x < lo ? x : lo;
+            hi = x > hi ? x : hi;
         }
+        lo = warp_min(lo);
+        hi = warp_max(hi);
+        if (tid == 0) { sh.kmin = ~K(0); sh.kmax = 0; }
+        __syncthreads();
+        if (lane == 0) {
+            if (sizeof(K) == 8) {
+                atomicMin(reinterpret_cast<unsigned long long*>(&sh.kmin), (unsigned long long)lo);
+                atomicMax(reinterpret_cast<unsigned long long*>(&sh.kmax), (unsigned long long)hi);
+            } else {
+                atomicMin(reinterpret_cast<unsigned int*>(&sh.kmin), (unsigned int)lo);
+                atomicMax(reinterpret_cast<unsigned int*>(&sh.kmax), (unsigned int)hi);
+            }
+        }
+        __syncthreads();
+        klo = sh.kmin; khi = sh.kmax;
     }
-    __syncthreads();
-    K klo = sh.kmin, khi = sh.kmax;
     uint32_t q = q1;  // rank inside [klo, khi]
     K answer = klo;
     for (int iter = 0; iter < 8; ++iter) {  // <= ceil(64 / 9) refinements
         const K width = khi - klo;
-        const int wbits = width == 0 ? 0 : kBitsK - (sizeof(K) == 8 ? __clzll((long long)width) : __clz((int)width));
-        const int shf = wbits > 9 ? wbits - 9 : 0;  // <= 512 buckets
-        for (int b = tid; b < kMonoBuckets; b += NT) sh.hist[b] = 0;
-        if (tid == 0) sh.n_small_a = 0;
-        __syncthreads();
-        for (uint32_t i = tid; i < M; i += NT) {
-            const K x = cand[i];
-            if ((K)(x - klo) <= width) atomicAdd(&sh.hist[(uint32_t)((x - klo) >> shf)], 1u);
+        const int shf = mono_bucket_shift<K>(width);  // <= 512 buckets
+        if (prebuilt && iter == 0) {
+            if (tid == 0) sh.n_small_a = 0;
+        } else {
+            for (int b = tid; b < kMonoBuckets; b += NT) sh.hist[b] = 0;
+            if (tid == 0) sh.n_small_a = 0;
+            __syncthreads();
+            for (uint32_t i = tid; i < M; i += NT) {
+                const K x = cand[i];
+                if ((K)(x - klo) <= width) atomicAdd(&sh.hist[(uint32_t)((x - klo) >> shf)], 1u);
+            }
         }
         __syncthreads();
         if (warp == 0) {  // bucket of rank q
@@ -304,6 +325,37 @@ RFI_DEVINL bool mono_tile_stats(const PlanDev& p, const void* __restrict__ data,
         if (GK && g >= GS) return gk + ((size_t)g * NT + tid_) * 4;
         if (FUSED) return skeys + ((size_t)g * NT + (tid_ ^ (((g * RS + (tid_ >> 5)) >> 2) & 7))) * 4;
         return skeys + ((size_t)g * NT + tid_) * 4;
+    };
+
+    // the thread's keys whose bit is set in `marked` (bit e = element g * 4 + i), appended to cand[at ...] in
+    // ascending element order -- what a sweep over all 32 keys would append, at the cost of the marked ones
+    // only (one loop per address space, so that neither needs generic addressing)
+    // With HIST the keys are also counted into sh.hist (bucket (key - hlo) >> hshf): mono_resolve's first
+    // histogram, built on the way.
+    auto gather_marked = [&](uint32_t marked, uint32_t at, auto hist_tag, K hlo, int hshf) {
+        constexpr bool HIST = decltype(hist_tag)::value;
+        uint32_t ms = (GK && GS < G) ? (marked & ((1u << (4 * (GS < G ? GS : 0))) - 1u)) : marked;
+        while (ms) {
+            const int e = __ffs((int)ms) - 1;
+            ms &= ms - 1u;
+            const int g = e >> 2;
+            const K* q = FUSED ? skeys + ((size_t)g * NT + (tid_ ^ (((g * RS + (tid_ >> 5)) >> 2) & 7))) * 4
+                               : skeys + ((size_t)g * NT + tid_) * 4;
+            const K x = q[e & 3];
+            cand[at++] = x;
+            if constexpr (HIST) atomicAdd(&sh.hist[(uint32_t)((K)(x - hlo) >> hshf)], 1u);
+        }
+        if constexpr (GK && GS < G) {
+            uint32_t mg = marked >> (4 * GS);
+            const K* mine_g = gk + ((size_t)GS * NT + tid_) * 4;
+            while (mg) {
+                const int e = __ffs((int)mg) - 1;
+                mg &= mg - 1u;
+                const K x = mine_g[(size_t)(e >> 2) * NT * 4 + (e & 3)];
+                cand[at++] = x;
+                if constexpr (HIST) atomicAdd(&sh.hist[(uint32_t)((K)(x - hlo) >> hshf)], 1u);
+            }
+        }
     };
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -488,7 +540,10 @@ RFI_DEVINL bool mono_tile_stats(const PlanDev& p, const void* __restrict__ data,
 #pragma unroll 1
         for (int attempt = 0;; ++attempt) {
             const K span = hi - lo;
-            uint32_t below = 0, mine = 0;
+            for (int b = tid; b < kMonoBuckets; b += NT) sh.hist[b] = 0;   // filled by the compaction (barrier below)
+            // (the thread's keys inside the bracket are remembered as one bit each: the compaction below
+            //  visits only those -- about one key in seven -- instead of sweeping the tile again)
+            uint32_t below = 0, inmask = 0;
 #pragma unroll
             for (int g = 0; g < G; ++g) {
                 K k4[4];
@@ -502,9 +557,10 @@ RFI_DEVINL bool mono_tile_stats(const PlanDev& p, const void* __restrict__ data,
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     below += (k4[i] < lo) ? 1u : 0u;
-                    mine += ((K)(k4[i] - lo) <= span) ? 1u : 0u;
+                    if ((K)(k4[i] - lo) <= span) inmask |= 1u << (g * 4 + i);
                 }
             }
+            const uint32_t mine = __popc(inmask);
             // warp scan of `mine` -> write offsets; block totals through two shared atomics per warp
             uint32_t incl = mine;
 #pragma unroll
@@ -536,24 +592,11 @@ RFI_DEVINL bool mono_tile_stats(const PlanDev& p, const void* __restrict__ data,
                 __syncthreads();
                 continue;
             }
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                K k4[4];
-                if (sizeof(K) == 4) {
-                    const uint4 q = *reinterpret_cast<const uint4*>(kp(g));
-                    k4[0] = q.x; k4[1] = q.y; k4[2] = q.z; k4[3] = q.w;
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) k4[i] = kp(g)[i];
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if ((K)(k4[i] - lo) <= span) cand[at++] = k4[i];
-            }
+            gather_marked(inmask, at, std::true_type{}, lo, mono_bucket_shift<K>(span));
             break;
         }
         __syncthreads();
-        mono_resolve<K, NT>(cand, M, k1 - B, k2 - B, v1k, v2k, sh);
+        mono_resolve<K, NT>(cand, M, k1 - B, k2 - B, v1k, v2k, sh, true, lo, hi);
     }
 
     // ================= statistics in the processed domain =================
@@ -631,10 +674,15 @@ RFI_DEVINL bool mono_tile_stats(const PlanDev& p, const void* __restrict__ data,
         const K d_in = dsamp[il] > dsamp[iu] ? dsamp[il] : dsamp[iu];       // interior deviations <= this
         const K d_lo2 = il2 > 0 ? dsamp[il2 - 1] : kExcl, d_up2 = iu2 + 1 < sv ? dsamp[iu2 + 1] : kExcl;
         const K d_out = d_lo2 < d_up2 ? d_lo2 : d_up2;                      // exterior deviations >= this
+        // every candidate deviates at least / at most this much (each arm of the V is monotone): the range of
+        // the histogram that is filled while the deviations are formed
+        const K d_min = dsamp[il] < dsamp[iu] ? dsamp[il] : dsamp[iu];
+        const K d_max = d_lo2 > d_up2 ? d_lo2 : d_up2;
         __syncthreads();  // dsamp (= cand) is overwritten below
+        for (int b = tid; b < kMonoBuckets; b += NT) sh.hist[b] = 0;
         const K span_all = U2 - L2;
         const K w_in = U1 > L1 ? U1 - L1 - 1 : K(0);
-        uint32_t inside = 0, mine = 0;
+        uint32_t inside = 0, inmask = 0;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             K k4[4];
@@ -650,9 +698,10 @@ RFI_DEVINL bool mono_tile_stats(const PlanDev& p, const void* __restrict__ data,
                 const bool in_all = (K)(k4[i] - L2) <= span_all;
                 const bool interior = (K)(k4[i] - L1 - 1) < w_in;
                 inside += interior ? 1u : 0u;
-                mine += (in_all && !interior) ? 1u : 0u;
+                if (in_all && !interior) inmask |= 1u << (g * 4 + i);
             }
         }
+        const uint32_t mine = __popc(inmask);
         uint32_t incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -667,32 +716,22 @@ RFI_DEVINL bool mono_tile_stats(const PlanDev& p, const void* __restrict__ data,
         __syncthreads();
         const uint32_t M = sh.cursor, B = sh.below;
         if (M > (uint32_t)kMonoCap || B > k1 || k2 >= B + M) return give_up(9);
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-            K k4[4];
-            if (sizeof(K) == 4) {
-                const uint4 q = *reinterpret_cast<const uint4*>(kp(g));
-                k4[0] = q.x; k4[1] = q.y; k4[2] = q.z; k4[3] = q.w;
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) k4[i] = kp(g)[i];
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const bool in_all = (K)(k4[i] - L2) <= span_all;
-                const bool interior = (K)(k4[i] - L1 - 1) < w_in;
-                if (in_all && !interior) cand[at++] = k4[i];
-            }
-        }
+        gather_marked(inmask, at, std::false_type{}, K(0), 0);
         __syncthreads();
         // exact deviation of every candidate, in place
+        const K d_width = d_max - d_min;
+        const int d_shf = mono_bucket_shift<K>(d_width);
+        bool outside = false;
         for (uint32_t i = tid; i < M; i += NT) {
             const T ps = proc_mode<T>(raw_val<T>(cand[i]), pmode, m, m2);
-            cand[i] = to_key<T>(fabs_(ps - c));
+            const K dk = to_key<T>(fabs_(ps - c));
+            cand[i] = dk;
+            if ((K)(dk - d_min) <= d_width) atomicAdd(&sh.hist[(uint32_t)((K)(dk - d_min) >> d_shf)], 1u);
+            else outside = true;
         }
-        __syncthreads();
+        const bool hist_ok = __syncthreads_or(outside) == 0;   // (never seen to fail; the list is then scanned as before)
         K r1k, r2k;
-        mono_resolve<K, NT>(cand, M, k1 - B, k2 - B, r1k, r2k, sh);
+        mono_resolve<K, NT>(cand, M, k1 - B, k2 - B, r1k, r2k, sh, hist_ok, d_min, d_max);
         // the answers must lie inside what the windows prove
         if (r1k < d_in || r2k > d_out) return give_up(11);
         d = median_of_pair<T>(from_key<T>(r1k), from_key<T>(r2k), nv);
@@ -761,13 +800,32 @@ RFI_DEVINL bool mono_tile_stats(const PlanDev& p, const void* __restrict__ data,
         const K khi_cmp = (khi == kExcl) ? K(0) : khi;              // "everything": key > -1
         const bool all_hi = (khi == kExcl);
         uint32_t nf = 0;
+        if (nv == (uint32_t)(kP * kP) && !all_hi && klo <= khi) {
+            // the common tile (no excluded key, a proper interval): flagged iff outside [klo, khi], one
+            // unsigned comparison per key
+            const K span_ok = khi - klo;
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
+            for (int g = 0; g < G; ++g) {
+                K k4[4];
+                if (sizeof(K) == 4) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(kp(g));
+                    k4[0] = q.x; k4[1] = q.y; k4[2] = q.z; k4[3] = q.w;
+                } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const K x = kp(g)[i];
-                const bool f = (x != kExcl) && (all_hi || x > khi_cmp || x < klo);
-                nf += f ? 1u : 0u;
+                    for (int i = 0; i < 4; ++i) k4[i] = kp(g)[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) nf += ((K)(k4[i] - klo) > span_ok) ? 1u : 0u;
+            }
+        } else {
+#pragma unroll 1
+            for (int g = 0; g < G; ++g) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const K x = kp(g)[i];
+                    const bool f = (x != kExcl) && (all_hi || x > khi_cmp || x < klo);
+                    nf += f ? 1u : 0u;
+                }
             }
         }
         nf = __reduce_add_sync(0xffffffffu, nf);

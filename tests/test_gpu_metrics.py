@@ -84,6 +84,17 @@ def test_sqrt_unit_range_is_exact(native_lib):
     assert int(bad.item()) == 0
 
 
+def test_cabs_fast_is_exact(native_lib):
+    """The magnitude of the hot path (own quotient sequence, ONE range test per sample) equals the IEEE
+    chain np.abs runs (div.rn, fma, sqrt.rn, mul) on 2^32 operand pairs: arbitrary bit patterns, close
+    exponents, and the edges of the fast range."""
+    import torch
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    rc = native_lib.rfi_selftest_cabs_fast(bad.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    assert int(bad.item()) == 0
+
+
 def _pairs(n, dtype, seed=0, shape=(128, 128)):
     rng = np.random.default_rng(seed)
     truth = rng.random((n,) + shape) < 0.10
