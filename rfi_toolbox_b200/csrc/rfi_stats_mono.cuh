@@ -379,7 +379,7 @@ RFI_DEVINL bool mono_tile_stats(const PlanDev& p, const void* __restrict__ data,
     // patterns is >= the +inf pattern iff the tile holds a NaN, an inf or a negative value
     // (sign bit); only then does a second pass classify them.
     if (tid < 4) sh.acc[tid] = 0;
-    if (tid == 0) { sh.cursor = 0; sh.below = 0; sh.kmin = kExcl; sh.kmax = 0; }
+    if (tid == 0) { sh.cursor = 0; sh.below = 0; sh.kmin = kExcl; sh.kmax = 0; sh.fail = 0; }
     __syncthreads();
     // this thread's sample, element e_s = g * 4 + i of its 32 (row g * 16 + warp, column
     // 4 * lane + i): stratified so that every row AND every column of the tile gives 4 samples
@@ -614,12 +614,13 @@ RFI_DEVINL bool mono_tile_stats(const PlanDev& p, const void* __restrict__ data,
         }
     }
     const PlanDev pp = [&]() { PlanDev q = p; if (!real_branch) { q.norm_before = q.norm_after = 0; q.stretch = RFI_STRETCH_NONE; } return q; }();
-    // the extreme samples must stay finite through the chain (else: inf fill -> general kernel)
+    // the extreme samples must stay finite through the chain (else: inf fill -> general kernel): two lanes
+    // of warp 0 evaluate them in ONE call of the chain (not two calls by every warp), everybody reads the
+    // verdict behind the next barrier
     const int pmode = proc_mode_of<T>(pp, m, m2);
-    {
-        const T pmin = proc_mode<T>(raw_val<T>(tile_min), pmode, m, m2);
-        const T pmax = proc_mode<T>(raw_val<T>(tile_max), pmode, m, m2);
-        if (is_inf(pmin) || is_inf(pmax) || is_nan(pmin) || is_nan(pmax)) return give_up(5);
+    if (warp == 0) {
+        const T pe = proc_mode<T>(raw_val<T>(lane == 0 ? tile_min : tile_max), pmode, m, m2);
+        if (__any_sync(0xffffffffu, is_inf(pe) || is_nan(pe)) && lane == 0) sh.fail = 1;
     }
 
     T c = T(0), d = T(0), thr_lo = T(0), thr_hi = T(0);
@@ -637,6 +638,7 @@ RFI_DEVINL bool mono_tile_stats(const PlanDev& p, const void* __restrict__ data,
         }
         if (tid == 0) { sh.win[0] = sh.win[1] = sh.win[2] = sh.win[3] = -1; sh.acc[3] = 0; sh.cursor = 0; sh.below = 0; }
         __syncthreads();
+        if (sh.fail) return give_up(5);
         {
             const uint32_t nb = __popc(__ballot_sync(0xffffffffu, below_c));
             if (lane == 0 && nb) atomicAdd(&sh.acc[3], nb);
@@ -835,6 +837,8 @@ RFI_DEVINL bool mono_tile_stats(const PlanDev& p, const void* __restrict__ data,
         __syncthreads();
         nflag = sh.acc[3];
     } else if (p.flag_mode == RFI_FLAGS_CUSTOM) {
+        __syncthreads();
+        if (sh.fail) return give_up(5);
         uint32_t nf = 0;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
@@ -849,6 +853,9 @@ RFI_DEVINL bool mono_tile_stats(const PlanDev& p, const void* __restrict__ data,
         if (lane == 0 && nf) atomicAdd(&sh.acc[3], nf);
         __syncthreads();
         nflag = sh.acc[3];
+    } else {
+        __syncthreads();
+        if (sh.fail) return give_up(5);
     }
 
     if (tid == 0) {
