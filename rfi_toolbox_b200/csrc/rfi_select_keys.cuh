@@ -136,6 +136,20 @@ RFI_DEVINL int sel_sort_sample(const KA ka, PK* runs, PK* samp) {
     return nvalid;
 }
 
+// the thread's keys whose bit is set in `marked` (bit e = key i of group g, e = g * 4 + i), appended to
+// cand[at ...] in ascending element order; with HIST each is also counted into sh.hist (bucket
+// (key - hlo) >> hshf): mono_resolve's first histogram, built on the way
+template <bool HIST, typename KA>
+RFI_DEVINL void sel_gather_marked(const KA ka, uint32_t marked, PK* cand, uint32_t at, MonoShared<PK>& sh, PK hlo, int hshf) {
+    while (marked) {
+        const int e = __ffs((int)marked) - 1;
+        marked &= marked - 1u;
+        const PK x = ka.load1(e >> 2, e & 3);
+        cand[at++] = x;
+        if (HIST) atomicAdd(&sh.hist[(uint32_t)((PK)(x - hlo) >> hshf)], 1u);
+    }
+}
+
 // ---- two middle order statistics of the nv valid keys by a sampled bracket (one directional retry).
 // false = bracket missed / too many candidates: the caller runs the radix select.
 template <typename KA>
@@ -155,7 +169,8 @@ __device__ __noinline__ bool sel_sampled_median(const KA ka, PK* cand, const PK*
 #pragma unroll 1
     for (int attempt = 0;; ++attempt) {
         const PK span = hi - lo;
-        uint32_t below = 0, mine = 0;
+        for (int b = tid; b < kMonoBuckets; b += kSelNT) sh.hist[b] = 0;   // filled by the compaction (barrier below)
+        uint32_t below = 0, inmask = 0;   // one bit per key inside the bracket: the compaction visits only those
 #pragma unroll
         for (int g = 0; g < kSelG; ++g) {
             const uint4 q = ka.load(g);
@@ -163,9 +178,10 @@ __device__ __noinline__ bool sel_sampled_median(const KA ka, PK* cand, const PK*
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 below += (k4[i] < lo) ? 1u : 0u;
-                mine += ((PK)(k4[i] - lo) <= span) ? 1u : 0u;
+                if ((PK)(k4[i] - lo) <= span) inmask |= 1u << (g * 4 + i);
             }
         }
+        const uint32_t mine = __popc(inmask);
         uint32_t incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -197,18 +213,11 @@ __device__ __noinline__ bool sel_sampled_median(const KA ka, PK* cand, const PK*
             __syncthreads();
             continue;
         }
-#pragma unroll
-        for (int g = 0; g < kSelG; ++g) {
-            const uint4 q = ka.load(g);
-            const PK k4[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if ((PK)(k4[i] - lo) <= span) cand[at++] = k4[i];
-        }
+        sel_gather_marked<true>(ka, inmask, cand, at, sh, lo, mono_bucket_shift<PK>(span));
         break;
     }
     __syncthreads();
-    mono_resolve<PK, kSelNT>(cand, M, k1 - B, k2 - B, v1k, v2k, sh);
+    mono_resolve<PK, kSelNT>(cand, M, k1 - B, k2 - B, v1k, v2k, sh, true, lo, hi);
     return true;
 }
 
@@ -264,10 +273,15 @@ __device__ __noinline__ bool sel_sampled_mad(const KA ka, PK* cand, const PK* sa
     const PK d_in = dsamp[il] > dsamp[iu] ? dsamp[il] : dsamp[iu];       // interior deviations <= this
     const PK d_lo2 = il2 > 0 ? dsamp[il2 - 1] : kSelExcl, d_up2 = iu2 + 1 < sv ? dsamp[iu2 + 1] : kSelExcl;
     const PK d_out = d_lo2 < d_up2 ? d_lo2 : d_up2;                      // exterior deviations >= this
+    // every candidate deviates at least / at most this much (each arm of the V is monotone): the range of the
+    // histogram that is filled while the deviations are formed
+    const PK d_min = dsamp[il] < dsamp[iu] ? dsamp[il] : dsamp[iu];
+    const PK d_max = d_lo2 > d_up2 ? d_lo2 : d_up2;
     __syncthreads();  // dsamp (= cand) is overwritten below
+    for (int b = tid; b < kMonoBuckets; b += kSelNT) sh.hist[b] = 0;
     const PK span_all = U2 - L2;
     const PK w_in = U1 > L1 ? U1 - L1 - 1 : PK(0);
-    uint32_t inside = 0, mine = 0;
+    uint32_t inside = 0, inmask = 0;
 #pragma unroll
     for (int g = 0; g < kSelG; ++g) {
         const uint4 q = ka.load(g);
@@ -277,9 +291,10 @@ __device__ __noinline__ bool sel_sampled_mad(const KA ka, PK* cand, const PK* sa
             const bool in_all = (PK)(k4[i] - L2) <= span_all;
             const bool interior = (PK)(k4[i] - L1 - 1) < w_in;
             inside += interior ? 1u : 0u;
-            mine += (in_all && !interior) ? 1u : 0u;
+            if (in_all && !interior) inmask |= 1u << (g * 4 + i);
         }
     }
+    const uint32_t mine = __popc(inmask);
     uint32_t incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -294,21 +309,19 @@ __device__ __noinline__ bool sel_sampled_mad(const KA ka, PK* cand, const PK* sa
     __syncthreads();
     const uint32_t M = sh.cursor, B = sh.below;
     if (M > (uint32_t)kMonoCap || B > k1 || k2 >= B + M) { __syncthreads(); return false; }
-#pragma unroll
-    for (int g = 0; g < kSelG; ++g) {
-        const uint4 q = ka.load(g);
-        const PK k4[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const bool in_all = (PK)(k4[i] - L2) <= span_all;
-            const bool interior = (PK)(k4[i] - L1 - 1) < w_in;
-            if (in_all && !interior) cand[at++] = k4[i];
-        }
+    sel_gather_marked<false>(ka, inmask, cand, at, sh, PK(0), 0);
+    __syncthreads();
+    const PK d_width = d_max - d_min;
+    const int d_shf = mono_bucket_shift<PK>(d_width);
+    bool outside = false;
+    for (uint32_t i = tid; i < M; i += kSelNT) {
+        const PK dk = to_key<float>(fabsf(from_key<float>(cand[i]) - c));
+        cand[i] = dk;
+        if ((PK)(dk - d_min) <= d_width) atomicAdd(&sh.hist[(uint32_t)((PK)(dk - d_min) >> d_shf)], 1u);
+        else outside = true;
     }
-    __syncthreads();
-    for (uint32_t i = tid; i < M; i += kSelNT) cand[i] = to_key<float>(fabsf(from_key<float>(cand[i]) - c));
-    __syncthreads();
-    mono_resolve<PK, kSelNT>(cand, M, k1 - B, k2 - B, r1k, r2k, sh);
+    const bool hist_ok = __syncthreads_or(outside) == 0;   // (else the list is scanned for its range and histogram)
+    mono_resolve<PK, kSelNT>(cand, M, k1 - B, k2 - B, r1k, r2k, sh, hist_ok, d_min, d_max);
     return !(r1k < d_in || r2k > d_out);  // the answers must lie inside what the windows prove
 }
 
