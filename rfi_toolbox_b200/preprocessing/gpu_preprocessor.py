@@ -6,12 +6,16 @@ arguments and the same draws from the GLOBAL legacy generator (`np.random.choice
 `num_patches` truncates, then one `np.random.permutation`, :918-928).  The upstream method can only
 run its "whole waterfall" branch (:885-890): `_create_patches` returns one list (:972) where two
 values are unpacked (:893, :896).  Here the patchifying branch does what that code evidently
-intends -- non-overlapping P x P tiles, remainders dropped, data and flags tiled alike.
+intends -- non-overlapping P x P tiles, data and flags tiled alike -- with the reference's two
+treatments of dimensions that are not multiples of P (:954-970): `num_workers > 0` (the default) is
+its worker-pool route through `_patchify_single_waterfall` (:46-112), which zero-pads bottom / right
+(the padded samples are unflagged), `num_workers=0` its in-process `patchify` loop, which drops the
+remainders (logged).
 
 B200 differences: the tiles are counted and gathered on the device (`rfi_raw_tile_counts`,
 `rfi_raw_gather`; each kept tile written once at its final shuffled position); the result is a
 pair of device tensors `(N, H, W)` complex and `(N, H, W)` bool -- iterating them yields the
-per-patch arrays the reference returns as lists.  `num_workers` is accepted and ignored.
+per-patch arrays the reference returns as lists.  `num_workers` only selects pad / drop (above).
 """
 from __future__ import annotations
 
@@ -64,13 +68,27 @@ class GPUPreprocessor:
             if tuple(flags.shape) != tuple(data.shape):
                 raise ValueError(f"flags shape {tuple(flags.shape)} != data shape {tuple(data.shape)}")
             flags = (flags != 0).view(torch.uint8) if flags.dtype != torch.bool else flags.view(torch.uint8)
+        P_ = int(patch_size)
+        shape_in = (C_, T_)
+        if not (C_ <= P_ and T_ <= P_) and (C_ % P_ or T_ % P_):
+            if num_workers and num_workers > 0:   # :80-101: zero pad bottom / right (a short dimension up to P)
+                pr = (-C_) % P_ if C_ >= P_ else P_ - C_
+                pc = (-T_) % P_ if T_ >= P_ else P_ - T_
+                # (padded through the (re, im) view: constant padding of complex tensors is not implemented everywhere)
+                data = torch.view_as_complex(torch.nn.functional.pad(torch.view_as_real(data), (0, 0, 0, pc, 0, pr)))
+                if flags is not None:
+                    flags = torch.nn.functional.pad(flags, (0, pc, 0, pr))
+                C_, T_ = C_ + pr, T_ + pc
+            else:
+                logger.info("[GPUPreprocessor] num_workers=0: %d of %d samples per waterfall fall outside the "
+                            "%dx%d tiling and are dropped", C_ * T_ - (C_ // P_) * (T_ // P_) * P_ * P_, C_ * T_, P_, P_)
         rows, cols = C.c_int32(), C.c_int32()
         n_tiles = int(lib.rfi_raw_num_tiles(dtype, B * npol, C_, T_, int(patch_size), C.byref(rows), C.byref(cols)))
         if n_tiles < 0:
             _native.check(_native.RFI_E_INVALID, "rfi_raw_num_tiles")
         H, W = rows.value, cols.value
         if not (C_ <= patch_size and T_ <= patch_size):
-            self.original_shapes = [(C_, T_)] * (B * npol)
+            self.original_shapes = [shape_in] * (B * npol)
         with torch.cuda.device(device):
             stream = current_stream_ptr(device)
             fptr = flags.data_ptr() if flags is not None else None

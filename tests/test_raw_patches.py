@@ -31,9 +31,33 @@ def test_oracle_matches_reference_on_whole_waterfalls():
         Ref(np.abs(data))
 
 
+@pytest.mark.reference
+@pytest.mark.parametrize("shape,p", [((256, 384), 100), ((256, 384), 300), ((64, 96), 64), ((128, 128), 64)])
+def test_oracle_padding_is_the_reference_worker_route(shape, p):
+    """The tiling of the default route (num_workers > 0) is the reference's own `_patchify_single_waterfall`
+    (preprocessor.py:46-112), which runs stand-alone: zero pad bottom / right, then P x P tiles in row-major order."""
+    import sys
+    sys.path.insert(0, str(REFERENCE))
+    from rfi_toolbox.preprocessing.preprocessor import _patchify_single_waterfall
+    data, mask = make_cube(n_bl=1, n_pol=2, channels=shape[0], times=shape[1], dtype=np.complex64, seed=8)
+    np.random.seed(1)
+    op, om = oracle.create_raw_patches(data, mask, patch_size=p, remove_blank=False, num_workers=4)
+    order = np.random.RandomState(1).permutation(len(op))       # the one permutation the call drew
+    ref_p, ref_m = [], []
+    for w, m in zip(data[0], mask[0]):
+        ref_p += _patchify_single_waterfall(w, p)[0]
+        ref_m += _patchify_single_waterfall(m, p)[0]
+    assert len(ref_p) == len(op)
+    for k, src in enumerate(order):
+        assert np.array_equal(op[k], ref_p[src]) and np.array_equal(om[k], ref_m[src])
+
+
 CASES = [
     dict(patch_size=128), dict(patch_size=64, num_patches=7), dict(patch_size=128, remove_blank=False),
-    dict(patch_size=100),   # remainders dropped (patchify without padding)
+    dict(patch_size=100),                   # zero-padded to multiples of the patch size (the default route)
+    dict(patch_size=100, num_workers=0),    # remainders dropped (patchify without padding)
+    dict(patch_size=300),                   # one dimension below the patch size: padded up to it
+    dict(patch_size=300, num_workers=0, remove_blank=False),   # ... or no tile at all
     dict(patch_size=512),   # whole waterfalls
 ]
 
