@@ -543,7 +543,8 @@ RFI_DEVINL bool mono_tile_stats(const PlanDev& p, const void* __restrict__ data,
             for (int b = tid; b < kMonoBuckets; b += NT) sh.hist[b] = 0;   // filled by the compaction (barrier below)
             // (the thread's keys inside the bracket are remembered as one bit each: the compaction below
             //  visits only those -- about one key in seven -- instead of sweeping the tile again)
-            uint32_t below = 0, inmask = 0;
+            // (counts as population counts of bit masks: a select and half a three-input add per key and mask)
+            uint32_t lowmask = 0, inmask = 0;
 #pragma unroll
             for (int g = 0; g < G; ++g) {
                 K k4[4];
@@ -556,11 +557,11 @@ RFI_DEVINL bool mono_tile_stats(const PlanDev& p, const void* __restrict__ data,
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    below += (k4[i] < lo) ? 1u : 0u;
-                    if ((K)(k4[i] - lo) <= span) inmask |= 1u << (g * 4 + i);
+                    lowmask += (k4[i] < lo) ? (1u << (g * 4 + i)) : 0u;
+                    inmask += ((K)(k4[i] - lo) <= span) ? (1u << (g * 4 + i)) : 0u;
                 }
             }
-            const uint32_t mine = __popc(inmask);
+            const uint32_t below = __popc(lowmask), mine = __popc(inmask);
             // warp scan of `mine` -> write offsets; block totals through two shared atomics per warp
             uint32_t incl = mine;
 #pragma unroll
@@ -684,7 +685,7 @@ RFI_DEVINL bool mono_tile_stats(const PlanDev& p, const void* __restrict__ data,
         for (int b = tid; b < kMonoBuckets; b += NT) sh.hist[b] = 0;
         const K span_all = U2 - L2;
         const K w_in = U1 > L1 ? U1 - L1 - 1 : K(0);
-        uint32_t inside = 0, inmask = 0;
+        uint32_t allmask = 0, intmask = 0;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             K k4[4];
@@ -697,13 +698,12 @@ RFI_DEVINL bool mono_tile_stats(const PlanDev& p, const void* __restrict__ data,
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const bool in_all = (K)(k4[i] - L2) <= span_all;
-                const bool interior = (K)(k4[i] - L1 - 1) < w_in;
-                inside += interior ? 1u : 0u;
-                if (in_all && !interior) inmask |= 1u << (g * 4 + i);
+                allmask += ((K)(k4[i] - L2) <= span_all) ? (1u << (g * 4 + i)) : 0u;
+                intmask += ((K)(k4[i] - L1 - 1) < w_in) ? (1u << (g * 4 + i)) : 0u;
             }
         }
-        const uint32_t mine = __popc(inmask);
+        uint32_t inmask = allmask & ~intmask;   // inside the outer window, not strictly inside the inner one
+        const uint32_t inside = __popc(intmask), mine = __popc(inmask);
         uint32_t incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -806,6 +806,7 @@ RFI_DEVINL bool mono_tile_stats(const PlanDev& p, const void* __restrict__ data,
             // the common tile (no excluded key, a proper interval): flagged iff outside [klo, khi], one
             // unsigned comparison per key
             const K span_ok = khi - klo;
+            uint32_t outmask = 0;
 #pragma unroll
             for (int g = 0; g < G; ++g) {
                 K k4[4];
@@ -817,8 +818,9 @@ RFI_DEVINL bool mono_tile_stats(const PlanDev& p, const void* __restrict__ data,
                     for (int i = 0; i < 4; ++i) k4[i] = kp(g)[i];
                 }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) nf += ((K)(k4[i] - klo) > span_ok) ? 1u : 0u;
+                for (int i = 0; i < 4; ++i) outmask += ((K)(k4[i] - klo) > span_ok) ? (1u << (g * 4 + i)) : 0u;
             }
+            nf = __popc(outmask);
         } else {
 #pragma unroll 1
             for (int g = 0; g < G; ++g) {
