@@ -812,9 +812,15 @@ big_write_kernel(BigGeom g, const void* __restrict__ src, const uint8_t* __restr
     const float* hT = halo, *hB = halo + kP, *hL = halo + 2 * kP, *hR = halo + 3 * kP;
     float* wstage = stage + (size_t)warp * 3 * kP;
 
-    auto emit = [&](auto rot_tag, long long sl, const ChanScale<float>& gs) {
+    // kPlain / the constant third channel: as in the P = 128 writer (rfi_tiles.cu, write_tile)
+    if constexpr (!kCplx) {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) wstage[(lane + 32 * q) * 3 + 2] = nb2;
+        __syncwarp();
+    }
+    auto emit_as = [&](auto rot_tag, auto plain_tag, long long sl, const ChanScale<float>& gs) {
         constexpr int rot = decltype(rot_tag)::value;
-        if (sl < 0) return;  // uniform across the block
+        constexpr bool kPlain = decltype(plain_tag)::value;
         float* out_img = images + ((size_t)sl * PP + (size_t)br[rot] * kP * P + (size_t)bc[rot] * kP) * 3;
         [[maybe_unused]] unsigned char* out_lab = labels + (size_t)sl * PP + (size_t)br[rot] * kP * P + (size_t)bc[rot] * kP;
         constexpr int srow = (rot == 0) ? LP : (rot == 1) ? -LP : (rot == 2) ? 1 : -1;
@@ -851,14 +857,14 @@ big_write_kernel(BigGeom g, const void* __restrict__ src, const uint8_t* __restr
                 const float fd = (ocol > 0) ? c - Ls[at + db] : (has_left ? c - left0 : 0.f);
                 prev[q] = c;
                 const float gr = sqrt_fast(__fmaf_rn(td, td, fd * fd));
-                o[q][0] = gs.ok ? __fmaf_rn(gr, ga, gb) : nb0;   // flat / all-NaN channel: exactly 0 before ImageNet
+                o[q][0] = (kPlain || gs.ok) ? __fmaf_rn(gr, ga, gb) : nb0;   // flat / all-NaN channel: exactly 0 before ImageNet
                 if constexpr (kCplx) {   // fixed scale clip((L + 3) / 7, 0, 1) and the phase (preprocessor.py:588-604)
                     float u = (c - (-3.0f)) * (float)(1.0 / 7.0);
                     u = u < 0.f ? 0.f : (u > 1.f ? 1.f : u);  // np.clip keeps NaN
                     o[q][1] = __fmaf_rn(u, is1, nb1);
                     o[q][2] = Ph[at];
                 } else {
-                    o[q][1] = ls.ok ? __fmaf_rn(c, la, lb) : nb1;
+                    o[q][1] = (kPlain || ls.ok) ? __fmaf_rn(c, la, lb) : nb1;
                     o[q][2] = nb2;
                 }
             }
@@ -871,7 +877,7 @@ big_write_kernel(BigGeom g, const void* __restrict__ src, const uint8_t* __restr
                 const int ocol = lane + 32 * q;
                 wstage[ocol * 3 + 0] = o[q][0];
                 wstage[ocol * 3 + 1] = o[q][1];
-                wstage[ocol * 3 + 2] = o[q][2];
+                if constexpr (kCplx) wstage[ocol * 3 + 2] = o[q][2];
             }
             big_fence_async_shared();
             __syncwarp();
@@ -881,6 +887,11 @@ big_write_kernel(BigGeom g, const void* __restrict__ src, const uint8_t* __restr
                 reinterpret_cast<uint32_t*>(out_lab + (size_t)orow * P)[lane] = reinterpret_cast<const uint32_t*>(lrow)[lane];
             }
         }
+    };
+    auto emit = [&](auto rot_tag, long long sl, const ChanScale<float>& gs) {
+        if (sl < 0) return;  // uniform across the block
+        if (gs.ok && (kCplx || ls.ok)) emit_as(rot_tag, std::true_type{}, sl, gs);
+        else emit_as(rot_tag, std::false_type{}, sl, gs);
     };
     emit(std::integral_constant<int, 0>{}, slot0, g0);
     emit(std::integral_constant<int, 1>{}, slot1, g1);

@@ -615,9 +615,17 @@ RFI_DEVINL void write_tile(const PlanDev& p, const void* __restrict__ data, cons
     // row-derivative neighbour of row r is the centre value of row r-1, carried in registers;
     // only the centre and the column-derivative neighbour are read from shared memory.
     // `rot` is a compile-time constant so the source / neighbour index arithmetic folds away.
-    auto emit = [&](auto rot_tag, long long sl, const ChanScale<T>& gs) {
+    // kPlain: both min-max channels of this rotation have a proper range (every patch but a flat or all-NaN one), so
+    // the per-pixel selects that pin such a channel to exactly 0 are not compiled in -- the decision is uniform per
+    // call; the real branch's third channel is a constant, staged once per warp instead of once per row.
+    if constexpr (!kComplexBranch) {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) wstage[(lane + 32 * q) * 3 + 2] = nb2;
+        __syncwarp();
+    }
+    auto emit_as = [&](auto rot_tag, auto plain_tag, long long sl, const ChanScale<T>& gs) {
         constexpr int rot = decltype(rot_tag)::value;
-        if (sl < 0) return;  // uniform across the block
+        constexpr bool kPlain = decltype(plain_tag)::value;
         float* out_img = images + (size_t)sl * kP * kP * 3;
         [[maybe_unused]] unsigned char* out_lab = labels + (size_t)sl * kP * kP;
         // source element of output (orow, ocol): rot 0 (orow, ocol); rot 1 (127 - orow, ocol);
@@ -652,14 +660,14 @@ RFI_DEVINL void write_tile(const PlanDev& p, const void* __restrict__ data, cons
                 const T g = sqrt_fast(Scalar<T>::fma(td, td, fd * fd));
                 // ((g - lo) * inv) * (1/std) - mean/std, folded; a flat (or all-NaN) channel is exactly 0
                 // before the ImageNet step, whatever its pixels hold (preprocessor.py:157-163)
-                o[q][0] = gs.ok ? (float)Scalar<T>::fma(g, ga, gb) : nb0;
+                o[q][0] = (kPlain || gs.ok) ? (float)Scalar<T>::fma(g, ga, gb) : nb0;
                 if constexpr (kComplexBranch) {
                     T u = (c - T(-3.0)) * T(1.0 / 7.0);
                     u = u < T(0) ? T(0) : (u > T(1) ? T(1) : u);  // np.clip keeps NaN
                     o[q][1] = __fmaf_rn((float)u, is1, nb1);
                     o[q][2] = Ph[at];
                 } else {
-                    o[q][1] = ls.ok ? (float)Scalar<T>::fma(c, la, lb) : nb1;
+                    o[q][1] = (kPlain || ls.ok) ? (float)Scalar<T>::fma(c, la, lb) : nb1;
                     o[q][2] = nb2;
                 }
             }
@@ -671,7 +679,7 @@ RFI_DEVINL void write_tile(const PlanDev& p, const void* __restrict__ data, cons
                 const int ocol = lane + 32 * q;
                 wstage[ocol * 3 + 0] = o[q][0];
                 wstage[ocol * 3 + 1] = o[q][1];
-                wstage[ocol * 3 + 2] = o[q][2];
+                if constexpr (kComplexBranch) wstage[ocol * 3 + 2] = o[q][2];
             }
             fence_async_shared();
             __syncwarp();
@@ -682,6 +690,11 @@ RFI_DEVINL void write_tile(const PlanDev& p, const void* __restrict__ data, cons
                     reinterpret_cast<const uint32_t*>(lrow)[lane];
             }
         }
+    };
+    auto emit = [&](auto rot_tag, long long sl, const ChanScale<T>& gs) {
+        if (sl < 0) return;  // uniform across the block
+        if (gs.ok && (kComplexBranch || ls.ok)) emit_as(rot_tag, std::true_type{}, sl, gs);
+        else emit_as(rot_tag, std::false_type{}, sl, gs);
     };
     emit(std::integral_constant<int, 0>{}, slot0, g0);
     emit(std::integral_constant<int, 1>{}, slot1, g1);
