@@ -361,6 +361,10 @@ def _measure_workload(R, w, rank, peak, warmup, steps, torch):
     ds = Preprocessor(cube, None, magnitude=True).create_dataset(**kw)
     truth = ds.labels ^ (torch.rand(ds.labels.shape, device=R.dev) < 0.01).to(torch.uint8)
     del ds
+    # configs[2] holds 76 GB of patches per step: the temporaries above (23 GB of random floats, two masks) must not
+    # stay cached, or a timed step runs into the allocator's free-everything-and-retry path (tens of ms, and only
+    # when the side stream still holds the previous step's label block)
+    torch.cuda.empty_cache()
     res = R2.timed(cube, truth, warmup, steps, profile=True)
     sec = res["seconds"] / steps
     n_tiles = npix // (w["patch"] ** 2)
