@@ -545,7 +545,7 @@ def run_ours(args):
     def committed_traffic(kname):
         if args.baselines or args.workload not in ("c2", "c5"):
             return None
-        for name in ("r02_traffic.json", "traffic.json"):   # the newest committed capture that holds this kernel
+        for name in ("r02c_traffic.json", "r02_traffic.json", "traffic.json"):   # the newest committed capture that holds this kernel
             tj = ROOT / "profiles" / name
             if tj.exists():
                 v = json.loads(tj.read_text()).get(kname, {}).get("dram_bytes_per_launch")
