@@ -49,6 +49,17 @@ def _flags_tensor(flags, device):
     return as_device_tensor(flags, device).view(torch.uint8)
 
 
+def _match_flags(f, d):
+    """`data[~flags]` (statistics.py:33) with NumPy's boolean-mask rule: the mask covers the LEADING dimensions of
+    the data -- all of them, or fewer (a mask per baseline / per waterfall drops whole slices).  Returns a mask
+    with one byte per sample."""
+    if tuple(f.shape) == tuple(d.shape):
+        return f
+    if f.ndim < d.ndim and tuple(f.shape) == tuple(d.shape[:f.ndim]):
+        return f.reshape(f.shape + (1,) * (d.ndim - f.ndim)).expand(d.shape).contiguous()
+    raise IndexError(f"boolean index did not match indexed array: flags {tuple(f.shape)}, data {tuple(d.shape)}")
+
+
 def _run(data, flags):
     lib = _native.load()
     device = _device_of(data, flags)
@@ -58,9 +69,7 @@ def _run(data, flags):
         raise TypeError(f"unsupported data dtype {d.dtype} (float32/64, complex64/128)")
     f = None
     if flags is not None:
-        f = _flags_tensor(flags, device)
-        if f.numel() != d.numel():
-            raise IndexError("flags and data must have the same shape")
+        f = _match_flags(_flags_tensor(flags, device), d)
     with torch.cuda.device(device):
         ws = torch.empty(int(lib.rfi_statistics_workspace_bytes()), dtype=torch.uint8, device=device)
         out = torch.empty(C.sizeof(_native.RfiStats), dtype=torch.uint8, device=device)
@@ -85,9 +94,7 @@ def _run_both(data, flags):
         raise TypeError(f"unsupported data dtype {d.dtype} (float32/64, complex64/128 or an integer type)")
     f = None
     if flags is not None:
-        f = _flags_tensor(flags, device)
-        if f.numel() != d.numel():
-            raise IndexError("flags and data must have the same shape")
+        f = _match_flags(_flags_tensor(flags, device), d)
     code = _DTYPE_CODE[d.dtype]
     with torch.cuda.device(device):
         ws = torch.empty(int(lib.rfi_statistics2_workspace_bytes(code, d.numel())), dtype=torch.uint8, device=device)
@@ -129,9 +136,7 @@ def _run_both_sharded(data, flags, group):
         raise TypeError(f"sharded statistics: float32 / complex64 data (got {d.dtype})")
     f = None
     if flags is not None:
-        f = _flags_tensor(flags, device)
-        if f.numel() != d.numel():
-            raise IndexError("flags and data must have the same shape")
+        f = _match_flags(_flags_tensor(flags, device), d)
     g = None if group is True else group
     code, n_loc = _DTYPE_CODE[d.dtype], d.numel()
     fptr = f.data_ptr() if f is not None else None
@@ -218,7 +223,11 @@ def compute_statistics(data, flags=None, group=None):
     """statistics.py:16-56.  `group` (extension; `True` = the default process group): `data` / `flags` are this
     rank's baseline shard and the statistics are those of the whole cube -- every rank gets the same dict."""
     before, after, n = _run_both(data, flags) if group is None else _run_both_sharded(data, flags, group)
-    return _stats_dict(after if flags is not None else before, n, flags is not None)
+    out = _stats_dict(after if flags is not None else before, n, flags is not None)
+    if flags is not None and flags.ndim < data.ndim and out["count"]:
+        # a mask over the leading dimensions: `count` is len(data[~flags]) (:52), the number of SLICES kept
+        out["count"] //= int(np.prod(tuple(data.shape)[flags.ndim:]))
+    return out
 
 
 def _stats_dict(st, n, flagged):

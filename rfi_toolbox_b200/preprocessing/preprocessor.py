@@ -369,12 +369,16 @@ class Preprocessor:
                 raise ValueError(f"flags shape {tuple(self.flags.shape)} != data shape {tuple(data.shape)}")
         if custom and not inference_mode:
             flags = as_device_tensor(self.flags, device, pin=self._pin)
-            if flags.dtype == torch.bool:
+            if flags.dtype in (torch.bool, torch.uint8, torch.int8):
                 flags = flags.view(torch.uint8)
-            elif flags.dtype not in (torch.uint8, torch.int8):
-                raise TypeError(f"unsupported flags dtype {flags.dtype}: bool or uint8")
+            elif not flags.dtype.is_complex:
+                # labels are the reference's `np.array(patch_flags, dtype=np.uint8)` (:386): other integer and
+                # floating flag arrays (0 / 1 masks kept as int64 or float32) are cast the same way, once, on the
+                # device.  (Blank patches are found on the cast bytes: a value that is a non-zero multiple of 256,
+                # or a fraction inside (-1, 1), counts as unflagged there, while the reference's `.any()` sees it.)
+                flags = flags.to(torch.uint8)
             else:
-                flags = flags.view(torch.uint8)
+                raise TypeError(f"unsupported flags dtype {flags.dtype}")
 
         R = self._effective_rotations(enable_augmentation, augmentation_rotations)
         P = int(patch_size)

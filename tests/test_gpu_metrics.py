@@ -72,6 +72,14 @@ def test_statistics_and_ffi(native_lib, dtype):
     assert compute_ffi(data, np.ones_like(mask)) == oracle.compute_ffi(data, np.ones_like(mask))
     with pytest.raises(IndexError):
         compute_ffi(data, mask.astype(np.uint8))
+    # a mask over the leading dimensions only (NumPy's boolean-mask rule: whole waterfalls / baselines dropped)
+    for lead in (mask[:, :, 0, 0].copy(), mask[:, 0, 0, 0].copy()):
+        lead.flat[0] = True
+        lead.flat[-1] = False
+        a, b = compute_statistics(data, lead), oracle.compute_statistics(data, lead)
+        assert a["count"] == b["count"] and a["median"] == b["median"] and a["mad"] == b["mad"]
+    with pytest.raises(IndexError):
+        compute_statistics(data, mask[:, :, :, :-1])
 
 
 def test_sqrt_unit_range_is_exact(native_lib):

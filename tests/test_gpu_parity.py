@@ -148,6 +148,17 @@ def test_custom_flags(native_lib, dtype, rot):
     _compare(ds, ods, inter, pre)
 
 
+@pytest.mark.parametrize("fdtype", [np.int64, np.int32, np.float32])
+def test_custom_flags_of_other_dtypes(native_lib, fdtype):
+    """0 / 1 masks kept as int64 / int32 / float32 (the reference casts them with `np.array(..., dtype=np.uint8)`,
+    preprocessor.py:386) give the dataset a bool mask gives."""
+    data, mask = make_cube(dtype=np.float32, seed=9)
+    kw = dict(stretch="SQRT", use_custom_flags=True, augmentation_rotations=4)
+    pre, ds = _run_gpu(data, mask.astype(fdtype), **kw)
+    ods, inter = _run_oracle(data, mask.astype(fdtype), **kw)
+    _compare(ds, ods, inter, pre)
+
+
 def test_complex_magnitude_route(native_lib):
     """magnitude=True: complex64 in, |z| fused into the load, real branch (= reference fed np.abs)."""
     data, _ = make_cube(dtype=np.complex64, seed=13)
