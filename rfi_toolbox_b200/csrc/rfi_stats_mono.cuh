@@ -16,14 +16,15 @@
 // every column of the tile contributes 4 samples) is sorted (four warps sort 128 keys each in
 // registers, then every thread ranks one key in the other three runs); two sample ranks 3 sigma
 // either side of the target bracket it; one pass over the 16384 keys counts what lies below the
-// bracket and compacts the ~2300 keys inside it; the exact rank inside that list is resolved by
-// a 512-bucket linear histogram + one <= 64 element ranking.  All brackets are validated (the
+// bracket and marks the ~2300 keys inside it (one bit per key), the marked keys are then gathered
+// into a list while the 512-bucket linear histogram over the bracket is filled; the exact rank inside
+// that list is resolved from that histogram + one <= 64 element ranking.  All brackets are validated (the
 // answer must fall strictly inside what was proven), otherwise the tile is handed to the general
 // kernel (tile_stats_general, RFI_TILE_GENERAL), which then runs in the same CTA -- results are
 // exact either way.
 //
-// Cost: ~80 k warp instructions per tile instead of ~150 k for the 32-round register bisection
-// (a third of them the NumPy-exact |z|).  float32 keys: half in shared memory, half in a
+// Cost: ~64 k warp instructions per tile instead of ~150 k for the 32-round register bisection
+// (a fifth of them the load with the NumPy-exact |z|; DESIGN.md 5.1 lists where the rest goes).  float32 keys: half in shared memory, half in a
 // thread-private global scratch (57 KB of shared memory per CTA, 3 CTAs / SM; see the kernel);
 // float64 keys: all in shared memory, 1 CTA / SM.
 #pragma once
