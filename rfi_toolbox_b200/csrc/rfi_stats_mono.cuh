@@ -182,14 +182,18 @@ RFI_DEVINL void mono_resolve(const K* cand, uint32_t M, uint32_t q1, uint32_t q2
     }
     uint32_t q = q1;  // rank inside [klo, khi]
     K answer = klo;
+    // rank q1 + 1 is usually found on the way: when the answer's bucket is ranked directly and the answer is not
+    // the bucket's last key, the key ranked right behind it is the next order statistic
+    bool have_next = false;
+    K next_key = 0;
     for (int iter = 0; iter < 8; ++iter) {  // <= ceil(64 / 9) refinements
         const K width = khi - klo;
         const int shf = mono_bucket_shift<K>(width);  // <= 512 buckets
         if (prebuilt && iter == 0) {
-            if (tid == 0) sh.n_small_a = 0;
+            if (tid == 0) { sh.n_small_a = 0; sh.n_small_b = 0; }
         } else {
             for (int b = tid; b < kMonoBuckets; b += NT) sh.hist[b] = 0;
-            if (tid == 0) sh.n_small_a = 0;
+            if (tid == 0) { sh.n_small_a = 0; sh.n_small_b = 0; }
             __syncthreads();
             for (uint32_t i = tid; i < M; i += NT) {
                 const K x = cand[i];
@@ -239,9 +243,12 @@ RFI_DEVINL void mono_resolve(const K* cand, uint32_t M, uint32_t q1, uint32_t q2
                 rank += __shfl_xor_sync(0xffffffffu, rank, 2);
                 rank += __shfl_xor_sync(0xffffffffu, rank, 4);
                 if (sub == 0 && i < n && rank == want) sh.res1 = x;
+                if (sub == 0 && i < n && rank == want + 1) { sh.small_b[0] = x; sh.n_small_b = 1; }
             }
             __syncthreads();
             answer = sh.res1;
+            have_next = sh.n_small_b != 0;
+            next_key = sh.small_b[0];
             break;
         }
         klo = blo; khi = blo + bw; q -= pre;  // refine on the answer's bucket
@@ -249,7 +256,9 @@ RFI_DEVINL void mono_resolve(const K* cand, uint32_t M, uint32_t q1, uint32_t q2
     }
     out1 = answer;
     out2 = answer;
-    if (q2 != q1) {  // rank q1 + 1: the same key if duplicates reach it, else the smallest key above
+    if (q2 != q1 && have_next) {
+        out2 = next_key;
+    } else if (q2 != q1) {  // rank q1 + 1: the same key if duplicates reach it, else the smallest key above
         uint32_t cle = 0;
         K nxt = ~K(0);
         for (uint32_t i = tid; i < M; i += NT) {
